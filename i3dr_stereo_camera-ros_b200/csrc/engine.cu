@@ -1,0 +1,506 @@
+// Host side of the B200 SGBM engine and its C ABI (include/b200sgm.h).
+// Orchestrates the CUDA kernels that replace cv::StereoSGBM::compute as called by the reference's
+// MatcherOpenCVSGBM::forwardMatch (/root/reference/src/stereoMatcher/matcherOpenCVSGBM.cpp:17-44).
+// No CPU fallback exists: every result is produced by the kernels below.
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <cmath>
+#include <string>
+#include <vector>
+#include <mutex>
+#include <atomic>
+
+#include "../../include/b200sgm.h"
+#include "sgm_types.h"
+#include "k_cost.cuh"
+#include "k_path.cuh"
+#include "k_wta.cuh"
+#include "k_post.cuh"
+
+using namespace b200sgm;
+
+namespace {
+
+struct Lane {
+    cudaStream_t stream = nullptr;
+    cudaEvent_t done = nullptr;
+    bool busy = false;
+    // device buffers
+    uint8_t *left = nullptr, *right = nullptr;      // W x H, pitch = W
+    Feat *feat_l = nullptr, *feat_r = nullptr;      // W x H
+    uint16_t *C = nullptr, *S = nullptr;            // [H][W1][Dp]
+    uint32_t* disp2key = nullptr;                   // W x H
+    int16_t *disp_wta = nullptr, *disp_med = nullptr, *disp_out = nullptr;  // W x H
+    int *label = nullptr, *csize = nullptr;         // W x H
+    float *f32a = nullptr, *f32b = nullptr;         // W x H (dmat / depth / CV_32F disparity)
+    float4* points = nullptr;                       // W x H
+    uint32_t *block_count = nullptr, *total = nullptr;
+    uint32_t* h_total = nullptr;                    // pinned
+    // pending enqueue
+    int16_t* pending_disp = nullptr;
+};
+
+}  // namespace
+
+struct b200sgm_engine {
+    int device = 0;
+    int maxW = 0, maxH = 0, maxD = 0;
+    std::vector<Lane> lanes;
+    b200sgm_params raw{};
+    bool have_params = false;
+    std::string err;
+    std::atomic<uint64_t> launches{0};
+    int path = 0;
+    int num_sms = 148;
+    std::mutex mu;
+};
+
+namespace {
+
+#define CUDA_TRY(h, expr)                                                                      \
+    do {                                                                                       \
+        cudaError_t e__ = (expr);                                                              \
+        if (e__ != cudaSuccess) {                                                              \
+            (h)->err = std::string(#expr) + ": " + cudaGetErrorString(e__);                    \
+            return B200SGM_ECUDA;                                                              \
+        }                                                                                      \
+    } while (0)
+
+#define LAUNCH_CHECK(h)                                                                        \
+    do {                                                                                       \
+        (h)->launches++;                                                                       \
+        cudaError_t e__ = cudaGetLastError();                                                  \
+        if (e__ != cudaSuccess) {                                                              \
+            (h)->err = std::string("kernel launch at line ") + std::to_string(__LINE__) + ": " + cudaGetErrorString(e__); \
+            return B200SGM_ECUDA;                                                              \
+        }                                                                                      \
+    } while (0)
+
+int fail(b200sgm_engine* h, int code, const std::string& msg)
+{
+    h->err = msg;
+    return code;
+}
+
+int nreg_for(int D)
+{
+    int n = 1;
+    while (64 * n < D) n *= 2;
+    return n;
+}
+
+// A.1 parameter normalisation + geometry.  Returns 0 or B200SGM_EINVAL with h->err set.
+int make_eff(b200sgm_engine* h, int W, int H, Eff& e)
+{
+    if (!h->have_params) return fail(h, B200SGM_ESTATE, "b200sgm_set_params has not been called");
+    const b200sgm_params& p = h->raw;
+    if (p.numDisparities <= 0) return fail(h, B200SGM_EINVAL, "numDisparities must be > 0");
+    if (p.numDisparities > h->maxD) return fail(h, B200SGM_ESIZE, "numDisparities exceeds the engine's max_disparities");
+    if (W <= 0 || H <= 0) return fail(h, B200SGM_EINVAL, "empty image");
+    if (W > h->maxW || H > h->maxH) return fail(h, B200SGM_ESIZE, "image exceeds the engine's max size");
+    if (W > 65535) return fail(h, B200SGM_EINVAL, "width > 65535 unsupported");
+    e.W = W; e.H = H;
+    e.minD = p.minDisparity; e.D = p.numDisparities;
+    e.nreg = nreg_for(e.D);
+    if (e.nreg > 32) return fail(h, B200SGM_EINVAL, "numDisparities > 2048 unsupported");
+    e.Dp = (e.D + 2 * e.nreg - 1) / (2 * e.nreg) * (2 * e.nreg);
+    e.SW2 = (p.blockSize > 0 ? p.blockSize : 5) / 2;
+    e.P1 = p.P1 > 0 ? p.P1 : 2;
+    e.P2 = std::max(p.P2 > 0 ? p.P2 : 5, e.P1 + 1);
+    e.d12 = p.disp12MaxDiff > 0 ? p.disp12MaxDiff : 1;
+    e.uniq = p.uniquenessRatio >= 0 ? p.uniquenessRatio : 10;
+    e.ftzero = std::max(p.preFilterCap, 15) | 1;
+    e.speckleWin = p.speckleWindowSize; e.speckleRange = p.speckleRange;
+    e.mode = p.mode;
+    e.INVALID = (e.minD - 1) * 16;
+    const int maxD = e.minD + e.D;
+    e.minX1 = std::max(maxD, 0);
+    e.W1 = W + std::min(e.minD, 0) - e.minX1;
+    if (p.mode != B200SGM_MODE_SGBM && p.mode != B200SGM_MODE_HH) return fail(h, B200SGM_EINVAL, "mode must be MODE_SGBM (0) or MODE_HH (1)");
+    if (e.ftzero > 127) return fail(h, B200SGM_EINVAL, "preFilterCap > 127 unsupported (Sobel channel must fit uint8)");
+    // packed uint16 arithmetic contract: "infinity" + penalties must not wrap, output must fit int16
+    if (e.P1 + e.P2 > 32000) return fail(h, B200SGM_EINVAL, "P1 + P2 > 32000 unsupported");
+    if (maxD * 16 >= 32768 || e.INVALID < -32768) return fail(h, B200SGM_EINVAL, "disparity range does not fit CV_16S x16");
+    if (e.SW2 > 127) return fail(h, B200SGM_EINVAL, "blockSize > 255 unsupported");
+    return B200SGM_OK;
+}
+
+size_t cost_smem_bytes(int TX, int DCP, int SW2)
+{
+    const int bs = 2 * SW2 + 1;
+    return size_t((TX + 2 * SW2) + bs * TX + TX) * DCP * 4;
+}
+
+template <int N>
+int launch_paths_generic(b200sgm_engine* h, Lane& ln, const Eff& e, cudaStream_t st)
+{
+    static const int dirs_sgbm[5][2] = {{1, 0}, {1, 1}, {0, 1}, {-1, 1}, {-1, 0}};
+    static const int dirs_hh[8][2] = {{1, 0}, {1, 1}, {0, 1}, {-1, 1}, {-1, 0}, {-1, -1}, {0, -1}, {1, -1}};
+    const int nd = e.mode == B200SGM_MODE_HH ? 8 : 5;
+    for (int r = 0; r < nd; r++) {
+        PathGeom g;
+        g.W1 = e.W1; g.H = e.H; g.Dp = e.Dp;
+        g.dx = e.mode == B200SGM_MODE_HH ? dirs_hh[r][0] : dirs_sgbm[r][0];
+        g.dy = e.mode == B200SGM_MODE_HH ? dirs_hh[r][1] : dirs_sgbm[r][1];
+        g.nchains = chain_count(e.W1, e.H, g.dx, g.dy);
+        g.P1x2 = uint32_t(e.P1) * 0x10001u; g.P2x2 = uint32_t(e.P2) * 0x10001u;
+        const int wpb = 4;
+        dim3 grid((g.nchains + wpb - 1) / wpb), block(32 * wpb);
+        if (r == 0) k_path_generic<N, true><<<grid, block, 0, st>>>(ln.C, ln.S, g);
+        else k_path_generic<N, false><<<grid, block, 0, st>>>(ln.C, ln.S, g);
+        LAUNCH_CHECK(h);
+    }
+    WtaGeom wg{e.W, e.H, e.W1, e.minX1, e.minD, e.D, e.Dp, e.uniq, e.d12, e.INVALID};
+    const long long npix = (long long)e.W1 * e.H;
+    k_wta<N><<<unsigned((npix + 7) / 8), 256, 0, st>>>(ln.S, wg, ln.disp_wta, ln.disp2key);
+    LAUNCH_CHECK(h);
+    return B200SGM_OK;
+}
+
+int launch_aggregation(b200sgm_engine* h, Lane& ln, const Eff& e, cudaStream_t st)
+{
+    switch (e.nreg) {
+        case 1: return launch_paths_generic<1>(h, ln, e, st);
+        case 2: return launch_paths_generic<2>(h, ln, e, st);
+        case 4: return launch_paths_generic<4>(h, ln, e, st);
+        case 8: return launch_paths_generic<8>(h, ln, e, st);
+        case 16: return launch_paths_generic<16>(h, ln, e, st);
+        case 32: return launch_paths_generic<32>(h, ln, e, st);
+    }
+    return fail(h, B200SGM_EINVAL, "bad nreg");
+}
+
+// Enqueues the whole matcher on `st`: ln.left/right (device, pitch W) -> ln.disp_out (device, pitch W).
+int run_pipeline(b200sgm_engine* h, Lane& ln, const Eff& e, const uint8_t* dL, size_t lp, const uint8_t* dR, size_t rp, cudaStream_t st)
+{
+    const int W = e.W, H = e.H;
+    const int npix = W * H;
+    {
+        dim3 block(256), grid((W + 255) / 256, H);
+        k_prefilter<<<grid, block, 0, st>>>(dL, lp, W, H, e.ftzero, ln.feat_l);
+        LAUNCH_CHECK(h);
+        k_prefilter<<<grid, block, 0, st>>>(dR, rp, W, H, e.ftzero, ln.feat_r);
+        LAUNCH_CHECK(h);
+    }
+    CUDA_TRY(h, cudaMemsetAsync(ln.disp2key, 0xFF, size_t(npix) * 4, st));
+    k_fill16<<<(npix + 255) / 256, 256, 0, st>>>(ln.disp_wta, npix, int16_t(e.INVALID));
+    LAUNCH_CHECK(h);
+    if (e.W1 > 0) {
+        // cost volume
+        CostGeom cg;
+        cg.W = W; cg.H = H; cg.W1 = e.W1; cg.minX1 = e.minX1; cg.minD = e.minD; cg.D = e.D; cg.Dp = e.Dp; cg.SW2 = e.SW2;
+        int TX = 32, DCP = 32;
+        while (DCP * 2 > e.Dp && DCP > 1) DCP /= 2;
+        const size_t limit = 200 * 1024;
+        while (cost_smem_bytes(TX, DCP, e.SW2) > limit && TX > 4) TX /= 2;
+        while (cost_smem_bytes(TX, DCP, e.SW2) > limit && DCP > 4) DCP /= 2;
+        while (cost_smem_bytes(TX, DCP, e.SW2) > limit && TX > 1) TX /= 2;
+        if (cost_smem_bytes(TX, DCP, e.SW2) > limit) return fail(h, B200SGM_EINVAL, "blockSize too large for the cost kernel");
+        // every thread group must own at least one column: columns-per-group = ceil(TX / (256/DCP))
+        cg.TX = TX; cg.DCP = DCP; cg.RS = 64;
+        const size_t smem = cost_smem_bytes(TX, DCP, e.SW2);
+        CUDA_TRY(h, cudaFuncSetAttribute(k_cost_generic, cudaFuncAttributeMaxDynamicSharedMemorySize, int(limit)));
+        dim3 grid((e.W1 + TX - 1) / TX, (e.Dp / 2 + DCP - 1) / DCP, (H + cg.RS - 1) / cg.RS);
+        k_cost_generic<<<grid, 256, smem, st>>>(ln.feat_l, ln.feat_r, ln.C, cg);
+        LAUNCH_CHECK(h);
+        int rc = launch_aggregation(h, ln, e, st);
+        if (rc) return rc;
+        WtaGeom wg{e.W, e.H, e.W1, e.minX1, e.minD, e.D, e.Dp, e.uniq, e.d12, e.INVALID};
+        dim3 block(256), grid2((e.W1 + 255) / 256, H);
+        k_lrcheck<<<grid2, block, 0, st>>>(ln.disp_wta, ln.disp2key, wg);
+        LAUNCH_CHECK(h);
+    }
+    {
+        dim3 block(256), grid((W + 255) / 256, H);
+        k_median3<<<grid, block, 0, st>>>(ln.disp_wta, ln.disp_med, W, H);
+        LAUNCH_CHECK(h);
+    }
+    CUDA_TRY(h, cudaMemcpyAsync(ln.disp_out, ln.disp_med, size_t(npix) * 2, cudaMemcpyDeviceToDevice, st));
+    if (e.speckleWin > 0) {
+        const int maxDiff = 16 * e.speckleRange;
+        k_speckle_init<<<(npix + 255) / 256, 256, 0, st>>>(ln.disp_out, ln.label, ln.csize, npix, e.INVALID);
+        LAUNCH_CHECK(h);
+        dim3 block(256), grid((W + 255) / 256, H);
+        k_speckle_merge<<<grid, block, 0, st>>>(ln.disp_out, ln.label, W, H, e.INVALID, maxDiff);
+        LAUNCH_CHECK(h);
+        k_speckle_count<<<(npix + 255) / 256, 256, 0, st>>>(ln.label, ln.csize, npix);
+        LAUNCH_CHECK(h);
+        k_speckle_apply<<<(npix + 255) / 256, 256, 0, st>>>(ln.disp_out, ln.label, ln.csize, npix, e.INVALID, e.speckleWin);
+        LAUNCH_CHECK(h);
+    }
+    return B200SGM_OK;
+}
+
+int lane_check(b200sgm_engine* h, int lane)
+{
+    if (lane < 0 || lane >= int(h->lanes.size())) return fail(h, B200SGM_EINVAL, "lane out of range");
+    return B200SGM_OK;
+}
+
+void free_lane(Lane& ln)
+{
+    cudaFree(ln.left); cudaFree(ln.right); cudaFree(ln.feat_l); cudaFree(ln.feat_r); cudaFree(ln.C); cudaFree(ln.S);
+    cudaFree(ln.disp2key); cudaFree(ln.disp_wta); cudaFree(ln.disp_med); cudaFree(ln.disp_out); cudaFree(ln.label);
+    cudaFree(ln.csize); cudaFree(ln.f32a); cudaFree(ln.f32b); cudaFree(ln.points); cudaFree(ln.block_count); cudaFree(ln.total);
+    if (ln.h_total) cudaFreeHost(ln.h_total);
+    if (ln.done) cudaEventDestroy(ln.done);
+    if (ln.stream) cudaStreamDestroy(ln.stream);
+    ln = Lane();
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* b200sgm_version(void) { return "b200sgm 0.1 (sm_100a)"; }
+
+int b200sgm_create(int device, int max_width, int max_height, int max_disparities, int lanes, b200sgm_handle* out)
+{
+    if (!out) return B200SGM_EINVAL;
+    *out = nullptr;
+    if (max_width <= 0 || max_height <= 0 || max_disparities <= 0 || lanes <= 0 || lanes > 64) return B200SGM_EINVAL;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev) return B200SGM_ECUDA;
+    if (cudaSetDevice(device) != cudaSuccess) return B200SGM_ECUDA;
+    b200sgm_engine* h = new b200sgm_engine();
+    h->device = device; h->maxW = max_width; h->maxH = max_height; h->maxD = max_disparities;
+    cudaDeviceGetAttribute(&h->num_sms, cudaDevAttrMultiProcessorCount, device);
+    const size_t npix = size_t(max_width) * max_height;
+    const int nreg = nreg_for(max_disparities);
+    const size_t Dp = size_t((max_disparities + 2 * nreg - 1) / (2 * nreg) * (2 * nreg));
+    const size_t vol = npix * Dp * sizeof(uint16_t);
+    h->lanes.resize(lanes);
+    bool ok = true;
+    for (Lane& ln : h->lanes) {
+        ok = ok && cudaStreamCreateWithFlags(&ln.stream, cudaStreamNonBlocking) == cudaSuccess;
+        ok = ok && cudaEventCreateWithFlags(&ln.done, cudaEventDisableTiming) == cudaSuccess;
+        ok = ok && cudaMalloc(&ln.left, npix) == cudaSuccess && cudaMalloc(&ln.right, npix) == cudaSuccess;
+        ok = ok && cudaMalloc(&ln.feat_l, npix * sizeof(Feat)) == cudaSuccess && cudaMalloc(&ln.feat_r, npix * sizeof(Feat)) == cudaSuccess;
+        ok = ok && cudaMalloc(&ln.C, vol) == cudaSuccess && cudaMalloc(&ln.S, vol) == cudaSuccess;
+        ok = ok && cudaMalloc(&ln.disp2key, npix * 4) == cudaSuccess;
+        ok = ok && cudaMalloc(&ln.disp_wta, npix * 2) == cudaSuccess && cudaMalloc(&ln.disp_med, npix * 2) == cudaSuccess && cudaMalloc(&ln.disp_out, npix * 2) == cudaSuccess;
+        ok = ok && cudaMalloc(&ln.label, npix * 4) == cudaSuccess && cudaMalloc(&ln.csize, npix * 4) == cudaSuccess;
+        ok = ok && cudaMalloc(&ln.f32a, npix * 4) == cudaSuccess && cudaMalloc(&ln.f32b, npix * 4) == cudaSuccess;
+        ok = ok && cudaMalloc(&ln.points, npix * sizeof(float4)) == cudaSuccess;
+        ok = ok && cudaMalloc(&ln.block_count, ((npix + 255) / 256 + 1) * 4) == cudaSuccess && cudaMalloc(&ln.total, 4) == cudaSuccess;
+        ok = ok && cudaMallocHost(&ln.h_total, 4) == cudaSuccess;
+        if (!ok) break;
+    }
+    if (!ok) {
+        fprintf(stderr, "b200sgm_create: CUDA allocation failed: %s\n", cudaGetErrorString(cudaGetLastError()));
+        for (Lane& ln : h->lanes) free_lane(ln);
+        delete h;
+        return B200SGM_ECUDA;
+    }
+    *out = h;
+    return B200SGM_OK;
+}
+
+int b200sgm_destroy(b200sgm_handle h)
+{
+    if (!h) return B200SGM_EINVAL;
+    cudaSetDevice(h->device);
+    for (Lane& ln : h->lanes) { if (ln.stream) cudaStreamSynchronize(ln.stream); free_lane(ln); }
+    delete h;
+    return B200SGM_OK;
+}
+
+int b200sgm_set_params(b200sgm_handle h, const b200sgm_params* p)
+{
+    if (!h || !p) return B200SGM_EINVAL;
+    std::lock_guard<std::mutex> lk(h->mu);
+    h->raw = *p;
+    h->have_params = true;
+    return B200SGM_OK;
+}
+
+int b200sgm_get_effective_params(b200sgm_handle h, b200sgm_params* out)
+{
+    if (!h || !out) return B200SGM_EINVAL;
+    Eff e;
+    int rc = make_eff(h, 1, 1, e);
+    if (rc) return rc;
+    out->minDisparity = e.minD; out->numDisparities = e.D; out->blockSize = 2 * e.SW2 + 1; out->P1 = e.P1; out->P2 = e.P2;
+    out->disp12MaxDiff = e.d12; out->preFilterCap = e.ftzero; out->uniquenessRatio = e.uniq;
+    out->speckleWindowSize = e.speckleWin; out->speckleRange = e.speckleRange; out->mode = e.mode;
+    return B200SGM_OK;
+}
+
+int b200sgm_compute_device(b200sgm_handle h, int lane, const uint8_t* d_left, size_t left_stride, const uint8_t* d_right,
+                           size_t right_stride, int width, int height, int16_t* d_disp, size_t disp_stride, void* cuda_stream)
+{
+    if (!h || !d_left || !d_right || !d_disp) return B200SGM_EINVAL;
+    int rc = lane_check(h, lane);
+    if (rc) return rc;
+    Eff e;
+    rc = make_eff(h, width, height, e);
+    if (rc) return rc;
+    if (left_stride < size_t(width) || right_stride < size_t(width) || disp_stride < size_t(width) * 2) return fail(h, B200SGM_EINVAL, "stride smaller than a row");
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    Lane& ln = h->lanes[lane];
+    cudaStream_t st = cuda_stream ? cudaStream_t(cuda_stream) : ln.stream;
+    rc = run_pipeline(h, ln, e, d_left, left_stride, d_right, right_stride, st);
+    if (rc) return rc;
+    CUDA_TRY(h, cudaMemcpy2DAsync(d_disp, disp_stride, ln.disp_out, size_t(width) * 2, size_t(width) * 2, height, cudaMemcpyDeviceToDevice, st));
+    return B200SGM_OK;
+}
+
+int b200sgm_enqueue(b200sgm_handle h, int lane, const uint8_t* left, size_t left_stride, const uint8_t* right, size_t right_stride,
+                    int width, int height, int16_t* disp, size_t disp_stride)
+{
+    if (!h || !left || !right || !disp) return B200SGM_EINVAL;
+    int rc = lane_check(h, lane);
+    if (rc) return rc;
+    Eff e;
+    rc = make_eff(h, width, height, e);
+    if (rc) return rc;
+    if (left_stride < size_t(width) || right_stride < size_t(width) || disp_stride < size_t(width) * 2) return fail(h, B200SGM_EINVAL, "stride smaller than a row");
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    Lane& ln = h->lanes[lane];
+    if (ln.busy) return fail(h, B200SGM_ESTATE, "lane is busy: call b200sgm_wait first");
+    cudaStream_t st = ln.stream;
+    CUDA_TRY(h, cudaMemcpy2DAsync(ln.left, width, left, left_stride, width, height, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(h, cudaMemcpy2DAsync(ln.right, width, right, right_stride, width, height, cudaMemcpyHostToDevice, st));
+    rc = run_pipeline(h, ln, e, ln.left, width, ln.right, width, st);
+    if (rc) return rc;
+    CUDA_TRY(h, cudaMemcpy2DAsync(disp, disp_stride, ln.disp_out, size_t(width) * 2, size_t(width) * 2, height, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(h, cudaEventRecord(ln.done, st));
+    ln.busy = true;
+    return B200SGM_OK;
+}
+
+int b200sgm_wait(b200sgm_handle h, int lane)
+{
+    if (!h) return B200SGM_EINVAL;
+    int rc = lane_check(h, lane);
+    if (rc) return rc;
+    Lane& ln = h->lanes[lane];
+    if (!ln.busy) return fail(h, B200SGM_ESTATE, "lane is idle");
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    ln.busy = false;
+    CUDA_TRY(h, cudaEventSynchronize(ln.done));
+    CUDA_TRY(h, cudaGetLastError());
+    return B200SGM_OK;
+}
+
+int b200sgm_compute(b200sgm_handle h, const uint8_t* left, size_t left_stride, const uint8_t* right, size_t right_stride,
+                    int width, int height, int16_t* disp, size_t disp_stride)
+{
+    int rc = b200sgm_enqueue(h, 0, left, left_stride, right, right_stride, width, height, disp, disp_stride);
+    if (rc) return rc;
+    return b200sgm_wait(h, 0);
+}
+
+int b200sgm_compute_f32(b200sgm_handle h, const uint8_t* left, size_t left_stride, const uint8_t* right, size_t right_stride,
+                        int width, int height, float* disp32, size_t disp_stride)
+{
+    if (!h || !left || !right || !disp32) return B200SGM_EINVAL;
+    Eff e;
+    int rc = make_eff(h, width, height, e);
+    if (rc) return rc;
+    if (left_stride < size_t(width) || right_stride < size_t(width) || disp_stride < size_t(width) * 4) return fail(h, B200SGM_EINVAL, "stride smaller than a row");
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    Lane& ln = h->lanes[0];
+    if (ln.busy) return fail(h, B200SGM_ESTATE, "lane 0 is busy");
+    cudaStream_t st = ln.stream;
+    CUDA_TRY(h, cudaMemcpy2DAsync(ln.left, width, left, left_stride, width, height, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(h, cudaMemcpy2DAsync(ln.right, width, right, right_stride, width, height, cudaMemcpyHostToDevice, st));
+    rc = run_pipeline(h, ln, e, ln.left, width, ln.right, width, st);
+    if (rc) return rc;
+    const int npix = width * height;
+    k_to_f32<<<(npix + 255) / 256, 256, 0, st>>>(ln.disp_out, ln.f32a, npix);
+    LAUNCH_CHECK(h);
+    CUDA_TRY(h, cudaMemcpy2DAsync(disp32, disp_stride, ln.f32a, size_t(width) * 4, size_t(width) * 4, height, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(h, cudaStreamSynchronize(st));
+    return B200SGM_OK;
+}
+
+int b200sgm_compute_xyz(b200sgm_handle h, const uint8_t* left, size_t left_stride, const uint8_t* right, size_t right_stride,
+                        int width, int height, const b200sgm_reproject* rp, int16_t* disp, size_t disp_stride, float* dmat,
+                        float* depth, b200sgm_point* points, uint32_t* count)
+{
+    if (!h || !left || !right || !rp) return B200SGM_EINVAL;
+    if (points && !count) return B200SGM_EINVAL;
+    Eff e;
+    int rc = make_eff(h, width, height, e);
+    if (rc) return rc;
+    if (left_stride < size_t(width) || right_stride < size_t(width) || (disp && disp_stride < size_t(width) * 2)) return fail(h, B200SGM_EINVAL, "stride smaller than a row");
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    Lane& ln = h->lanes[0];
+    if (ln.busy) return fail(h, B200SGM_ESTATE, "lane 0 is busy");
+    cudaStream_t st = ln.stream;
+    CUDA_TRY(h, cudaMemcpy2DAsync(ln.left, width, left, left_stride, width, height, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(h, cudaMemcpy2DAsync(ln.right, width, right, right_stride, width, height, cudaMemcpyHostToDevice, st));
+    rc = run_pipeline(h, ln, e, ln.left, width, ln.right, width, st);
+    if (rc) return rc;
+    const int npix = width * height;
+    const int nblk = (npix + 255) / 256;
+    ReprojGeom g{width, height, rp->q03, rp->q13, rp->wz, rp->q32, rp->q33, rp->depth_min, rp->depth_max, rp->min_disparity, rp->max_disparity};
+    k_reproject_count<<<nblk, 256, 0, st>>>(ln.disp_out, g, ln.f32a, ln.f32b, ln.block_count);
+    LAUNCH_CHECK(h);
+    k_scan_blocks<<<1, 1024, 0, st>>>(ln.block_count, nblk, ln.total);
+    LAUNCH_CHECK(h);
+    if (points) {
+        k_reproject_write<<<nblk, 256, 0, st>>>(ln.disp_out, ln.left, size_t(width), g, ln.block_count, ln.points);
+        LAUNCH_CHECK(h);
+    }
+    CUDA_TRY(h, cudaMemcpyAsync(ln.h_total, ln.total, 4, cudaMemcpyDeviceToHost, st));
+    if (disp) CUDA_TRY(h, cudaMemcpy2DAsync(disp, disp_stride, ln.disp_out, size_t(width) * 2, size_t(width) * 2, height, cudaMemcpyDeviceToHost, st));
+    if (dmat) CUDA_TRY(h, cudaMemcpyAsync(dmat, ln.f32a, size_t(npix) * 4, cudaMemcpyDeviceToHost, st));
+    if (depth) CUDA_TRY(h, cudaMemcpyAsync(depth, ln.f32b, size_t(npix) * 4, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(h, cudaStreamSynchronize(st));
+    const uint32_t n = *ln.h_total;
+    if (count) *count = n;
+    if (points && n) CUDA_TRY(h, cudaMemcpy(points, ln.points, size_t(n) * sizeof(b200sgm_point), cudaMemcpyDeviceToHost));
+    return B200SGM_OK;
+}
+
+const char* b200sgm_last_error(b200sgm_handle h) { return h ? h->err.c_str() : "null handle"; }
+
+int b200sgm_launch_count(b200sgm_handle h, uint64_t* count)
+{
+    if (!h || !count) return B200SGM_EINVAL;
+    *count = h->launches.load();
+    return B200SGM_OK;
+}
+
+int b200sgm_lane_stream(b200sgm_handle h, int lane, void** cuda_stream)
+{
+    if (!h || !cuda_stream) return B200SGM_EINVAL;
+    int rc = lane_check(h, lane);
+    if (rc) return rc;
+    *cuda_stream = (void*)h->lanes[lane].stream;
+    return B200SGM_OK;
+}
+
+int b200sgm_debug_read(b200sgm_handle h, int lane, const char* what, void* host, size_t bytes, int* dp)
+{
+    if (!h || !what || !host) return B200SGM_EINVAL;
+    int rc = lane_check(h, lane);
+    if (rc) return rc;
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    Lane& ln = h->lanes[lane];
+    CUDA_TRY(h, cudaStreamSynchronize(ln.stream));
+    const void* src = nullptr;
+    if (!strcmp(what, "C")) src = ln.C;
+    else if (!strcmp(what, "S")) src = ln.S;
+    else if (!strcmp(what, "wta")) src = ln.disp_wta;
+    else if (!strcmp(what, "median")) src = ln.disp_med;
+    else return fail(h, B200SGM_EINVAL, "unknown debug buffer");
+    if (dp) {
+        Eff e;
+        if (make_eff(h, 1, 1, e) == 0) *dp = e.Dp;
+    }
+    CUDA_TRY(h, cudaMemcpy(host, src, bytes, cudaMemcpyDeviceToHost));
+    return B200SGM_OK;
+}
+
+int b200sgm_debug_set_path(b200sgm_handle h, int path)
+{
+    if (!h) return B200SGM_EINVAL;
+    h->path = path;
+    return B200SGM_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,33 @@
+// Shared host/device types of the B200 SGBM engine.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace b200sgm {
+
+constexpr int kMaxCost = 32767;        // OpenCV's MAX_COST (SHRT_MAX); also the "infinity" of padded cells
+constexpr uint32_t kMaxCostX2 = 0x7FFF7FFFu;
+constexpr uint32_t kFullMask = 0xFFFFFFFFu;
+
+// Parameters after OpenCV's defaulting rules plus derived geometry.
+struct Eff {
+    int W, H;        // image size
+    int minD, D;     // minDisparity, numDisparities
+    int Dp;          // padded disparity count of the cost volumes (multiple of 2*nreg)
+    int nreg;        // packed uint32 (2 disparities each) held per lane by the aggregation kernels
+    int SW2;         // blockSize/2
+    int P1, P2;
+    int d12;         // effective disp12MaxDiff (>= 1)
+    int uniq;        // effective uniquenessRatio
+    int ftzero;      // max(preFilterCap,15)|1
+    int speckleWin, speckleRange;
+    int mode;        // 0 SGBM (5 paths), 1 HH (8 paths)
+    int INVALID;     // (minD-1)*16
+    int minX1, W1;   // first valid column, number of valid columns
+};
+
+// One prefiltered pixel (A.2): Sobel-x value and its half-pixel interval, raw value and its interval.
+// Packed as uint2: x = sob | sob_lo<<8 | sob_hi<<16 | raw<<24 ; y = raw_lo | raw_hi<<8.
+typedef uint2 Feat;
+
+}  // namespace b200sgm

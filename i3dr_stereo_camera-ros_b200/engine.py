@@ -1,0 +1,195 @@
+"""ctypes binding of libb200sgm.so (the C ABI of include/b200sgm.h).
+
+There is no CPU fallback: importing works without a GPU, but creating an Engine raises if the CUDA
+library is missing or no device is usable.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import numpy as np
+
+from .params import CParams, SGBMParams
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libb200sgm.so")
+_lib = None
+
+# every symbol include/b200sgm.h declares
+SYMBOLS = (
+    "b200sgm_create", "b200sgm_destroy", "b200sgm_set_params", "b200sgm_get_effective_params", "b200sgm_compute",
+    "b200sgm_compute_f32", "b200sgm_compute_device", "b200sgm_enqueue", "b200sgm_wait", "b200sgm_compute_xyz",
+    "b200sgm_last_error", "b200sgm_version", "b200sgm_launch_count", "b200sgm_lane_stream", "b200sgm_debug_read",
+    "b200sgm_debug_set_path",
+)
+
+
+class B200SGMError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__("b200sgm error %d: %s" % (code, msg))
+        self.code = code
+
+
+class CReproject(ctypes.Structure):
+    _fields_ = [(n, ctypes.c_float) for n in ("q03", "q13", "wz", "q32", "q33", "depth_min", "depth_max",
+                                              "min_disparity", "max_disparity")]
+
+
+def load_library():
+    """Loads the in-tree CUDA library; raises if it has not been built (no silent fallback)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError("libb200sgm.so is not built: run `python __graft_entry__.py build` (nvcc, sm_100a). "
+                           "There is no CPU fallback.")
+    lib = ctypes.CDLL(LIB_PATH)
+    for s in SYMBOLS:
+        getattr(lib, s)
+    lib.b200sgm_last_error.restype = ctypes.c_char_p
+    lib.b200sgm_version.restype = ctypes.c_char_p
+    _lib = lib
+    return lib
+
+
+def _u8(a):
+    a = np.asarray(a)
+    if a.dtype != np.uint8 or a.ndim != 2:
+        raise ValueError("images must be 2-D uint8 (CV_8UC1)")
+    if a.strides[1] != 1:
+        a = np.ascontiguousarray(a)
+    return a
+
+
+class Engine:
+    """One engine per GPU. `lanes` = frames that may be in flight (each lane owns its scratch volumes)."""
+
+    def __init__(self, device=0, max_width=640, max_height=480, max_disparities=64, lanes=1, params: SGBMParams | None = None):
+        self.lib = load_library()
+        self.h = ctypes.c_void_p()
+        rc = self.lib.b200sgm_create(int(device), int(max_width), int(max_height), int(max_disparities), int(lanes), ctypes.byref(self.h))
+        if rc != 0:
+            raise B200SGMError(rc, "b200sgm_create failed (no usable CUDA device or out of memory)")
+        self.device = device
+        self.lanes = lanes
+        self.params = None
+        if params is not None:
+            self.set_params(params)
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.b200sgm_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        if rc != 0:
+            raise B200SGMError(rc, self.lib.b200sgm_last_error(self.h).decode())
+
+    def set_params(self, p: SGBMParams):
+        cp = p.to_c()
+        self._check(self.lib.b200sgm_set_params(self.h, ctypes.byref(cp)))
+        self.params = p
+
+    def effective_params(self) -> SGBMParams:
+        cp = CParams()
+        self._check(self.lib.b200sgm_get_effective_params(self.h, ctypes.byref(cp)))
+        return SGBMParams(**{n: getattr(cp, n) for n, _ in CParams._fields_})
+
+    # ---- host-pointer synchronous path (what the matcher plugin calls) ----
+    def compute(self, left, right) -> np.ndarray:
+        L, R = _u8(left), _u8(right)
+        if L.shape != R.shape:
+            raise ValueError("Images MUST be the same resolution")
+        H, W = L.shape
+        disp = np.empty((H, W), np.int16)
+        self._check(self.lib.b200sgm_compute(self.h, L.ctypes.data_as(ctypes.c_void_p), ctypes.c_size_t(L.strides[0]),
+                                             R.ctypes.data_as(ctypes.c_void_p), ctypes.c_size_t(R.strides[0]),
+                                             W, H, disp.ctypes.data_as(ctypes.c_void_p), ctypes.c_size_t(W * 2)))
+        return disp
+
+    def compute_f32(self, left, right) -> np.ndarray:
+        L, R = _u8(left), _u8(right)
+        H, W = L.shape
+        out = np.empty((H, W), np.float32)
+        self._check(self.lib.b200sgm_compute_f32(self.h, L.ctypes.data_as(ctypes.c_void_p), ctypes.c_size_t(L.strides[0]),
+                                                 R.ctypes.data_as(ctypes.c_void_p), ctypes.c_size_t(R.strides[0]),
+                                                 W, H, out.ctypes.data_as(ctypes.c_void_p), ctypes.c_size_t(W * 4)))
+        return out
+
+    def compute_xyz(self, left, right, q, depth_min, depth_max, min_disparity, max_disparity, want_points=True):
+        L, R = _u8(left), _u8(right)
+        H, W = L.shape
+        rp = CReproject(float(q[0]), float(q[1]), float(q[2]), float(q[3]), float(q[4]), float(depth_min), float(depth_max),
+                        float(min_disparity), float(max_disparity))
+        disp = np.empty((H, W), np.int16)
+        dmat = np.empty((H, W), np.float32)
+        depth = np.empty((H, W), np.float32)
+        pts = np.empty((H * W, 4), np.float32) if want_points else None
+        cnt = ctypes.c_uint32(0)
+        self._check(self.lib.b200sgm_compute_xyz(
+            self.h, L.ctypes.data_as(ctypes.c_void_p), ctypes.c_size_t(L.strides[0]), R.ctypes.data_as(ctypes.c_void_p),
+            ctypes.c_size_t(R.strides[0]), W, H, ctypes.byref(rp), disp.ctypes.data_as(ctypes.c_void_p), ctypes.c_size_t(W * 2),
+            dmat.ctypes.data_as(ctypes.c_void_p), depth.ctypes.data_as(ctypes.c_void_p),
+            pts.ctypes.data_as(ctypes.c_void_p) if pts is not None else None, ctypes.byref(cnt)))
+        return disp, dmat, depth, (pts[:cnt.value] if pts is not None else None), cnt.value
+
+    # ---- streaming with host buffers (pinned for true overlap) ----
+    def enqueue(self, lane, left, right, disp_out):
+        L, R = _u8(left), _u8(right)
+        H, W = L.shape
+        assert disp_out.dtype == np.int16 and disp_out.shape == (H, W) and disp_out.strides[1] == 2
+        self._check(self.lib.b200sgm_enqueue(self.h, int(lane), L.ctypes.data_as(ctypes.c_void_p), ctypes.c_size_t(L.strides[0]),
+                                             R.ctypes.data_as(ctypes.c_void_p), ctypes.c_size_t(R.strides[0]), W, H,
+                                             disp_out.ctypes.data_as(ctypes.c_void_p), ctypes.c_size_t(disp_out.strides[0])))
+
+    def enqueue_ptr(self, lane, lptr, lstride, rptr, rstride, W, H, dptr, dstride):
+        self._check(self.lib.b200sgm_enqueue(self.h, int(lane), ctypes.c_void_p(lptr), ctypes.c_size_t(lstride), ctypes.c_void_p(rptr),
+                                             ctypes.c_size_t(rstride), int(W), int(H), ctypes.c_void_p(dptr), ctypes.c_size_t(dstride)))
+
+    def wait(self, lane):
+        self._check(self.lib.b200sgm_wait(self.h, int(lane)))
+
+    # ---- device-resident path (raw device pointers, e.g. torch tensors' data_ptr()) ----
+    def compute_device(self, lane, lptr, lstride, rptr, rstride, W, H, dptr, dstride, stream=0):
+        self._check(self.lib.b200sgm_compute_device(self.h, int(lane), ctypes.c_void_p(lptr), ctypes.c_size_t(lstride),
+                                                    ctypes.c_void_p(rptr), ctypes.c_size_t(rstride), int(W), int(H),
+                                                    ctypes.c_void_p(dptr), ctypes.c_size_t(dstride), ctypes.c_void_p(stream)))
+
+    def lane_stream(self, lane) -> int:
+        s = ctypes.c_void_p()
+        self._check(self.lib.b200sgm_lane_stream(self.h, int(lane), ctypes.byref(s)))
+        return s.value or 0
+
+    def launch_count(self) -> int:
+        c = ctypes.c_uint64(0)
+        self._check(self.lib.b200sgm_launch_count(self.h, ctypes.byref(c)))
+        return c.value
+
+    def set_path(self, path: int):
+        self._check(self.lib.b200sgm_debug_set_path(self.h, int(path)))
+
+    def debug_volume(self, what, W, H, lane=0) -> np.ndarray:
+        """Reads the C or S cost volume of the last frame as [H][W1][D] uint16 (padding stripped)."""
+        p = self.params
+        W1 = p.w1(W)
+        n = 1
+        while 64 * n < p.numDisparities:
+            n *= 2
+        Dp = (p.numDisparities + 2 * n - 1) // (2 * n) * (2 * n)
+        dp = ctypes.c_int(0)
+        buf = np.empty((H, W1, Dp), np.uint16)
+        self._check(self.lib.b200sgm_debug_read(self.h, lane, what.encode(), buf.ctypes.data_as(ctypes.c_void_p),
+                                                ctypes.c_size_t(buf.nbytes), ctypes.byref(dp)))
+        return buf[:, :, :p.numDisparities]
+
+    def debug_image(self, what, W, H, lane=0) -> np.ndarray:
+        buf = np.empty((H, W), np.int16)
+        self._check(self.lib.b200sgm_debug_read(self.h, lane, what.encode(), buf.ctypes.data_as(ctypes.c_void_p),
+                                                ctypes.c_size_t(buf.nbytes), None))
+        return buf

@@ -1,0 +1,141 @@
+/*
+ * b200sgm.h -- C ABI of the B200-native semi-global block matching (SGBM) disparity engine.
+ *
+ * This is the drop-in boundary for ONE path of i3drobotics/i3dr_stereo_camera-ros: the
+ * disparity computation that the reference's MatcherOpenCVSGBM plugin delegates to
+ * cv::StereoSGBM::compute (reference: src/stereoMatcher/matcherOpenCVSGBM.cpp:14-44), plus the
+ * float conversions and the reprojection either side of it.  A reference maintainer binds these
+ * entry points from a new AbstractStereoMatcher subclass (see INTEGRATION.md and
+ * i3dr_stereo_camera-ros_b200/host/matcherB200SGM.{h,cpp}).
+ *
+ * Conventions: every function returns 0 on success and a negative B200SGM_E* code on failure;
+ * no C++ types and no exceptions cross the boundary; the caller owns every buffer it passes;
+ * "stride" arguments are in BYTES.  There is no CPU fallback: if no CUDA device is usable,
+ * b200sgm_create fails with B200SGM_ECUDA.
+ */
+#ifndef B200SGM_H
+#define B200SGM_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200SGM_OK 0
+#define B200SGM_EINVAL (-1)   /* bad argument / parameter outside the supported contract      */
+#define B200SGM_ECUDA (-2)    /* CUDA runtime error (no device, launch failure, out of memory) */
+#define B200SGM_ESIZE (-3)    /* image larger than the engine was created for                  */
+#define B200SGM_ESTATE (-4)   /* call sequence error (e.g. wait on an idle lane)               */
+
+#define B200SGM_MODE_SGBM 0   /* 5 aggregation paths, single top-down sweep (cv::StereoSGBM::MODE_SGBM) */
+#define B200SGM_MODE_HH 1     /* 8 aggregation paths, two sweeps            (cv::StereoSGBM::MODE_HH)   */
+
+typedef struct b200sgm_engine *b200sgm_handle;
+
+/*
+ * RAW parameter values, exactly what the reference's setters hand to cv::StereoSGBM
+ * (matcherOpenCVSGBM.cpp:53-110, driven by generate_disparity.cpp:245-256, parameter set
+ * cfg/i3DR_Disparity.cfg:21-39).  The engine applies OpenCV's defaulting rules itself:
+ * uniquenessRatio<0 -> 10, disp12MaxDiff<=0 -> 1, P1<=0 -> 2, P2<=0 -> 5, P2 = max(P2, P1+1),
+ * blockSize<=0 -> 5 (even sizes act as the next odd), ftzero = max(preFilterCap,15)|1.
+ */
+typedef struct b200sgm_params {
+    int minDisparity;      /* setMinDisparity        matcherOpenCVSGBM.cpp:53-57   */
+    int numDisparities;    /* setDisparityRange      matcherOpenCVSGBM.cpp:59-64   */
+    int blockSize;         /* setWindowSize          matcherOpenCVSGBM.cpp:66-70   */
+    int P1;                /* setP1                  matcherOpenCVSGBM.cpp:97-100  */
+    int P2;                /* setP2                  matcherOpenCVSGBM.cpp:102-105 */
+    int disp12MaxDiff;     /* setDisp12MaxDiff       matcherOpenCVSGBM.cpp:87-90   */
+    int preFilterCap;      /* setPreFilterCap        matcherOpenCVSGBM.cpp:107-110 */
+    int uniquenessRatio;   /* setUniquenessRatio     matcherOpenCVSGBM.cpp:72-75   */
+    int speckleWindowSize; /* setSpeckleFilterWindow matcherOpenCVSGBM.cpp:77-80   */
+    int speckleRange;      /* setSpeckleFilterRange  matcherOpenCVSGBM.cpp:82-85   */
+    int mode;              /* B200SGM_MODE_*; the reference leaves MODE_SGBM (create(64,9,5), :14) */
+} b200sgm_params;
+
+/* One point of the reprojected cloud: pcl::PointXYZRGB-compatible payload (disparity_to_depth.cpp:176-199). */
+typedef struct b200sgm_point {
+    float x, y, z;
+    uint32_t rgb; /* 0x00RRGGBB */
+} b200sgm_point;
+
+/* Reprojection inputs: calc_q() of disparity_to_depth.cpp:62-85 cast to float as :136-140 does. */
+typedef struct b200sgm_reproject {
+    float q03, q13, wz, q32, q33; /* -cx, -cy, fx, 1/T, -(cx-cxr)/T                                  */
+    float depth_min, depth_max;   /* cfg/i3DR_pointCloud.cfg; test of disparity_to_depth.cpp:174-175  */
+    float min_disparity;          /* T*f/depth_max  (generate_disparity.cpp:449)                      */
+    float max_disparity;          /* T*f/depth_min  (generate_disparity.cpp:450); +inf if depth_min=0 */
+} b200sgm_reproject;
+
+/* ---- lifetime ------------------------------------------------------------------------------------------- */
+
+/* Replaces `new MatcherOpenCVSGBM(param_file, size)` + init() (matcherOpenCVSGBM.h:10-14, .cpp:3-15;
+ * created lazily with the first frame's size by init_matcher, generate_disparity.cpp:263-279).
+ * Allocates all device memory for images up to max_width x max_height and max_disparities up front so
+ * that later calls do not allocate.  `lanes` >= 1 is the number of frames that may be in flight. */
+int b200sgm_create(int device, int max_width, int max_height, int max_disparities, int lanes, b200sgm_handle *out);
+int b200sgm_destroy(b200sgm_handle h);
+
+/* Replaces the 12 setters pushed by updateMatcher() (generate_disparity.cpp:241-261). Cheap, lazy: only
+ * stores and validates; takes effect on the next compute/enqueue. */
+int b200sgm_set_params(b200sgm_handle h, const b200sgm_params *p);
+/* Returns the parameters after OpenCV's defaulting rules (Appendix A.1) -- what the kernels will use. */
+int b200sgm_get_effective_params(b200sgm_handle h, b200sgm_params *out);
+
+/* ---- the hot path ----------------------------------------------------------------------------------------- */
+
+/* Replaces matcher->compute(*left, *right, disparity_lr) (matcherOpenCVSGBM.cpp:21).
+ * left/right: CV_8UC1 host images; disp: CV_16S host image, disparity x16, invalid = (minDisparity-1)*16.
+ * Synchronous: host->device copy, kernels, device->host copy. */
+int b200sgm_compute(b200sgm_handle h, const uint8_t *left, size_t left_stride, const uint8_t *right,
+                    size_t right_stride, int width, int height, int16_t *disp, size_t disp_stride);
+
+/* Same, but the result is what forwardMatch() must leave in disparity_lr: CV_32FC1 holding the SAME
+ * numeric value (still x16) -- disparity_lr.convertTo(CV_32FC1), matcherOpenCVSGBM.cpp:34 and
+ * AbstractStereoMatcher::match(), abstractStereoMatcher.cpp:44-53. */
+int b200sgm_compute_f32(b200sgm_handle h, const uint8_t *left, size_t left_stride, const uint8_t *right,
+                        size_t right_stride, int width, int height, float *disp32, size_t disp_stride);
+
+/* Device-resident variant: all pointers are device memory on the engine's device; work is enqueued on
+ * `cuda_stream` (a cudaStream_t, may be 0) of lane `lane` and NOT synchronised. */
+int b200sgm_compute_device(b200sgm_handle h, int lane, const uint8_t *d_left, size_t left_stride,
+                           const uint8_t *d_right, size_t right_stride, int width, int height,
+                           int16_t *d_disp, size_t disp_stride, void *cuda_stream);
+
+/* Streaming: enqueue a host frame on lane `lane` (asynchronous when the host buffers are page-locked),
+ * later wait for it.  Frames on different lanes overlap copies and kernels. */
+int b200sgm_enqueue(b200sgm_handle h, int lane, const uint8_t *left, size_t left_stride, const uint8_t *right,
+                    size_t right_stride, int width, int height, int16_t *disp, size_t disp_stride);
+int b200sgm_wait(b200sgm_handle h, int lane);
+
+/* ---- the steps either side of the path (rows a11 and R of SURVEY.md section 8) ----------------------------- */
+
+/* Matching fused with processDisparity() (generate_disparity.cpp:436-452: /16, depth-window -> 10000) and
+ * the reprojection of disparity_to_depth.cpp:136-205.  Any of dmat/depth/points may be NULL.
+ * dmat, depth: float H x W (tight); points: capacity W*H; *count = number of points, row-major order. */
+int b200sgm_compute_xyz(b200sgm_handle h, const uint8_t *left, size_t left_stride, const uint8_t *right,
+                        size_t right_stride, int width, int height, const b200sgm_reproject *rp,
+                        int16_t *disp, size_t disp_stride, float *dmat, float *depth,
+                        b200sgm_point *points, uint32_t *count);
+
+/* ---- diagnostics ------------------------------------------------------------------------------------------ */
+
+const char *b200sgm_last_error(b200sgm_handle h);
+const char *b200sgm_version(void);
+/* Number of kernel launches issued by this engine since creation (bench.py's gpu_launches). */
+int b200sgm_launch_count(b200sgm_handle h, uint64_t *count);
+/* The engine's internal stream for `lane` (a cudaStream_t) -- lets a caller time with CUDA events on the
+ * stream the kernels are launched on. */
+int b200sgm_lane_stream(b200sgm_handle h, int lane, void **cuda_stream);
+/* Copies an internal stage buffer of `lane` to the host (tests only): what = "C" | "S" (volumes
+ * [H][W1][Dp] uint16, *dp receives the padded disparity count), "wta" | "median" (H x W int16). */
+int b200sgm_debug_read(b200sgm_handle h, int lane, const char *what, void *host, size_t bytes, int *dp);
+/* Selects the kernel path: 0 = default (fastest validated), 1 = generic per-direction chains. Tests only. */
+int b200sgm_debug_set_path(b200sgm_handle h, int path);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200SGM_H */
