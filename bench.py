@@ -1,0 +1,369 @@
+#!/usr/bin/env python
+"""Benchmark of the SGBM disparity hot path (BASELINE.json metric: disparity frames/s at 2448x2048x256d).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--config c3]
+
+A "step" is one pass of the hot path over one batch of `--frames` synthetic rectified stereo pairs per GPU.
+N > 1 is launched by torchrun (one rank per GPU); frames are independent, so ranks never exchange data
+(weak scaling, no collective on the data path); torch.distributed is used only for the barrier and the
+max-over-ranks of the device-timed duration.
+
+value      : whole-job frames/s with the input frames resident in HBM (16 distinct pairs, 160 MB > L2).
+e2e        : the same metric through the host-buffer C-ABI call (b200sgm_enqueue/wait) with pinned host
+             images in and the CV_16S disparity out, copies inside the timed region.
+roofline   : dominant stage timed live with CUDA events on the stream it runs on (engine stage profiling).
+cpu_baseline / --impl reference : cv::StereoSGBM (cv2, the library the reference calls) with the reference's
+             call sequence on the host cores, one matcher per thread, frame-parallel.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import b200sgm  # noqa: E402
+from b200sgm import CONFIGS, synth  # noqa: E402
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--config", default="c3", choices=sorted(CONFIGS))
+    ap.add_argument("--frames", type=int, default=16, help="distinct frames per step per GPU")
+    ap.add_argument("--lanes", type=int, default=4, help="frames in flight per GPU")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--cpu-frames", type=int, default=0, help="frames in the CPU sample (default: one per core)")
+    return ap.parse_args()
+
+
+# ---------------------------------------------------------------------------------------------------------
+# CPU arm: cv::StereoSGBM through cv2 (kind "reference"), else the C oracle port (kind "port").
+# ---------------------------------------------------------------------------------------------------------
+def cpu_sample(cfg, frames, n_threads):
+    """Times `len(frames)` frames on `n_threads` host threads. Returns (fps, kind, seconds)."""
+    from concurrent.futures import ThreadPoolExecutor
+    from oracle import cv2_reference as ref
+    p = cfg.params
+    if ref.have_cv2():
+        import cv2
+        cv2.setNumThreads(1)
+        kind = "reference"
+        tl = threading.local()
+
+        def work(fr):
+            if not hasattr(tl, "m"):
+                tl.m = ref.make_matcher(p)
+            return tl.m.compute(fr[0], fr[1])
+    else:
+        from oracle import oracle
+        kind = "port"
+
+        def work(fr):
+            return oracle.compute(fr[0], fr[1], p)
+    with ThreadPoolExecutor(n_threads) as ex:
+        t0 = time.perf_counter()
+        list(ex.map(work, frames))
+        dt = time.perf_counter() - t0
+    return len(frames) / dt, kind, dt
+
+
+def cpu_model():
+    try:
+        for line in open("/proc/cpuinfo"):
+            if line.startswith("model name"):
+                return line.split(":", 1)[1].strip()
+    except Exception:
+        pass
+    return "unknown"
+
+
+def run_reference(args, cfg):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return  # the CPU arm runs on rank 0 alone
+    cores = os.cpu_count() or 1
+    p = cfg.params
+    n = args.cpu_frames or cores
+    frames = [synth.make_pair(cfg.width, cfg.height, p.numDisparities, p.minDisparity, 1000 + i) for i in range(min(n, 4))]
+    frames = [frames[i % len(frames)] for i in range(n)]
+    for _ in range(args.warmup):
+        cpu_sample(cfg, frames[:max(1, min(len(frames), cores))], cores)
+    t_total, kind = 0.0, "reference"
+    for _ in range(args.steps):
+        fps, kind, dt = cpu_sample(cfg, frames, cores)
+        t_total += dt
+    fps = args.steps * n / t_total
+    line = {
+        "impl": "reference", "metric": "disparity frames/s", "value": fps, "unit": "frames/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_total / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "u16", "data": "synthetic",
+        "config": workload(cfg, n, 0),
+        "gpix_disp_per_s": fps * cfg.gpix_disp,
+        "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "kind": kind,
+                         "sample": "%d frames per step, one cv::StereoSGBM matcher per thread, %d threads, %s" % (n, cores, cpu_model())},
+        "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload(cfg, frames, lanes):
+    p = cfg.params
+    return {"workload": "%s: %dx%d pair, %d disparities, blockSize %d, %s, P1/P2 %d/%d, uniq %d, speckle %d/%d" % (
+        cfg.name, cfg.width, cfg.height, p.numDisparities, p.blockSize, "MODE_HH 8-path" if p.mode else "MODE_SGBM 5-path",
+        p.P1, p.P2, p.uniquenessRatio, p.speckleWindowSize, p.speckleRange),
+        "frames_per_step_per_gpu": frames, "lanes_per_gpu": lanes,
+        "l2_policy": "inputs larger than L2: %d distinct pairs cycled, cost volumes 2 x %.2f GB per lane" % (
+            frames, cfg.width * cfg.height * p.numDisparities * 2 / 1e9)}
+
+
+# ---------------------------------------------------------------------------------------------------------
+# clocks sampling (B200_PROFILING.md "clocks DURING the timed region")
+# ---------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.p = None
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
+                                      stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        if self.p is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.p.terminate()
+        try:
+            out = self.p.communicate(timeout=5)[0]
+        except Exception:
+            self.p.kill()
+            out = ""
+        sm, mx, pw, reasons = [], [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in out.strip().splitlines():
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1])); pw.append(float(f[2]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "power_w_max": float(max(pw)),
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ---------------------------------------------------------------------------------------------------------
+# B200 arm
+# ---------------------------------------------------------------------------------------------------------
+def run_b200(args, cfg):
+    import torch
+    import torch.distributed as dist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the B200 arm has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    p = cfg.params
+    W, H, D = cfg.width, cfg.height, p.numDisparities
+    NF, lanes = args.frames, max(1, min(args.lanes, args.frames))
+    eng = b200sgm.Engine(local, W, H, D, lanes, p)
+
+    # ---- synthetic frames: NF distinct pairs per rank; pinned host copies + device-resident copies
+    hostL = torch.empty((NF, H, W), dtype=torch.uint8).pin_memory()
+    hostR = torch.empty((NF, H, W), dtype=torch.uint8).pin_memory()
+    hostD = torch.empty((NF, H, W), dtype=torch.int16).pin_memory()
+    n_unique = min(NF, 16)
+    for i in range(n_unique):
+        L, R = synth.make_pair(W, H, D, p.minDisparity, 1000 + rank * n_unique + i)
+        hostL[i].copy_(torch.from_numpy(L)); hostR[i].copy_(torch.from_numpy(R))
+    for i in range(n_unique, NF):
+        hostL[i].copy_(hostL[i % n_unique]); hostR[i].copy_(hostR[i % n_unique])
+    devL, devR = hostL.to(dev), hostR.to(dev)
+    devD = torch.empty((NF, H, W), dtype=torch.int16, device=dev)
+    streams = [torch.cuda.Stream(device=dev) for _ in range(lanes)]
+    main = torch.cuda.current_stream()
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+
+    def device_step():
+        for i in range(NF):
+            ln = i % lanes
+            eng.compute_device(ln, devL[i].data_ptr(), W, devR[i].data_ptr(), W, W, H, devD[i].data_ptr(), W * 2,
+                               stream=streams[ln].cuda_stream)
+
+    def timed_device(steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(main)
+        for s in streams:
+            s.wait_event(e0)
+        for _ in range(steps):
+            device_step()
+        for s in streams:
+            ev = torch.cuda.Event()
+            ev.record(s)
+            main.wait_event(ev)
+        e1.record(main)
+        barrier()
+        return e0.elapsed_time(e1)
+
+    # ---- parity gate inside the bench: frame 0 of rank 0 (seed 1000) against the committed golden CRC
+    checked = None
+    eng.compute_device(0, devL[0].data_ptr(), W, devR[0].data_ptr(), W, W, H, devD[0].data_ptr(), W * 2, stream=streams[0].cuda_stream)
+    torch.cuda.synchronize()
+    if rank == 0:
+        try:
+            gold = json.load(open(os.path.join(ROOT, "tests", "golden", "golden_crc.json")))
+            key = "c3" if cfg.name in ("c3", "c4", "c5") else cfg.name
+            checked = synth.crc32(devD[0].cpu().numpy()) == gold[key]["disp"]
+        except Exception as e:  # pragma: no cover
+            checked = "unavailable: %s" % e
+
+    for _ in range(args.warmup):
+        device_step()
+    l0 = eng.launch_count()
+    sampler = ClockSampler(local) if rank == 0 else None
+    ms = timed_device(args.steps)
+    clocks = sampler.stop() if sampler else None
+    launches = eng.launch_count() - l0
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max = float(t.item())
+    fps = world * args.steps * NF / (ms_max * 1e-3)
+
+    # ---- e2e: pinned host images in, CV_16S disparity out, through b200sgm_enqueue / b200sgm_wait
+    e2e = None
+    if not args.no_e2e:
+        def host_step():
+            for i in range(NF):
+                ln = i % lanes
+                if i >= lanes:
+                    eng.wait(ln)
+                eng.enqueue_ptr(ln, hostL[i].data_ptr(), W, hostR[i].data_ptr(), W, W, H, hostD[i].data_ptr(), W * 2)
+            for ln in range(min(lanes, NF)):
+                eng.wait(ln)
+        for _ in range(max(1, args.warmup)):
+            host_step()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            host_step()
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        t = torch.tensor([dt], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e = {"value": world * args.steps * NF / float(t.item()), "unit": "frames/s",
+               "h2d_bytes_per_step": 2 * W * H * NF * world, "d2h_bytes_per_step": 2 * W * H * NF * world,
+               "api": "b200sgm_enqueue/b200sgm_wait, pinned host buffers, %d lanes" % lanes}
+
+    # ---- roofline of the dominant stage: stage events on one lane, frames back to back (rank 0)
+    roofline, stages = None, None
+    if rank == 0:
+        eng.profile(True)
+        eng.stage_times(0)
+        nprof = min(NF, 8)
+        for i in range(nprof):
+            eng.compute_device(0, devL[i].data_ptr(), W, devR[i].data_ptr(), W, W, H, devD[i].data_ptr(), W * 2, stream=0)
+        st_ms, nfr = eng.stage_times(0)
+        eng.profile(False)
+        stages = {k: v / max(nfr, 1) for k, v in st_ms.items()}
+        total = sum(stages.values())
+        dom = max(stages, key=stages.get)
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+        W1 = p.w1(W)
+        R = 8 if p.mode else 5
+        alg_bytes = 4 * W * H if p.mode == 0 else 4 * W * H + 4 * W1 * H * D   # SURVEY 8d, per frame
+        alg_ops = W1 * H * D * (30 + 9 * R)                                    # SURVEY 8d, per frame
+        frame_s = total * 1e-3
+        try:
+            alu = b200sgm.alu_peak(local)
+        except Exception:
+            alu = (None, None, None)
+        ach_gbs = alg_bytes / frame_s / 1e9
+        ach_tops = alg_ops / frame_s / 1e12
+        roofline = {
+            "bound": "hbm", "achieved": ach_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": ach_gbs / hbm_peak,
+            "traffic": None,
+            "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if "hbm_gbs" in peaks else "fallback 6650 GB/s",
+            "kernel": "whole pipeline of one frame (dominant stage: %s, %.1f%% of the frame)" % (dom, 100 * stages[dom] / max(total, 1e-9)),
+            "algorithmic_bytes_per_frame": alg_bytes,
+            "binding": "alu",
+            "alu": {"achieved": ach_tops, "peak": alu[0], "unit": "Tops/s (elementary int16 ops)",
+                    "frac": (ach_tops / alu[0]) if alu[0] else None, "algorithmic_ops_per_frame": alg_ops,
+                    "peak_source": "b200sgm_alu_peak: measured VIMNMX3.U16x2 issue rate x4 ops; min2 %.1f, mix %.1f" % (alu[1] or 0, alu[2] or 0)},
+            "stage_ms_per_frame": stages, "single_lane_fps": 1.0 / frame_s,
+        }
+
+    # ---- CPU baseline beside it (rank 0, N=1 only)
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cores = os.cpu_count() or 1
+        n = args.cpu_frames or cores
+        fr = [(hostL[i % n_unique].numpy(), hostR[i % n_unique].numpy()) for i in range(n)]
+        v, kind, dt = cpu_sample(cfg, fr, cores)
+        cpu = {"value": v, "unit": "frames/s", "cores": cores, "kind": kind,
+               "sample": "%d frames of the same workload in %.1f s, one cv::StereoSGBM matcher per thread, %d threads, %s" % (n, dt, cores, cpu_model())}
+
+    if rank == 0:
+        line = {
+            "metric": "disparity frames/s", "value": fps, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "u16", "data": "synthetic", "config": workload(cfg, NF, lanes),
+            "gpix_disp_per_s": fps * cfg.gpix_disp, "parity_checked_vs_golden_crc": checked,
+            "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
+        }
+        print(json.dumps(line), flush=True)
+    eng.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse()
+    cfg = CONFIGS[args.config]
+    if args.impl == "reference":
+        run_reference(args, cfg)
+    else:
+        run_b200(args, cfg)
+
+
+if __name__ == "__main__":
+    main()

@@ -37,9 +37,15 @@ struct Lane {
     float4* points = nullptr;                       // W x H
     uint32_t *block_count = nullptr, *total = nullptr;
     uint32_t* h_total = nullptr;                    // pinned
-    // pending enqueue
-    int16_t* pending_disp = nullptr;
+    // stage profiling (b200sgm_profile): ring of event sets, harvested by b200sgm_stage_times
+    std::vector<cudaEvent_t> prof_events;           // kProfRing * (kStages + 1)
+    int prof_head = 0, prof_count = 0;
+    double stage_ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    uint64_t stage_frames = 0;
 };
+
+constexpr int kStages = 6;    // prefilter, cost, aggregate+wta, lrcheck, median, speckle
+constexpr int kProfRing = 256;
 
 }  // namespace
 
@@ -52,6 +58,7 @@ struct b200sgm_engine {
     std::string err;
     std::atomic<uint64_t> launches{0};
     int path = 0;
+    bool profile = false;
     int num_sms = 148;
     std::mutex mu;
 };
@@ -171,11 +178,41 @@ int launch_aggregation(b200sgm_engine* h, Lane& ln, const Eff& e, cudaStream_t s
     return fail(h, B200SGM_EINVAL, "bad nreg");
 }
 
+// Stage profiling: records event `idx` of the current frame's event set (no-op unless profiling is on).
+inline void prof_mark(b200sgm_engine* h, Lane& ln, int idx, cudaStream_t st)
+{
+    if (!h->profile || ln.prof_events.empty()) return;
+    cudaEventRecord(ln.prof_events[size_t(ln.prof_head) * (kStages + 1) + idx], st);
+}
+
+void prof_harvest(Lane& ln)
+{
+    // all recorded sets are complete once the stream is synchronised
+    int first = (ln.prof_head - ln.prof_count + kProfRing) % kProfRing;
+    for (int f = 0; f < ln.prof_count; f++) {
+        size_t base = size_t((first + f) % kProfRing) * (kStages + 1);
+        for (int s = 0; s < kStages; s++) {
+            float ms = 0;
+            if (cudaEventElapsedTime(&ms, ln.prof_events[base + s], ln.prof_events[base + s + 1]) == cudaSuccess) ln.stage_ms[s] += ms;
+        }
+        ln.stage_frames++;
+    }
+    ln.prof_count = 0;
+}
+
 // Enqueues the whole matcher on `st`: ln.left/right (device, pitch W) -> ln.disp_out (device, pitch W).
 int run_pipeline(b200sgm_engine* h, Lane& ln, const Eff& e, const uint8_t* dL, size_t lp, const uint8_t* dR, size_t rp, cudaStream_t st)
 {
     const int W = e.W, H = e.H;
     const int npix = W * H;
+    if (h->profile) {
+        if (ln.prof_events.empty()) {
+            ln.prof_events.resize(size_t(kProfRing) * (kStages + 1));
+            for (auto& ev : ln.prof_events) CUDA_TRY(h, cudaEventCreate(&ev));
+        }
+        if (ln.prof_count == kProfRing) { CUDA_TRY(h, cudaStreamSynchronize(st)); prof_harvest(ln); }
+    }
+    prof_mark(h, ln, 0, st);
     {
         dim3 block(256), grid((W + 255) / 256, H);
         k_prefilter<<<grid, block, 0, st>>>(dL, lp, W, H, e.ftzero, ln.feat_l);
@@ -186,8 +223,8 @@ int run_pipeline(b200sgm_engine* h, Lane& ln, const Eff& e, const uint8_t* dL, s
     CUDA_TRY(h, cudaMemsetAsync(ln.disp2key, 0xFF, size_t(npix) * 4, st));
     k_fill16<<<(npix + 255) / 256, 256, 0, st>>>(ln.disp_wta, npix, int16_t(e.INVALID));
     LAUNCH_CHECK(h);
+    prof_mark(h, ln, 1, st);
     if (e.W1 > 0) {
-        // cost volume
         CostGeom cg;
         cg.W = W; cg.H = H; cg.W1 = e.W1; cg.minX1 = e.minX1; cg.minD = e.minD; cg.D = e.D; cg.Dp = e.Dp; cg.SW2 = e.SW2;
         int TX = 32, DCP = 32;
@@ -197,25 +234,32 @@ int run_pipeline(b200sgm_engine* h, Lane& ln, const Eff& e, const uint8_t* dL, s
         while (cost_smem_bytes(TX, DCP, e.SW2) > limit && DCP > 4) DCP /= 2;
         while (cost_smem_bytes(TX, DCP, e.SW2) > limit && TX > 1) TX /= 2;
         if (cost_smem_bytes(TX, DCP, e.SW2) > limit) return fail(h, B200SGM_EINVAL, "blockSize too large for the cost kernel");
-        // every thread group must own at least one column: columns-per-group = ceil(TX / (256/DCP))
         cg.TX = TX; cg.DCP = DCP; cg.RS = 64;
         const size_t smem = cost_smem_bytes(TX, DCP, e.SW2);
         CUDA_TRY(h, cudaFuncSetAttribute(k_cost_generic, cudaFuncAttributeMaxDynamicSharedMemorySize, int(limit)));
         dim3 grid((e.W1 + TX - 1) / TX, (e.Dp / 2 + DCP - 1) / DCP, (H + cg.RS - 1) / cg.RS);
         k_cost_generic<<<grid, 256, smem, st>>>(ln.feat_l, ln.feat_r, ln.C, cg);
         LAUNCH_CHECK(h);
+    }
+    prof_mark(h, ln, 2, st);
+    if (e.W1 > 0) {
         int rc = launch_aggregation(h, ln, e, st);
         if (rc) return rc;
+    }
+    prof_mark(h, ln, 3, st);
+    if (e.W1 > 0) {
         WtaGeom wg{e.W, e.H, e.W1, e.minX1, e.minD, e.D, e.Dp, e.uniq, e.d12, e.INVALID};
         dim3 block(256), grid2((e.W1 + 255) / 256, H);
         k_lrcheck<<<grid2, block, 0, st>>>(ln.disp_wta, ln.disp2key, wg);
         LAUNCH_CHECK(h);
     }
+    prof_mark(h, ln, 4, st);
     {
         dim3 block(256), grid((W + 255) / 256, H);
         k_median3<<<grid, block, 0, st>>>(ln.disp_wta, ln.disp_med, W, H);
         LAUNCH_CHECK(h);
     }
+    prof_mark(h, ln, 5, st);
     CUDA_TRY(h, cudaMemcpyAsync(ln.disp_out, ln.disp_med, size_t(npix) * 2, cudaMemcpyDeviceToDevice, st));
     if (e.speckleWin > 0) {
         const int maxDiff = 16 * e.speckleRange;
@@ -229,9 +273,13 @@ int run_pipeline(b200sgm_engine* h, Lane& ln, const Eff& e, const uint8_t* dL, s
         k_speckle_apply<<<(npix + 255) / 256, 256, 0, st>>>(ln.disp_out, ln.label, ln.csize, npix, e.INVALID, e.speckleWin);
         LAUNCH_CHECK(h);
     }
+    prof_mark(h, ln, 6, st);
+    if (h->profile && !ln.prof_events.empty()) { ln.prof_head = (ln.prof_head + 1) % kProfRing; ln.prof_count++; }
     return B200SGM_OK;
 }
 
+}  // namespace
+namespace {
 int lane_check(b200sgm_engine* h, int lane)
 {
     if (lane < 0 || lane >= int(h->lanes.size())) return fail(h, B200SGM_EINVAL, "lane out of range");
@@ -244,6 +292,7 @@ void free_lane(Lane& ln)
     cudaFree(ln.disp2key); cudaFree(ln.disp_wta); cudaFree(ln.disp_med); cudaFree(ln.disp_out); cudaFree(ln.label);
     cudaFree(ln.csize); cudaFree(ln.f32a); cudaFree(ln.f32b); cudaFree(ln.points); cudaFree(ln.block_count); cudaFree(ln.total);
     if (ln.h_total) cudaFreeHost(ln.h_total);
+    for (auto ev : ln.prof_events) cudaEventDestroy(ev);
     if (ln.done) cudaEventDestroy(ln.done);
     if (ln.stream) cudaStreamDestroy(ln.stream);
     ln = Lane();
@@ -471,6 +520,29 @@ int b200sgm_lane_stream(b200sgm_handle h, int lane, void** cuda_stream)
     int rc = lane_check(h, lane);
     if (rc) return rc;
     *cuda_stream = (void*)h->lanes[lane].stream;
+    return B200SGM_OK;
+}
+
+int b200sgm_profile(b200sgm_handle h, int enable)
+{
+    if (!h) return B200SGM_EINVAL;
+    h->profile = enable != 0;
+    return B200SGM_OK;
+}
+
+int b200sgm_stage_times(b200sgm_handle h, int lane, double* ms, int n, uint64_t* frames)
+{
+    if (!h || !ms || n < kStages) return B200SGM_EINVAL;
+    int rc = lane_check(h, lane);
+    if (rc) return rc;
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    Lane& ln = h->lanes[lane];
+    CUDA_TRY(h, cudaStreamSynchronize(ln.stream));
+    CUDA_TRY(h, cudaDeviceSynchronize());   // frames may have been enqueued on caller-provided streams
+    prof_harvest(ln);
+    for (int s = 0; s < kStages; s++) { ms[s] = ln.stage_ms[s]; ln.stage_ms[s] = 0; }
+    if (frames) *frames = ln.stage_frames;
+    ln.stage_frames = 0;
     return B200SGM_OK;
 }
 

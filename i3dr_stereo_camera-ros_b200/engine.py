@@ -20,8 +20,10 @@ SYMBOLS = (
     "b200sgm_create", "b200sgm_destroy", "b200sgm_set_params", "b200sgm_get_effective_params", "b200sgm_compute",
     "b200sgm_compute_f32", "b200sgm_compute_device", "b200sgm_enqueue", "b200sgm_wait", "b200sgm_compute_xyz",
     "b200sgm_last_error", "b200sgm_version", "b200sgm_launch_count", "b200sgm_lane_stream", "b200sgm_debug_read",
-    "b200sgm_debug_set_path",
+    "b200sgm_debug_set_path", "b200sgm_profile", "b200sgm_stage_times", "b200sgm_alu_peak",
 )
+
+STAGES = ("prefilter", "cost", "aggregate_wta", "lrcheck", "median", "speckle")
 
 
 class B200SGMError(RuntimeError):
@@ -171,6 +173,16 @@ class Engine:
         self._check(self.lib.b200sgm_launch_count(self.h, ctypes.byref(c)))
         return c.value
 
+    def profile(self, enable: bool):
+        self._check(self.lib.b200sgm_profile(self.h, int(bool(enable))))
+
+    def stage_times(self, lane=0):
+        """(dict stage -> accumulated ms, frames) since the previous call; synchronises the device."""
+        ms = (ctypes.c_double * len(STAGES))()
+        fr = ctypes.c_uint64(0)
+        self._check(self.lib.b200sgm_stage_times(self.h, int(lane), ms, len(STAGES), ctypes.byref(fr)))
+        return {k: ms[i] for i, k in enumerate(STAGES)}, fr.value
+
     def set_path(self, path: int):
         self._check(self.lib.b200sgm_debug_set_path(self.h, int(path)))
 
@@ -193,3 +205,13 @@ class Engine:
         self._check(self.lib.b200sgm_debug_read(self.h, lane, what.encode(), buf.ctypes.data_as(ctypes.c_void_p),
                                                 ctypes.c_size_t(buf.nbytes), None))
         return buf
+
+
+def alu_peak(device=0):
+    """Measured packed-int16 issue peak in 1e12 elementary ops/s: (min3, min2, aggregation mix)."""
+    lib = load_library()
+    out = (ctypes.c_double * 3)()
+    rc = lib.b200sgm_alu_peak(int(device), out)
+    if rc != 0:
+        raise B200SGMError(rc, "b200sgm_alu_peak failed")
+    return tuple(out)

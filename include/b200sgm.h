@@ -129,6 +129,17 @@ int b200sgm_launch_count(b200sgm_handle h, uint64_t *count);
 /* The engine's internal stream for `lane` (a cudaStream_t) -- lets a caller time with CUDA events on the
  * stream the kernels are launched on. */
 int b200sgm_lane_stream(b200sgm_handle h, int lane, void **cuda_stream);
+/* Stage profiling: when enabled every frame records CUDA events at the stage boundaries on the stream it
+ * runs on.  b200sgm_stage_times synchronises, returns the accumulated milliseconds of the 6 stages
+ * {prefilter, cost, aggregate+wta, lrcheck, median, speckle} since the previous call, the number of frames
+ * they cover, and resets the accumulators. */
+int b200sgm_profile(b200sgm_handle h, int enable);
+int b200sgm_stage_times(b200sgm_handle h, int lane, double *ms, int n, uint64_t *frames);
+/* Measures the packed 16-bit integer issue peak of `device` with a register-resident VIMNMX3.U16x2 /
+ * VIADD.16x2 microbenchmark (the ALU roofline denominator).  Results in 1e12
+ * elementary 16-bit ops per second: [0] = 3-input min (4 ops per lane-instruction), [1] = 2-input min
+ * (2 ops), [2] = the aggregation instruction mix. */
+int b200sgm_alu_peak(int device, double tera_ops[3]);
 /* Copies an internal stage buffer of `lane` to the host (tests only): what = "C" | "S" (volumes
  * [H][W1][Dp] uint16, *dp receives the padded disparity count), "wta" | "median" (H x W int16). */
 int b200sgm_debug_read(b200sgm_handle h, int lane, const char *what, void *host, size_t bytes, int *dp);

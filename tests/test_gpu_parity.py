@@ -1,0 +1,213 @@
+"""GPU parity tests: the CUDA path through the C ABI against the CPU oracle and the OpenCV golden vectors.
+Bit-exact (integer path): zero differing pixels is the only accepted result."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+import b200sgm
+from b200sgm import SGBMParams, CONFIGS, synth, Engine
+from oracle import oracle, cv2_reference as ref
+
+pytestmark = pytest.mark.gpu
+
+
+def run_gpu(L, R, p, lanes=1):
+    H, W = L.shape
+    eng = Engine(0, W, H, p.numDisparities, lanes, p)
+    try:
+        return eng.compute(L, R)
+    finally:
+        eng.close()
+
+
+def test_golden_small_bit_exact(golden_small):
+    for i, (L, R, p, want) in enumerate(golden_small):
+        got = run_gpu(L, R, p)
+        assert np.array_equal(got, want), "golden case %d: %d px differ (%s)" % (i, (got != want).sum(), p)
+
+
+def test_stage_dumps_match_oracle():
+    """Cost volume C, aggregated cost S, WTA+LR output and the median stage, one by one."""
+    for W, H, p in [(96, 64, SGBMParams(numDisparities=32)), (130, 50, SGBMParams(numDisparities=48, minDisparity=-8, blockSize=5, mode=1)),
+                    (200, 40, SGBMParams(numDisparities=128, minDisparity=9))]:
+        L, R = synth.make_pair(W, H, p.numDisparities, p.minDisparity, 3)
+        want, st = oracle.compute(L, R, p, dumps=True)
+        eng = Engine(0, W, H, p.numDisparities, 1, p)
+        eng.set_path(1)   # generic per-direction path materialises both volumes
+        got = eng.compute(L, R)
+        assert np.array_equal(eng.debug_volume("C", W, H), st["C"].view(np.uint16))
+        assert np.array_equal(eng.debug_volume("S", W, H), st["S"].view(np.uint16))
+        assert np.array_equal(eng.debug_image("wta", W, H), st["disp_wta"])
+        assert np.array_equal(eng.debug_image("median", W, H), st["disp_med"])
+        assert np.array_equal(got, want)
+        eng.close()
+
+
+def test_random_parameter_sweep_vs_oracle():
+    rng = np.random.default_rng(99)
+    n = 0
+    for it in range(60):
+        W = int(rng.integers(70, 300)); H = int(rng.integers(24, 100))
+        D = int(rng.choice([16, 32, 48, 8, 24, 40, 64, 80, 128, 144, 256])); minD = int(rng.choice([-8, 0, 1, 2, 9, -20, 30]))
+        if W - (D + abs(minD)) < 8:
+            continue
+        p = SGBMParams(minDisparity=minD, numDisparities=D, blockSize=int(rng.choice([3, 5, 9, 15, 8, 21])),
+                       P1=int(rng.choice([200, 8, 1800, 0])), P2=int(rng.choice([400, 32, 7200, 0])),
+                       disp12MaxDiff=int(rng.choice([0, 1, 2, 5, -1])), preFilterCap=int(rng.choice([7, 31, 63, 1])),
+                       uniquenessRatio=int(rng.choice([0, 2, 10, 15, -1, 50])), speckleWindowSize=int(rng.choice([0, 100, 20, 400])),
+                       speckleRange=int(rng.choice([4, 2, 1, 0])), mode=int(rng.integers(0, 2)))
+        L, R = synth.make_pair(W, H, D, minD, seed=int(rng.integers(1 << 30)))
+        if it % 3 == 0:
+            R = np.clip(R.astype(int) + rng.integers(-25, 26, R.shape), 0, 255).astype(np.uint8)
+        want = oracle.compute(L, R, p)
+        got = run_gpu(L, R, p)
+        assert np.array_equal(got, want), "%d px differ for %s (%dx%d)" % ((got != want).sum(), p, W, H)
+        n += 1
+    assert n >= 35
+
+
+def test_edge_cases():
+    p = SGBMParams(numDisparities=64)
+    # W1 <= 0: everything INVALID
+    L = np.full((8, 40), 7, np.uint8)
+    assert (run_gpu(L, L, p) == p.invalid()).all()
+    # constant images, saturated images, tiny heights
+    for img in (np.zeros((5, 100), np.uint8), np.full((3, 120), 255, np.uint8), np.full((1, 90), 9, np.uint8)):
+        q = SGBMParams(numDisparities=16)
+        assert np.array_equal(run_gpu(img, img, q), oracle.compute(img, img, q))
+    # strided (non-tight) host images
+    L, R = synth.make_pair(150, 40, 32, 0, 5)
+    Lp = np.zeros((40, 200), np.uint8); Lp[:, :150] = L
+    q = SGBMParams(numDisparities=32)
+    assert np.array_equal(run_gpu(Lp[:, :150], R, q), oracle.compute(L, R, q))
+
+
+def test_error_behaviour():
+    eng = Engine(0, 64, 64, 32, 1)
+    L = np.zeros((64, 64), np.uint8)
+    with pytest.raises(b200sgm.B200SGMError):   # no params yet
+        eng.compute(L, L)
+    eng.set_params(SGBMParams(numDisparities=64))
+    with pytest.raises(b200sgm.B200SGMError):   # exceeds max_disparities
+        eng.compute(L, L)
+    eng.set_params(SGBMParams(numDisparities=32))
+    with pytest.raises(b200sgm.B200SGMError):   # exceeds max size
+        eng.compute(np.zeros((80, 64), np.uint8), np.zeros((80, 64), np.uint8))
+    with pytest.raises(ValueError):             # "Images MUST be the same resolution"
+        eng.compute(L, np.zeros((32, 64), np.uint8))
+    eng.set_params(SGBMParams(numDisparities=0))
+    with pytest.raises(b200sgm.B200SGMError):
+        eng.compute(L, L)
+    eng.close()
+
+
+def test_config_c1_vs_oracle_and_golden_crc(golden_crc):
+    c = CONFIGS["c1"]
+    L, R = synth.make_pair(c.width, c.height, c.params.numDisparities, 0, 1000)
+    got = run_gpu(L, R, c.params)
+    assert synth.crc32(got) == golden_crc["c1"]["disp"]
+    assert np.array_equal(got, oracle.compute(L, R, c.params))
+    # the node's compiled-in default min_disparity (generate_disparity.cpp:100) and a negative one
+    for minD in (9, -32):
+        p = c.params.replace(minDisparity=minD)
+        L, R = synth.make_pair(c.width, c.height, 64, minD, 1001)
+        assert np.array_equal(run_gpu(L, R, p), oracle.compute(L, R, p))
+
+
+def test_config_c2_hh_golden_crc(golden_crc):
+    c = CONFIGS["c2"]
+    L, R = synth.make_pair(c.width, c.height, c.params.numDisparities, 0, 1000)
+    got = run_gpu(L, R, c.params)
+    assert synth.crc32(got) == golden_crc["c2"]["disp"]
+    assert int(got.astype(np.int64).sum()) == golden_crc["c2"]["disp_sum"]
+
+
+def test_config_c3_full_size_golden_crc_and_properties(golden_crc):
+    c = CONFIGS["c3"]
+    p = c.params
+    L, R = synth.make_pair(c.width, c.height, p.numDisparities, 0, 1000)
+    eng = Engine(0, c.width, c.height, p.numDisparities, 2, p)
+    got = eng.compute(L, R)
+    assert synth.crc32(got) == golden_crc["c3"]["disp"]
+    assert int(got.astype(np.int64).sum()) == golden_crc["c3"]["disp_sum"]
+    # size-independent properties: left band invalid, idempotent post filters, determinism across lanes
+    assert (got[:, :p.min_x1()] == p.invalid()).all()
+    out2 = np.empty_like(got)
+    eng.enqueue(1, L, R, out2); eng.wait(1)
+    assert np.array_equal(out2, got)
+    if ref.have_cv2():
+        import cv2
+        f = got.copy()
+        cv2.filterSpeckles(f, p.invalid(), p.speckleWindowSize, 16 * p.speckleRange)
+        assert np.array_equal(f, got)      # speckle filter is idempotent on its own output
+    eng.close()
+
+
+@pytest.mark.skipif(not ref.have_cv2(), reason="cv2 not importable")
+def test_live_cv2_reference_call_sequence():
+    """Same inputs through the reference's own call sequence on OpenCV (oracle/cv2_reference.py)."""
+    for name, seed in (("c1", 1234),):
+        c = CONFIGS[name]
+        L, R = synth.make_pair(c.width, c.height, c.params.numDisparities, 0, seed)
+        assert np.array_equal(run_gpu(L, R, c.params), ref.compute(L, R, c.params))
+
+
+def test_f32_output_and_streaming_lanes():
+    """a10: forwardMatch leaves CV_32FC1 holding the x16 value; lanes give identical results in any order."""
+    p = SGBMParams(numDisparities=64)
+    W, H = 320, 200
+    frames = [synth.make_pair(W, H, 64, 0, 50 + i) for i in range(6)]
+    want = [oracle.compute(L, R, p) for L, R in frames]
+    eng = Engine(0, W, H, 64, 3, p)
+    f32 = eng.compute_f32(*frames[0])
+    assert f32.dtype == np.float32 and np.array_equal(f32, oracle.to_float(want[0]))
+    outs = [np.empty((H, W), np.int16) for _ in frames]
+    for i, (L, R) in enumerate(frames):
+        if i >= 3:
+            eng.wait(i % 3)
+        eng.enqueue(i % 3, L, R, outs[i])
+    for ln in range(3):
+        eng.wait(ln)
+    for o, w in zip(outs, want):
+        assert np.array_equal(o, w)
+    eng.close()
+
+
+def test_device_resident_path_torch():
+    import torch
+    p = SGBMParams(numDisparities=64)
+    W, H = 320, 200
+    L, R = synth.make_pair(W, H, 64, 0, 77)
+    eng = Engine(0, W, H, 64, 1, p)
+    dL, dR = torch.from_numpy(L).cuda(), torch.from_numpy(R).cuda()
+    dD = torch.empty((H, W), dtype=torch.int16, device="cuda")
+    s = torch.cuda.Stream()
+    eng.compute_device(0, dL.data_ptr(), W, dR.data_ptr(), W, W, H, dD.data_ptr(), W * 2, stream=s.cuda_stream)
+    s.synchronize()
+    assert np.array_equal(dD.cpu().numpy(), oracle.compute(L, R, p))
+    eng.close()
+
+
+def test_reprojection_c5_style():
+    """Rows a11 + R: /16 + depth window + float32 reprojection, compacted row-major; exact float32 equality
+    (tolerance 0: the kernel uses non-contracted mul/add/div, IEEE round-to-nearest, like the x86 reference)."""
+    p = SGBMParams(numDisparities=64)
+    W, H = 320, 240
+    L, R = synth.make_pair(W, H, 64, 0, 11)
+    cam = b200sgm.C5_CAMERA
+    q = oracle.calc_q(cam["fx"], W / 2.0, W / 2.0, H / 2.0, cam["p14"])
+    fT = np.float32(0.3 * 2400.0)
+    min_disp = float(fT / np.float32(cam["depth_max"]))
+    eng = Engine(0, W, H, 64, 1, p)
+    disp, dmat, depth, pts, n = eng.compute_xyz(L, R, q, cam["depth_min"], cam["depth_max"], min_disp, float("inf"))
+    want = oracle.compute(L, R, p)
+    assert np.array_equal(disp, want)
+    wdm = oracle.process_disparity(want, min_disp, float("inf"))
+    assert np.array_equal(dmat, wdm)
+    wdepth, wpts = oracle.reproject(wdm, L, q, cam["depth_min"], cam["depth_max"])
+    assert n == wpts.shape[0] and n > 1000
+    assert np.array_equal(depth, wdepth)
+    assert np.array_equal(pts.view(np.uint32), wpts.view(np.uint32))
+    eng.close()
