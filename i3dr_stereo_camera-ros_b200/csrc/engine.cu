@@ -16,6 +16,7 @@
 #include "k_cost.cuh"
 #include "k_path.cuh"
 #include "k_wta.cuh"
+#include "k_fused.cuh"
 #include "k_post.cuh"
 
 using namespace b200sgm;
@@ -37,6 +38,11 @@ struct Lane {
     float4* points = nullptr;                       // W x H
     uint32_t *block_count = nullptr, *total = nullptr;
     uint32_t* h_total = nullptr;                    // pinned
+    uint16_t* xbuf = nullptr;                       // k_vert exchange records
+    int* flags = nullptr;                           // k_vert per-strip row flags (2 * kMaxStrips)
+    int* d_err = nullptr;                           // device error word of the fused kernels
+    int* h_err = nullptr;                           // pinned copy
+    cudaEvent_t coop_ev = nullptr;
     // stage profiling (b200sgm_profile): ring of event sets, harvested by b200sgm_stage_times
     std::vector<cudaEvent_t> prof_events;           // kProfRing * (kStages + 1)
     int prof_head = 0, prof_count = 0;
@@ -46,6 +52,8 @@ struct Lane {
 
 constexpr int kStages = 6;    // prefilter, cost, aggregate+wta, lrcheck, median, speckle
 constexpr int kProfRing = 256;
+constexpr int kMaxStrips = 1024;
+constexpr int kVertMaxWarps = 16;
 
 }  // namespace
 
@@ -60,6 +68,8 @@ struct b200sgm_engine {
     int path = 0;
     bool profile = false;
     int num_sms = 148;
+    cudaEvent_t coop_prev = nullptr;   // last cooperative (k_vert) launch of any lane: such kernels never overlap
+    int clock_khz = 1965000;
     std::mutex mu;
 };
 
@@ -165,15 +175,105 @@ int launch_paths_generic(b200sgm_engine* h, Lane& ln, const Eff& e, cudaStream_t
     return B200SGM_OK;
 }
 
+// ---- fused path: k_horiz + cooperative k_vert ---------------------------------------------------------
+struct VertPlan { bool ok; int nstrips, twmax; size_t smem; };
+
+VertPlan plan_vert(const b200sgm_engine* h, const Eff& e)
+{
+    VertPlan p{false, 0, 0, 0};
+    if (e.W1 < 2) return p;
+    int n = std::min(h->num_sms, e.W1 / 2);
+    n = std::min(n, kMaxStrips);
+    int tw = (e.W1 + n - 1) / n;
+    if (tw > kVertMaxWarps) return p;      // wider than one co-resident wave of strips: use the hybrid path
+    p.nstrips = n; p.twmax = tw;
+    p.smem = size_t(4) * (tw + 2) * e.Dp * sizeof(uint16_t) + size_t(4) * (tw + 2) * sizeof(uint32_t);
+    p.ok = p.smem <= 200 * 1024;
+    return p;
+}
+
+template <int N, bool UP, bool DO_WTA>
+int launch_vert(b200sgm_engine* h, Lane& ln, const Eff& e, const VertPlan& vp, cudaStream_t st)
+{
+    VertGeom g;
+    g.w = WtaGeom{e.W, e.H, e.W1, e.minX1, e.minD, e.D, e.Dp, e.uniq, e.d12, e.INVALID};
+    g.nstrips = vp.nstrips; g.twmax = vp.twmax;
+    g.P1x2 = uint32_t(e.P1) * 0x10001u; g.P2x2 = uint32_t(e.P2) * 0x10001u;
+    g.spin_limit = (long long)h->clock_khz * 500;   // ~0.5 s of SM clock ticks
+    auto kern = k_vert<N, UP, DO_WTA>;
+    CUDA_TRY(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(vp.smem)));
+    CUDA_TRY(h, cudaMemsetAsync(ln.flags, 0xFF, size_t(2) * kMaxStrips * sizeof(int), st));
+    const uint16_t* Cp = ln.C; uint16_t* Sp = ln.S; int16_t* dp = ln.disp_wta; uint32_t* kp = ln.disp2key;
+    uint16_t* xb = ln.xbuf; int* fl = ln.flags; int* er = ln.d_err;
+    void* args[] = {(void*)&Cp, (void*)&Sp, (void*)&g, (void*)&dp, (void*)&kp, (void*)&xb, (void*)&fl, (void*)&er};
+    {
+        std::lock_guard<std::mutex> lk(h->mu);
+        if (h->coop_prev) CUDA_TRY(h, cudaStreamWaitEvent(st, h->coop_prev, 0));
+        CUDA_TRY(h, cudaLaunchCooperativeKernel((void*)kern, dim3(vp.nstrips), dim3(32 * vp.twmax), args, vp.smem, st));
+        h->launches++;
+        CUDA_TRY(h, cudaEventRecord(ln.coop_ev, st));
+        h->coop_prev = ln.coop_ev;
+    }
+    return B200SGM_OK;
+}
+
+template <int N>
+int launch_fused(b200sgm_engine* h, Lane& ln, const Eff& e, cudaStream_t st, bool hybrid)
+{
+    const uint32_t P1x2 = uint32_t(e.P1) * 0x10001u, P2x2 = uint32_t(e.P2) * 0x10001u;
+    const int wpb = 4;
+    k_horiz<N><<<(e.H + wpb - 1) / wpb, 32 * wpb, 0, st>>>(ln.C, ln.S, e.W1, e.H, e.Dp, P1x2, P2x2);
+    LAUNCH_CHECK(h);
+    VertPlan vp = plan_vert(h, e);
+    if (hybrid || !vp.ok) {
+        static const int dirs_sgbm[3][2] = {{1, 1}, {0, 1}, {-1, 1}};
+        static const int dirs_hh[6][2] = {{1, 1}, {0, 1}, {-1, 1}, {-1, -1}, {0, -1}, {1, -1}};
+        const int nd = e.mode == B200SGM_MODE_HH ? 6 : 3;
+        for (int r = 0; r < nd; r++) {
+            PathGeom g;
+            g.W1 = e.W1; g.H = e.H; g.Dp = e.Dp;
+            g.dx = e.mode == B200SGM_MODE_HH ? dirs_hh[r][0] : dirs_sgbm[r][0];
+            g.dy = e.mode == B200SGM_MODE_HH ? dirs_hh[r][1] : dirs_sgbm[r][1];
+            g.nchains = chain_count(e.W1, e.H, g.dx, g.dy);
+            g.P1x2 = P1x2; g.P2x2 = P2x2;
+            k_path_generic<N, false><<<(g.nchains + wpb - 1) / wpb, 32 * wpb, 0, st>>>(ln.C, ln.S, g);
+            LAUNCH_CHECK(h);
+        }
+        WtaGeom wg{e.W, e.H, e.W1, e.minX1, e.minD, e.D, e.Dp, e.uniq, e.d12, e.INVALID};
+        const long long npix = (long long)e.W1 * e.H;
+        k_wta<N><<<unsigned((npix + 7) / 8), 256, 0, st>>>(ln.S, wg, ln.disp_wta, ln.disp2key);
+        LAUNCH_CHECK(h);
+        return B200SGM_OK;
+    }
+    int rc;
+    if (e.mode == B200SGM_MODE_HH) {
+        rc = launch_vert<N, false, false>(h, ln, e, vp, st);
+        if (rc) return rc;
+        rc = launch_vert<N, true, true>(h, ln, e, vp, st);
+    } else {
+        rc = launch_vert<N, false, true>(h, ln, e, vp, st);
+    }
+    if (rc) return rc;
+    CUDA_TRY(h, cudaMemcpyAsync(ln.h_err, ln.d_err, sizeof(int), cudaMemcpyDeviceToHost, st));
+    return B200SGM_OK;
+}
+
+template <int N>
+int launch_agg_n(b200sgm_engine* h, Lane& ln, const Eff& e, cudaStream_t st)
+{
+    if (h->path == 1) return launch_paths_generic<N>(h, ln, e, st);
+    return launch_fused<N>(h, ln, e, st, h->path == 2);
+}
+
 int launch_aggregation(b200sgm_engine* h, Lane& ln, const Eff& e, cudaStream_t st)
 {
     switch (e.nreg) {
-        case 1: return launch_paths_generic<1>(h, ln, e, st);
-        case 2: return launch_paths_generic<2>(h, ln, e, st);
-        case 4: return launch_paths_generic<4>(h, ln, e, st);
-        case 8: return launch_paths_generic<8>(h, ln, e, st);
-        case 16: return launch_paths_generic<16>(h, ln, e, st);
-        case 32: return launch_paths_generic<32>(h, ln, e, st);
+        case 1: return launch_agg_n<1>(h, ln, e, st);
+        case 2: return launch_agg_n<2>(h, ln, e, st);
+        case 4: return launch_agg_n<4>(h, ln, e, st);
+        case 8: return launch_agg_n<8>(h, ln, e, st);
+        case 16: return launch_agg_n<16>(h, ln, e, st);
+        case 32: return launch_agg_n<32>(h, ln, e, st);
     }
     return fail(h, B200SGM_EINVAL, "bad nreg");
 }
@@ -292,6 +392,9 @@ void free_lane(Lane& ln)
     cudaFree(ln.disp2key); cudaFree(ln.disp_wta); cudaFree(ln.disp_med); cudaFree(ln.disp_out); cudaFree(ln.label);
     cudaFree(ln.csize); cudaFree(ln.f32a); cudaFree(ln.f32b); cudaFree(ln.points); cudaFree(ln.block_count); cudaFree(ln.total);
     if (ln.h_total) cudaFreeHost(ln.h_total);
+    cudaFree(ln.xbuf); cudaFree(ln.flags); cudaFree(ln.d_err);
+    if (ln.h_err) cudaFreeHost(ln.h_err);
+    if (ln.coop_ev) cudaEventDestroy(ln.coop_ev);
     for (auto ev : ln.prof_events) cudaEventDestroy(ev);
     if (ln.done) cudaEventDestroy(ln.done);
     if (ln.stream) cudaStreamDestroy(ln.stream);
@@ -315,6 +418,7 @@ int b200sgm_create(int device, int max_width, int max_height, int max_disparitie
     b200sgm_engine* h = new b200sgm_engine();
     h->device = device; h->maxW = max_width; h->maxH = max_height; h->maxD = max_disparities;
     cudaDeviceGetAttribute(&h->num_sms, cudaDevAttrMultiProcessorCount, device);
+    cudaDeviceGetAttribute(&h->clock_khz, cudaDevAttrClockRate, device);
     const size_t npix = size_t(max_width) * max_height;
     const int nreg = nreg_for(max_disparities);
     const size_t Dp = size_t((max_disparities + 2 * nreg - 1) / (2 * nreg) * (2 * nreg));
@@ -334,6 +438,12 @@ int b200sgm_create(int device, int max_width, int max_height, int max_disparitie
         ok = ok && cudaMalloc(&ln.points, npix * sizeof(float4)) == cudaSuccess;
         ok = ok && cudaMalloc(&ln.block_count, ((npix + 255) / 256 + 1) * 4) == cudaSuccess && cudaMalloc(&ln.total, 4) == cudaSuccess;
         ok = ok && cudaMallocHost(&ln.h_total, 4) == cudaSuccess;
+        ok = ok && cudaMalloc(&ln.xbuf, size_t(2) * kMaxStrips * 2 * (Dp + kXbufTail) * sizeof(uint16_t)) == cudaSuccess;
+        ok = ok && cudaMalloc(&ln.flags, size_t(2) * kMaxStrips * sizeof(int)) == cudaSuccess;
+        ok = ok && cudaMalloc(&ln.d_err, sizeof(int)) == cudaSuccess && cudaMemset(ln.d_err, 0, sizeof(int)) == cudaSuccess;
+        ok = ok && cudaMallocHost(&ln.h_err, sizeof(int)) == cudaSuccess;
+        if (ok) *ln.h_err = 0;
+        ok = ok && cudaEventCreateWithFlags(&ln.coop_ev, cudaEventDisableTiming) == cudaSuccess;
         if (!ok) break;
     }
     if (!ok) {
@@ -430,6 +540,7 @@ int b200sgm_wait(b200sgm_handle h, int lane)
     ln.busy = false;
     CUDA_TRY(h, cudaEventSynchronize(ln.done));
     CUDA_TRY(h, cudaGetLastError());
+    if (*ln.h_err) return fail(h, B200SGM_ECUDA, "fused aggregation kernel: inter-strip flag wait timed out");
     return B200SGM_OK;
 }
 

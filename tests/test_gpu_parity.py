@@ -199,14 +199,15 @@ def test_reprojection_c5_style():
     cam = b200sgm.C5_CAMERA
     q = oracle.calc_q(cam["fx"], W / 2.0, W / 2.0, H / 2.0, cam["p14"])
     fT = np.float32(0.3 * 2400.0)
-    min_disp = float(fT / np.float32(cam["depth_max"]))
+    depth_max = 60.0   # D=64 only reaches 11 m and beyond at this focal length / baseline
+    min_disp = float(fT / np.float32(depth_max))
     eng = Engine(0, W, H, 64, 1, p)
-    disp, dmat, depth, pts, n = eng.compute_xyz(L, R, q, cam["depth_min"], cam["depth_max"], min_disp, float("inf"))
+    disp, dmat, depth, pts, n = eng.compute_xyz(L, R, q, cam["depth_min"], depth_max, min_disp, float("inf"))
     want = oracle.compute(L, R, p)
     assert np.array_equal(disp, want)
     wdm = oracle.process_disparity(want, min_disp, float("inf"))
     assert np.array_equal(dmat, wdm)
-    wdepth, wpts = oracle.reproject(wdm, L, q, cam["depth_min"], cam["depth_max"])
+    wdepth, wpts = oracle.reproject(wdm, L, q, cam["depth_min"], depth_max)
     assert n == wpts.shape[0] and n > 1000
     assert np.array_equal(depth, wdepth)
     assert np.array_equal(pts.view(np.uint32), wpts.view(np.uint32))
