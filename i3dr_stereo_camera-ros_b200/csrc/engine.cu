@@ -438,7 +438,7 @@ int b200sgm_create(int device, int max_width, int max_height, int max_disparitie
         ok = ok && cudaMalloc(&ln.points, npix * sizeof(float4)) == cudaSuccess;
         ok = ok && cudaMalloc(&ln.block_count, ((npix + 255) / 256 + 1) * 4) == cudaSuccess && cudaMalloc(&ln.total, 4) == cudaSuccess;
         ok = ok && cudaMallocHost(&ln.h_total, 4) == cudaSuccess;
-        ok = ok && cudaMalloc(&ln.xbuf, size_t(2) * kMaxStrips * 2 * (Dp + kXbufTail) * sizeof(uint16_t)) == cudaSuccess;
+        ok = ok && cudaMalloc(&ln.xbuf, size_t(2) * kMaxStrips * kXbufGen * (Dp + kXbufTail) * sizeof(uint16_t)) == cudaSuccess;
         ok = ok && cudaMalloc(&ln.flags, size_t(2) * kMaxStrips * sizeof(int)) == cudaSuccess;
         ok = ok && cudaMalloc(&ln.d_err, sizeof(int)) == cudaSuccess && cudaMemset(ln.d_err, 0, sizeof(int)) == cudaSuccess;
         ok = ok && cudaMallocHost(&ln.h_err, sizeof(int)) == cudaSuccess;

@@ -186,10 +186,14 @@ __device__ __forceinline__ int ld_acquire(const int* p)
     return v;
 }
 
-// exchange record = Dp costs + minimum; [side][strip][parity]
-__device__ __forceinline__ uint16_t* xrec(uint16_t* xbuf, int nstrips, int Dp, int side, int strip, int parity)
+// exchange record = Dp costs + minimum; [side][strip][row & 3].
+// Four generations are live at once: a strip publishes row R at the START of its row R, having only
+// waited (end of row R-1) for the neighbour to START row R-2 -- and that neighbour still reads our
+// record R-3 at the END of its row R-2.
+constexpr int kXbufGen = 4;
+__device__ __forceinline__ uint16_t* xrec(uint16_t* xbuf, int nstrips, int Dp, int side, int strip, int row)
 {
-    return xbuf + (size_t((side * nstrips + strip) * 2 + parity)) * (Dp + kXbufTail);
+    return xbuf + (size_t((side * nstrips + strip) * kXbufGen + (row & (kXbufGen - 1)))) * (Dp + kXbufTail);
 }
 
 template <int N, bool UP, bool DO_WTA>
@@ -262,7 +266,7 @@ __global__ void __launch_bounds__(512, 1) k_vert(const uint16_t* __restrict__ Cv
                 const bool pub = (left_edge && has_left_nb) || (right_edge && has_right_nb && dirA == 0);
                 if (pub) {
                     const int side = dirA;   // record side 1 = left-edge (<-down) values, side 0 = right-edge (->down) values
-                    uint16_t* rec = xrec(xbuf, n, Dp, side, b, cur);
+                    uint16_t* rec = xrec(xbuf, n, Dp, side, b, r);
                     if (active) st_regs<N>(rec + lane * 2 * N, LA);
                     if (lane == 0) *reinterpret_cast<uint32_t*>(rec + Dp) = mA;
                     __threadfence();
@@ -292,7 +296,7 @@ __global__ void __launch_bounds__(512, 1) k_vert(const uint16_t* __restrict__ Cv
                             }
                         }
                         dead = __shfl_sync(kFullMask, int(dead), 0) != 0;
-                        const uint16_t* rec = xrec(xbuf, n, Dp, side, nb, prv);
+                        const uint16_t* rec = xrec(xbuf, n, Dp, side, nb, r - 1);
                         if (active) {
                             if constexpr (N == 1) {
                                 LB[0] = __ldcg(reinterpret_cast<const uint32_t*>(rec + lane * 2));
@@ -325,7 +329,7 @@ __global__ void __launch_bounds__(512, 1) k_vert(const uint16_t* __restrict__ Cv
                 if (lane == 0) *md_ptr(cur, dirB, j + 1) = mB;
                 // a 2-column strip: the right edge also publishes its dir-0 values when it computed them as step B
                 if (right_edge && has_right_nb && dirB == 0) {
-                    uint16_t* rec = xrec(xbuf, n, Dp, 0, b, cur);
+                    uint16_t* rec = xrec(xbuf, n, Dp, 0, b, r);
                     if (active) st_regs<N>(rec + lane * 2 * N, LB);
                     if (lane == 0) *reinterpret_cast<uint32_t*>(rec + Dp) = mB;
                     __threadfence();
