@@ -38,8 +38,7 @@ struct Lane {
     float4* points = nullptr;                       // W x H
     uint32_t *block_count = nullptr, *total = nullptr;
     uint32_t* h_total = nullptr;                    // pinned
-    uint16_t* xbuf = nullptr;                       // k_vert exchange records
-    int* flags = nullptr;                           // k_vert per-strip row flags (2 * kMaxStrips)
+    uint2* xbuf = nullptr;                          // k_vert exchange records (LL protocol)
     int* d_err = nullptr;                           // device error word of the fused kernels
     int* h_err = nullptr;                           // pinned copy
     cudaEvent_t coop_ev = nullptr;
@@ -182,7 +181,8 @@ VertPlan plan_vert(const b200sgm_engine* h, const Eff& e)
 {
     VertPlan p{false, 0, 0, 0};
     if (e.W1 < 2) return p;
-    int n = std::min(h->num_sms, e.W1 / 2);
+    static const int per_sm = [] { const char* v = getenv("B200SGM_VERT_STRIPS_PER_SM"); return v ? std::max(1, atoi(v)) : 1; }();
+    int n = std::min(h->num_sms * per_sm, e.W1 / 2);
     n = std::min(n, kMaxStrips);
     int tw = (e.W1 + n - 1) / n;
     if (tw > kVertMaxWarps) return p;      // wider than one co-resident wave of strips: use the hybrid path
@@ -202,10 +202,10 @@ int launch_vert(b200sgm_engine* h, Lane& ln, const Eff& e, const VertPlan& vp, c
     g.spin_limit = (long long)h->clock_khz * 500;   // ~0.5 s of SM clock ticks
     auto kern = k_vert<N, UP, DO_WTA>;
     CUDA_TRY(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(vp.smem)));
-    CUDA_TRY(h, cudaMemsetAsync(ln.flags, 0xFF, size_t(2) * kMaxStrips * sizeof(int), st));
+    CUDA_TRY(h, cudaMemsetAsync(ln.xbuf, 0, size_t(2) * vp.nstrips * kXbufGen * (e.Dp / 2) * sizeof(uint2), st));
     const uint16_t* Cp = ln.C; uint16_t* Sp = ln.S; int16_t* dp = ln.disp_wta; uint32_t* kp = ln.disp2key;
-    uint16_t* xb = ln.xbuf; int* fl = ln.flags; int* er = ln.d_err;
-    void* args[] = {(void*)&Cp, (void*)&Sp, (void*)&g, (void*)&dp, (void*)&kp, (void*)&xb, (void*)&fl, (void*)&er};
+    uint2* xb = ln.xbuf; int* er = ln.d_err;
+    void* args[] = {(void*)&Cp, (void*)&Sp, (void*)&g, (void*)&dp, (void*)&kp, (void*)&xb, (void*)&er};
     {
         std::lock_guard<std::mutex> lk(h->mu);
         if (h->coop_prev) CUDA_TRY(h, cudaStreamWaitEvent(st, h->coop_prev, 0));
@@ -392,7 +392,7 @@ void free_lane(Lane& ln)
     cudaFree(ln.disp2key); cudaFree(ln.disp_wta); cudaFree(ln.disp_med); cudaFree(ln.disp_out); cudaFree(ln.label);
     cudaFree(ln.csize); cudaFree(ln.f32a); cudaFree(ln.f32b); cudaFree(ln.points); cudaFree(ln.block_count); cudaFree(ln.total);
     if (ln.h_total) cudaFreeHost(ln.h_total);
-    cudaFree(ln.xbuf); cudaFree(ln.flags); cudaFree(ln.d_err);
+    cudaFree(ln.xbuf); cudaFree(ln.d_err);
     if (ln.h_err) cudaFreeHost(ln.h_err);
     if (ln.coop_ev) cudaEventDestroy(ln.coop_ev);
     for (auto ev : ln.prof_events) cudaEventDestroy(ev);
@@ -438,8 +438,7 @@ int b200sgm_create(int device, int max_width, int max_height, int max_disparitie
         ok = ok && cudaMalloc(&ln.points, npix * sizeof(float4)) == cudaSuccess;
         ok = ok && cudaMalloc(&ln.block_count, ((npix + 255) / 256 + 1) * 4) == cudaSuccess && cudaMalloc(&ln.total, 4) == cudaSuccess;
         ok = ok && cudaMallocHost(&ln.h_total, 4) == cudaSuccess;
-        ok = ok && cudaMalloc(&ln.xbuf, size_t(2) * kMaxStrips * kXbufGen * (Dp + kXbufTail) * sizeof(uint16_t)) == cudaSuccess;
-        ok = ok && cudaMalloc(&ln.flags, size_t(2) * kMaxStrips * sizeof(int)) == cudaSuccess;
+        ok = ok && cudaMalloc(&ln.xbuf, size_t(2) * kMaxStrips * kXbufGen * (Dp / 2) * sizeof(uint2)) == cudaSuccess;
         ok = ok && cudaMalloc(&ln.d_err, sizeof(int)) == cudaSuccess && cudaMemset(ln.d_err, 0, sizeof(int)) == cudaSuccess;
         ok = ok && cudaMallocHost(&ln.h_err, sizeof(int)) == cudaSuccess;
         if (ok) *ln.h_err = 0;

@@ -177,29 +177,32 @@ struct VertGeom {
     long long spin_limit; // clock64 ticks before a flag wait gives up
 };
 
-constexpr int kXbufTail = 8;  // uint16 slots after the Dp costs of an exchange record (holds the minimum)
-
-__device__ __forceinline__ int ld_acquire(const int* p)
-{
-    int v;
-    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-    return v;
-}
-
-// exchange record = Dp costs + minimum; [side][strip][row & 3].
+// Inter-strip exchange, "low latency" protocol: a record is Dp/2 entries of {two packed costs, tag}; each
+// entry is one 8-byte volatile store, so data and flag arrive together and no fence or separate flag is
+// needed.  tag = row + 1 (the buffer is zeroed before the launch).  [side][strip][row & 3][Dp/2] uint2.
 // Four generations are live at once: a strip publishes row R at the START of its row R, having only
-// waited (end of row R-1) for the neighbour to START row R-2 -- and that neighbour still reads our
-// record R-3 at the END of its row R-2.
+// waited (end of row R-1) for the neighbour's record R-2 -- and that neighbour still reads our record
+// R-3 at the END of its row R-2.
 constexpr int kXbufGen = 4;
-__device__ __forceinline__ uint16_t* xrec(uint16_t* xbuf, int nstrips, int Dp, int side, int strip, int row)
+__device__ __forceinline__ uint2* xrec(uint2* xbuf, int nstrips, int Dp, int side, int strip, int row)
 {
-    return xbuf + (size_t((side * nstrips + strip) * kXbufGen + (row & (kXbufGen - 1)))) * (Dp + kXbufTail);
+    return xbuf + (size_t((side * nstrips + strip) * kXbufGen + (row & (kXbufGen - 1)))) * (Dp / 2);
+}
+__device__ __forceinline__ void st_volatile_v2(uint2* p, uint32_t a, uint32_t b)
+{
+    asm volatile("st.volatile.global.v2.u32 [%0], {%1, %2};" ::"l"(p), "r"(a), "r"(b) : "memory");
+}
+__device__ __forceinline__ uint2 ld_volatile_v2(const uint2* p)
+{
+    uint2 v;
+    asm volatile("ld.volatile.global.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p) : "memory");
+    return v;
 }
 
 template <int N, bool UP, bool DO_WTA>
 __global__ void __launch_bounds__(512, 1) k_vert(const uint16_t* __restrict__ Cvol, uint16_t* __restrict__ Svol, VertGeom g,
                                                   int16_t* __restrict__ disp, uint32_t* __restrict__ disp2key,
-                                                  uint16_t* __restrict__ xbuf, int* __restrict__ flags, int* __restrict__ err)
+                                                  uint2* __restrict__ xbuf, int* __restrict__ err)
 {
     extern __shared__ __align__(16) uint16_t smem_v[];
     const int W1 = g.w.W1, H = g.w.H, Dp = g.w.Dp;
@@ -218,8 +221,6 @@ __global__ void __launch_bounds__(512, 1) k_vert(const uint16_t* __restrict__ Cv
     const int x = x0 + j;
     const bool left_edge = col && j == 0, right_edge = col && j == TW - 1;
     const bool has_left_nb = b > 0, has_right_nb = b < n - 1;
-    int* flagL = flags;          // flagL[s]: last row for which strip s published its LEFT-edge diagonal (<-down)
-    int* flagR = flags + n;      // flagR[s]: ... RIGHT-edge diagonal (->down)
 
     uint32_t Lv[N], Cc[N], Cn[N], Sc[N], Sn[N];
 #pragma unroll
@@ -264,14 +265,11 @@ __global__ void __launch_bounds__(512, 1) k_vert(const uint16_t* __restrict__ Cv
                 if (lane == 0) *md_ptr(cur, dirA, j + 1) = mA;
                 // publish to the neighbouring strip: left edge sends dir 1 to strip b-1, right edge sends dir 0 to b+1
                 const bool pub = (left_edge && has_left_nb) || (right_edge && has_right_nb && dirA == 0);
-                if (pub) {
-                    const int side = dirA;   // record side 1 = left-edge (<-down) values, side 0 = right-edge (->down) values
-                    uint16_t* rec = xrec(xbuf, n, Dp, side, b, r);
-                    if (active) st_regs<N>(rec + lane * 2 * N, LA);
-                    if (lane == 0) *reinterpret_cast<uint32_t*>(rec + Dp) = mA;
-                    __threadfence();
-                    __syncwarp();
-                    if (lane == 0) *reinterpret_cast<volatile int*>((side ? flagL : flagR) + b) = r;
+                if (pub && active) {
+                    // record side 1 = left-edge (<-down) values, side 0 = right-edge (->down) values
+                    uint2* rec = xrec(xbuf, n, Dp, dirA, b, r) + lane * N;
+#pragma unroll
+                    for (int q = 0; q < N; q++) st_volatile_v2(rec + q, LA[q], uint32_t(r + 1));
                 }
             }
             // ---- vertical path: registers only
@@ -286,35 +284,32 @@ __global__ void __launch_bounds__(512, 1) k_vert(const uint16_t* __restrict__ Cv
                     const bool halo = (dirB == 0 && j == 0) || (dirB == 1 && j == TW - 1);
                     if (halo) {
                         const int nb = dirB == 0 ? b - 1 : b + 1;
-                        const int side = dirB == 0 ? 0 : 1;   // want nb's right-edge (side 0) or left-edge (side 1) values
-                        const int* fl = (side ? flagL : flagR) + nb;
-                        if (lane == 0 && !dead) {
-                            const long long t0 = clock64();
-                            while (ld_acquire(fl) < r - 1) {
-                                if (clock64() - t0 > g.spin_limit) { atomicExch(err, 1); dead = true; break; }
-                                if (*reinterpret_cast<volatile int*>(err)) { dead = true; break; }
-                            }
-                        }
-                        dead = __shfl_sync(kFullMask, int(dead), 0) != 0;
-                        const uint16_t* rec = xrec(xbuf, n, Dp, side, nb, r - 1);
-                        if (active) {
-                            if constexpr (N == 1) {
-                                LB[0] = __ldcg(reinterpret_cast<const uint32_t*>(rec + lane * 2));
-                            } else if constexpr (N == 2) {
-                                uint2 v = __ldcg(reinterpret_cast<const uint2*>(rec + lane * 4));
-                                LB[0] = v.x; LB[1] = v.y;
-                            } else {
+                        // want nb's right-edge record (side 0) for direction 0, its left-edge record (side 1) for direction 1
+                        const uint2* rec = xrec(xbuf, n, Dp, dirB, nb, r - 1) + lane * N;
 #pragma unroll
-                                for (int q = 0; q < N / 4; q++) {
-                                    uint4 v = __ldcg(reinterpret_cast<const uint4*>(rec + lane * 2 * N) + q);
-                                    LB[4 * q] = v.x; LB[4 * q + 1] = v.y; LB[4 * q + 2] = v.z; LB[4 * q + 3] = v.w;
+                        for (int q = 0; q < N; q++) LB[q] = kMaxCostX2;
+                        if (active && !dead) {
+                            const long long t0 = clock64();
+                            int spins = 0;
+                            while (true) {
+                                bool ok = true;
+#pragma unroll
+                                for (int q = 0; q < N; q++) {
+                                    uint2 v = ld_volatile_v2(rec + q);
+                                    LB[q] = v.x;
+                                    ok = ok && v.y == uint32_t(r);
+                                }
+                                if (ok) break;
+                                if ((++spins & 255) == 0 &&
+                                    (clock64() - t0 > g.spin_limit || *reinterpret_cast<volatile int*>(err))) {
+                                    atomicExch(err, 1);
+                                    dead = true;
+                                    break;
                                 }
                             }
-                        } else {
-#pragma unroll
-                            for (int q = 0; q < N; q++) LB[q] = kMaxCostX2;
                         }
-                        mB = __ldcg(reinterpret_cast<const uint32_t*>(rec + Dp));
+                        dead = __any_sync(kFullMask, dead);
+                        mB = warp_min16<N>(LB);
                     } else {
                         if (active) ld_regs<N>(ld_ptr(prv, dirB, slot), LB);
                         else {
@@ -327,15 +322,6 @@ __global__ void __launch_bounds__(512, 1) k_vert(const uint16_t* __restrict__ Cv
                 path_step<N>(Cc, LB, mB, g.P1x2, g.P2x2, lane);
                 if (active) st_regs<N>(ld_ptr(cur, dirB, j + 1), LB);
                 if (lane == 0) *md_ptr(cur, dirB, j + 1) = mB;
-                // a 2-column strip: the right edge also publishes its dir-0 values when it computed them as step B
-                if (right_edge && has_right_nb && dirB == 0) {
-                    uint16_t* rec = xrec(xbuf, n, Dp, 0, b, r);
-                    if (active) st_regs<N>(rec + lane * 2 * N, LB);
-                    if (lane == 0) *reinterpret_cast<uint32_t*>(rec + Dp) = mB;
-                    __threadfence();
-                    __syncwarp();
-                    if (lane == 0) *reinterpret_cast<volatile int*>(flagR + b) = r;
-                }
             }
             // ---- sum: S = sat(S_h + L_v + L_A + L_B)
             uint32_t S[N];
