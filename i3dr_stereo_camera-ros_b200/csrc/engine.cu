@@ -33,7 +33,7 @@ struct Lane {
     uint16_t *C = nullptr, *S = nullptr;            // [H][W1][Dp]
     uint32_t* disp2key = nullptr;                   // W x H
     int16_t *disp_wta = nullptr, *disp_med = nullptr, *disp_out = nullptr;  // W x H
-    int *label = nullptr, *csize = nullptr;         // W x H
+    int *label = nullptr, *csize = nullptr, *parent = nullptr, *runlen = nullptr;   // W x H (speckle filter)
     float *f32a = nullptr, *f32b = nullptr;         // W x H (dmat / depth / CV_32F disparity)
     float4* points = nullptr;                       // W x H
     uint32_t *block_count = nullptr, *total = nullptr;
@@ -325,21 +325,31 @@ int run_pipeline(b200sgm_engine* h, Lane& ln, const Eff& e, const uint8_t* dL, s
     LAUNCH_CHECK(h);
     prof_mark(h, ln, 1, st);
     if (e.W1 > 0) {
-        CostGeom cg;
-        cg.W = W; cg.H = H; cg.W1 = e.W1; cg.minX1 = e.minX1; cg.minD = e.minD; cg.D = e.D; cg.Dp = e.Dp; cg.SW2 = e.SW2;
-        int TX = 32, DCP = 32;
-        while (DCP * 2 > e.Dp && DCP > 1) DCP /= 2;
-        const size_t limit = 200 * 1024;
-        while (cost_smem_bytes(TX, DCP, e.SW2) > limit && TX > 4) TX /= 2;
-        while (cost_smem_bytes(TX, DCP, e.SW2) > limit && DCP > 4) DCP /= 2;
-        while (cost_smem_bytes(TX, DCP, e.SW2) > limit && TX > 1) TX /= 2;
-        if (cost_smem_bytes(TX, DCP, e.SW2) > limit) return fail(h, B200SGM_EINVAL, "blockSize too large for the cost kernel");
-        cg.TX = TX; cg.DCP = DCP; cg.RS = 64;
-        const size_t smem = cost_smem_bytes(TX, DCP, e.SW2);
-        CUDA_TRY(h, cudaFuncSetAttribute(k_cost_generic, cudaFuncAttributeMaxDynamicSharedMemorySize, int(limit)));
-        dim3 grid((e.W1 + TX - 1) / TX, (e.Dp / 2 + DCP - 1) / DCP, (H + cg.RS - 1) / cg.RS);
-        k_cost_generic<<<grid, 256, smem, st>>>(ln.feat_l, ln.feat_r, ln.C, cg);
-        LAUNCH_CHECK(h);
+        if (e.SW2 <= 10 && h->path != 1) {
+            CostFastGeom fg{W, H, e.W1, e.minX1, e.minD, e.D, e.Dp, e.SW2, 128};
+            const size_t smem = cost_fast_smem(e.SW2);
+            CUDA_TRY(h, cudaFuncSetAttribute(k_cost_fast, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+            const int TX = kCfTXH - 2 * e.SW2;
+            dim3 grid((e.W1 + TX - 1) / TX, (e.Dp / 2 + kCfDCP - 1) / kCfDCP, (H + fg.RS - 1) / fg.RS);
+            k_cost_fast<<<grid, 256, smem, st>>>(ln.feat_l, ln.feat_r, ln.C, fg);
+            LAUNCH_CHECK(h);
+        } else {
+            CostGeom cg;
+            cg.W = W; cg.H = H; cg.W1 = e.W1; cg.minX1 = e.minX1; cg.minD = e.minD; cg.D = e.D; cg.Dp = e.Dp; cg.SW2 = e.SW2;
+            int TX = 32, DCP = 32;
+            while (DCP * 2 > e.Dp && DCP > 1) DCP /= 2;
+            const size_t limit = 200 * 1024;
+            while (cost_smem_bytes(TX, DCP, e.SW2) > limit && TX > 4) TX /= 2;
+            while (cost_smem_bytes(TX, DCP, e.SW2) > limit && DCP > 4) DCP /= 2;
+            while (cost_smem_bytes(TX, DCP, e.SW2) > limit && TX > 1) TX /= 2;
+            if (cost_smem_bytes(TX, DCP, e.SW2) > limit) return fail(h, B200SGM_EINVAL, "blockSize too large for the cost kernel");
+            cg.TX = TX; cg.DCP = DCP; cg.RS = 64;
+            const size_t smem = cost_smem_bytes(TX, DCP, e.SW2);
+            CUDA_TRY(h, cudaFuncSetAttribute(k_cost_generic, cudaFuncAttributeMaxDynamicSharedMemorySize, int(limit)));
+            dim3 grid((e.W1 + TX - 1) / TX, (e.Dp / 2 + DCP - 1) / DCP, (H + cg.RS - 1) / cg.RS);
+            k_cost_generic<<<grid, 256, smem, st>>>(ln.feat_l, ln.feat_r, ln.C, cg);
+            LAUNCH_CHECK(h);
+        }
     }
     prof_mark(h, ln, 2, st);
     if (e.W1 > 0) {
@@ -363,14 +373,14 @@ int run_pipeline(b200sgm_engine* h, Lane& ln, const Eff& e, const uint8_t* dL, s
     CUDA_TRY(h, cudaMemcpyAsync(ln.disp_out, ln.disp_med, size_t(npix) * 2, cudaMemcpyDeviceToDevice, st));
     if (e.speckleWin > 0) {
         const int maxDiff = 16 * e.speckleRange;
-        k_speckle_init<<<(npix + 255) / 256, 256, 0, st>>>(ln.disp_out, ln.label, ln.csize, npix, e.INVALID);
+        k_speckle_runs<<<H, 256, 0, st>>>(ln.disp_out, ln.label, ln.parent, ln.runlen, ln.csize, W, e.INVALID, maxDiff);
         LAUNCH_CHECK(h);
         dim3 block(256), grid((W + 255) / 256, H);
-        k_speckle_merge<<<grid, block, 0, st>>>(ln.disp_out, ln.label, W, H, e.INVALID, maxDiff);
+        k_speckle_vmerge<<<grid, block, 0, st>>>(ln.disp_out, ln.label, ln.parent, W, H, e.INVALID, maxDiff);
         LAUNCH_CHECK(h);
-        k_speckle_count<<<(npix + 255) / 256, 256, 0, st>>>(ln.label, ln.csize, npix);
+        k_speckle_size<<<(npix + 255) / 256, 256, 0, st>>>(ln.label, ln.parent, ln.runlen, ln.csize, npix);
         LAUNCH_CHECK(h);
-        k_speckle_apply<<<(npix + 255) / 256, 256, 0, st>>>(ln.disp_out, ln.label, ln.csize, npix, e.INVALID, e.speckleWin);
+        k_speckle_apply<<<(npix + 255) / 256, 256, 0, st>>>(ln.disp_out, ln.label, ln.parent, ln.csize, npix, e.INVALID, e.speckleWin);
         LAUNCH_CHECK(h);
     }
     prof_mark(h, ln, 6, st);
@@ -390,7 +400,7 @@ void free_lane(Lane& ln)
 {
     cudaFree(ln.left); cudaFree(ln.right); cudaFree(ln.feat_l); cudaFree(ln.feat_r); cudaFree(ln.C); cudaFree(ln.S);
     cudaFree(ln.disp2key); cudaFree(ln.disp_wta); cudaFree(ln.disp_med); cudaFree(ln.disp_out); cudaFree(ln.label);
-    cudaFree(ln.csize); cudaFree(ln.f32a); cudaFree(ln.f32b); cudaFree(ln.points); cudaFree(ln.block_count); cudaFree(ln.total);
+    cudaFree(ln.csize); cudaFree(ln.parent); cudaFree(ln.runlen); cudaFree(ln.f32a); cudaFree(ln.f32b); cudaFree(ln.points); cudaFree(ln.block_count); cudaFree(ln.total);
     if (ln.h_total) cudaFreeHost(ln.h_total);
     cudaFree(ln.xbuf); cudaFree(ln.d_err);
     if (ln.h_err) cudaFreeHost(ln.h_err);
@@ -434,6 +444,7 @@ int b200sgm_create(int device, int max_width, int max_height, int max_disparitie
         ok = ok && cudaMalloc(&ln.disp2key, npix * 4) == cudaSuccess;
         ok = ok && cudaMalloc(&ln.disp_wta, npix * 2) == cudaSuccess && cudaMalloc(&ln.disp_med, npix * 2) == cudaSuccess && cudaMalloc(&ln.disp_out, npix * 2) == cudaSuccess;
         ok = ok && cudaMalloc(&ln.label, npix * 4) == cudaSuccess && cudaMalloc(&ln.csize, npix * 4) == cudaSuccess;
+        ok = ok && cudaMalloc(&ln.parent, npix * 4) == cudaSuccess && cudaMalloc(&ln.runlen, npix * 4) == cudaSuccess;
         ok = ok && cudaMalloc(&ln.f32a, npix * 4) == cudaSuccess && cudaMalloc(&ln.f32b, npix * 4) == cudaSuccess;
         ok = ok && cudaMalloc(&ln.points, npix * sizeof(float4)) == cudaSuccess;
         ok = ok && cudaMalloc(&ln.block_count, ((npix + 255) / 256 + 1) * 4) == cudaSuccess && cudaMalloc(&ln.total, 4) == cudaSuccess;

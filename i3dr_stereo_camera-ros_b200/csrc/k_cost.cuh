@@ -134,4 +134,146 @@ __global__ void __launch_bounds__(256) k_cost_generic(const Feat* __restrict__ f
     }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// A.3 + A.4, fast version (blockSize <= 21).  One CTA (256 threads) owns a tile of 64 x1-columns (56 output
+// columns + the 2*SW2 halo for blockSize 9) x 32 disparity pairs and slides down a segment of rows.
+//
+// Per entering row:
+//   stage   : the row's prefiltered pixels are repacked into shared memory as signed 16x2 operands:
+//             right image: for every xr the pair (f[xr], f[xr-1]) that a disparity pair (d, d+1) needs;
+//             left image: every field replicated into both halves.  The raw channel is pre-scaled by 64
+//             so that (cost >> 2) is the high byte of each half (one PRMT).
+//   phase 1 : lanes <-> columns.  Birchfield-Tomasi cost of a disparity pair = 2 x {VIADD.16x2,
+//             VIADDMNMX.S16x2.RELU, VIADD.16x2, VIADDMNMX.S16x2.RELU, VIMNMX} + PRMT + IADD; the vertical
+//             sliding sum lives in registers, the ring of the last `bs` rows in shared memory.
+//   phase 2 : lanes <-> disparity pairs.  Sliding horizontal sum over the vertical sums, coalesced
+//             128-byte stores of C[y][x1][k0 .. k0+64).
+// ------------------------------------------------------------------------------------------------
+struct CostFastGeom {
+    int W, H, W1, minX1, minD, D, Dp, SW2, RS;
+};
+
+constexpr int kCfTXH = 64;    // tile columns incl. halo
+constexpr int kCfDCP = 32;    // disparity pairs per CTA
+constexpr int kCfNRP = 128;   // right-image pair records per row (>= TXH + 2*DCP - 2)
+constexpr int kCfPPT = 8;     // disparity pairs per thread in phase 1
+
+inline size_t cost_fast_smem(int SW2)
+{
+    const int bs = 2 * SW2 + 1;
+    return size_t(2) * (2 * kCfNRP + 2 * kCfTXH) * sizeof(uint4) + size_t(kCfDCP) * (kCfTXH + 1) * 4 +
+           size_t(bs) * kCfDCP * kCfTXH * 4;
+}
+
+__device__ __forceinline__ uint32_t pk16(int a, int b) { return (uint32_t(a) & 0xFFFFu) | (uint32_t(b) << 16); }
+
+__global__ void __launch_bounds__(256, 2) k_cost_fast(const Feat* __restrict__ fl, const Feat* __restrict__ fr,
+                                                      uint16_t* __restrict__ Cvol, CostFastGeom g)
+{
+    extern __shared__ uint4 cf_smem[];
+    const int bs = 2 * g.SW2 + 1;
+    const int TX = kCfTXH - 2 * g.SW2;
+    uint4* Rs = cf_smem;                       // [2][NRP]  sobel: (v, lo, -hi, -v) pairs
+    uint4* Rr = Rs + 2 * kCfNRP;               // [2][NRP]  raw x64
+    uint4* Ls = Rr + 2 * kCfNRP;               // [2][TXH]  sobel: (u, -u, lo, -hi) replicated
+    uint4* Lr = Ls + 2 * kCfTXH;               // [2][TXH]  raw x64
+    uint32_t* vs = reinterpret_cast<uint32_t*>(Lr + 2 * kCfTXH);   // [DCP][TXH+1]
+    uint32_t* ring = vs + kCfDCP * (kCfTXH + 1);                    // [bs][DCP][TXH]
+
+    const int t = threadIdx.x, lane = t & 31, w = t >> 5;
+    const int tx0 = blockIdx.x * TX;
+    const int k0 = blockIdx.y * kCfDCP * 2;
+    const int ya = blockIdx.z * g.RS, yb = min(ya + g.RS, g.H);
+    auto col_x = [&](int c) { return min(max(tx0 - g.SW2 + c, 0), g.W1 - 1) + g.minX1; };
+    const int xr_min = col_x(0) - g.minD - k0 - 2 * (kCfDCP - 1);
+    const int nR = col_x(kCfTXH - 1) - col_x(0) + 2 * (kCfDCP - 1) + 1;
+
+    // phase-1 role
+    const int col = (w & 1) * 32 + lane, pg = w >> 1;
+    const int rbase = col_x(col) - g.minD - k0 - xr_min;   // record index of pair p: rbase - 2p
+    uint32_t V[kCfPPT];
+#pragma unroll
+    for (int i = 0; i < kCfPPT; i++) V[i] = 0;
+    for (int i = t; i < bs * kCfDCP * kCfTXH; i += 256) ring[i] = 0;
+
+    auto stage = [&](int s, int buf) {
+        const int e = min(max(ya - g.SW2 + s, 0), g.H - 1);
+        if (t < nR) {
+            const int xr = xr_min + t;
+            const Feat a = __ldg(fr + size_t(e) * g.W + min(max(xr, 0), g.W - 1));
+            const Feat b = __ldg(fr + size_t(e) * g.W + min(max(xr - 1, 0), g.W - 1));
+            int va = a.x & 0xFF, la = (a.x >> 8) & 0xFF, ha = (a.x >> 16) & 0xFF;
+            int vb = b.x & 0xFF, lb = (b.x >> 8) & 0xFF, hb = (b.x >> 16) & 0xFF;
+            Rs[buf * kCfNRP + t] = make_uint4(pk16(va, vb), pk16(la, lb), pk16(-ha, -hb), pk16(-va, -vb));
+            va = (a.x >> 24) * 64; la = (a.y & 0xFF) * 64; ha = ((a.y >> 8) & 0xFF) * 64;
+            vb = (b.x >> 24) * 64; lb = (b.y & 0xFF) * 64; hb = ((b.y >> 8) & 0xFF) * 64;
+            Rr[buf * kCfNRP + t] = make_uint4(pk16(va, vb), pk16(la, lb), pk16(-ha, -hb), pk16(-va, -vb));
+        } else if (t >= 128 && t < 128 + kCfTXH) {
+            const int c = t - 128;
+            const Feat a = __ldg(fl + size_t(e) * g.W + col_x(c));
+            int u = a.x & 0xFF, lo = (a.x >> 8) & 0xFF, hi = (a.x >> 16) & 0xFF;
+            Ls[buf * kCfTXH + c] = make_uint4(pk16(u, u), pk16(-u, -u), pk16(lo, lo), pk16(-hi, -hi));
+            u = (a.x >> 24) * 64; lo = (a.y & 0xFF) * 64; hi = ((a.y >> 8) & 0xFF) * 64;
+            Lr[buf * kCfTXH + c] = make_uint4(pk16(u, u), pk16(-u, -u), pk16(lo, lo), pk16(-hi, -hi));
+        }
+    };
+
+    stage(0, 0);
+    __syncthreads();
+    const int nsteps = (yb - ya) + bs - 1;
+    // phase-2 role: lanes <-> pairs, warp -> run of output columns
+    const int cpw = (TX + 7) / 8;
+    const int c_lo = w * cpw, c_hi = min(c_lo + cpw, TX);
+    const int kk = k0 + 2 * lane;
+    const uint32_t pad_or = kk >= g.D ? kMaxCostX2 : (kk + 1 >= g.D ? (uint32_t(kMaxCost) << 16) : 0u);
+    const uint32_t pad_and = kk >= g.D ? 0u : (kk + 1 >= g.D ? 0x0000FFFFu : 0xFFFFFFFFu);
+
+    for (int s = 0; s < nsteps; s++) {
+        const int buf = s & 1;
+        // ---- phase 1
+        {
+            const uint4 ls = Ls[buf * kCfTXH + col], lr = Lr[buf * kCfTXH + col];
+            uint32_t* rrow = ring + size_t(s % bs) * kCfDCP * kCfTXH + col;
+            const uint4* rs_p = Rs + buf * kCfNRP + rbase;
+            const uint4* rr_p = Rr + buf * kCfNRP + rbase;
+#pragma unroll
+            for (int i = 0; i < kCfPPT; i++) {
+                const int p = pg + 4 * i;
+                const uint4 rs = rs_p[-2 * p], rr = rr_p[-2 * p];
+                uint32_t X = __vadd2(rs.y, ls.y);
+                uint32_t c0 = __viaddmax_s16x2_relu(ls.x, rs.z, X);
+                uint32_t Y = __vadd2(ls.z, rs.w);
+                uint32_t c1 = __viaddmax_s16x2_relu(rs.x, ls.w, Y);
+                const uint32_t cs = __vmins2(c0, c1);
+                X = __vadd2(rr.y, lr.y);
+                c0 = __viaddmax_s16x2_relu(lr.x, rr.z, X);
+                Y = __vadd2(lr.z, rr.w);
+                c1 = __viaddmax_s16x2_relu(rr.x, lr.w, Y);
+                const uint32_t cr = __vmins2(c0, c1);
+                const uint32_t pd = cs + __byte_perm(cr, 0, 0x4341);   // + (cost_raw >> 2)
+                const uint32_t old = rrow[p * kCfTXH];
+                rrow[p * kCfTXH] = pd;
+                V[i] = V[i] + pd - old;
+                vs[p * (kCfTXH + 1) + col] = V[i];
+            }
+        }
+        __syncthreads();
+        // ---- phase 2 (once the vertical window is full) + staging of the next row
+        if (s >= bs - 1 && c_lo < c_hi) {
+            const int y = ya + s - (bs - 1);
+            const uint32_t* vrow = vs + lane * (kCfTXH + 1);
+            uint32_t hs = 0;
+            for (int jj = 0; jj < bs; jj++) hs += vrow[c_lo + jj];
+            for (int c = c_lo; c < c_hi; c++) {
+                if (c > c_lo) hs = hs + vrow[c + bs - 1] - vrow[c - 1];
+                if (tx0 + c < g.W1 && kk < g.Dp)
+                    *reinterpret_cast<uint32_t*>(Cvol + (size_t(y) * g.W1 + tx0 + c) * g.Dp + kk) = (hs & pad_and) | pad_or;
+            }
+        }
+        if (s + 1 < nsteps) stage(s + 1, buf ^ 1);
+        __syncthreads();
+    }
+}
+
 }  // namespace b200sgm

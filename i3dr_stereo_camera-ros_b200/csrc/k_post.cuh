@@ -56,45 +56,99 @@ __device__ __forceinline__ void uf_union(int* L, int a, int b)
     }
 }
 
-__global__ void k_speckle_init(const int16_t* __restrict__ img, int* __restrict__ label, int* __restrict__ size,
-                               int n, int newVal)
+// Run-based labelling: every maximal horizontal run of connected pixels is one union-find node (its first
+// pixel).  k_speckle_runs labels the runs of one image row per CTA and records their lengths, k_speckle_vmerge
+// unites vertically touching runs (one union per touching run pair segment), k_speckle_size adds each run's
+// length to its root, k_speckle_apply overwrites small components.
+//   label[p]  : pixel index of the run start of p (or -1 for invalid pixels)
+//   parent[p] : union-find parent, meaningful at run starts only
+//   runlen[p] : run length, at run starts only;  csize[p]: component size, at roots only
+__global__ void __launch_bounds__(256) k_speckle_runs(const int16_t* __restrict__ img, int* __restrict__ label,
+                                                      int* __restrict__ parent, int* __restrict__ runlen,
+                                                      int* __restrict__ csize, int W, int newVal, int maxDiff)
 {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    label[i] = img[i] == newVal ? -1 : i;
-    size[i] = 0;
+    __shared__ int warp_last[8];
+    const int y = blockIdx.x, t = threadIdx.x, lane = t & 31, wid = t >> 5;
+    const int16_t* row = img + size_t(y) * W;
+    const int base = y * W;
+    const int ppt = (W + 255) / 256;
+    const int xa = t * ppt, xb = min(xa + ppt, W);
+    // pass 1: last run start inside my segment
+    int last = -1;
+    const int prev = (xa > 0 && xa < W) ? int(row[xa - 1]) : newVal;
+    int pv = prev;
+    for (int x = xa; x < xb; x++) {
+        const int v = row[x];
+        const bool valid = v != newVal;
+        const bool start = valid && !(pv != newVal && abs(v - pv) <= maxDiff);
+        if (start) last = x;
+        pv = v;
+    }
+    // block-wide exclusive max-scan of `last`
+    int inc = last;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { int n = __shfl_up_sync(kFullMask, inc, o); if (lane >= o) inc = max(inc, n); }
+    if (lane == 31) warp_last[wid] = inc;
+    __syncthreads();
+    int before = __shfl_up_sync(kFullMask, inc, 1);
+    if (lane == 0) before = -1;
+    for (int w2 = 0; w2 < wid; w2++) before = max(before, warp_last[w2]);
+    // pass 2: labels, run lengths (written by the pixel that ends the run)
+    int cur = before;
+    pv = prev;
+    for (int x = xa; x < xb; x++) {
+        const int v = row[x];
+        const bool valid = v != newVal;
+        const bool start = valid && !(pv != newVal && abs(v - pv) <= maxDiff);
+        if (start) cur = x;
+        const int p = base + x;
+        csize[p] = 0;
+        if (valid) {
+            label[p] = base + cur;
+            if (start) parent[p] = p;
+            const int nv = x + 1 < W ? int(row[x + 1]) : newVal;
+            const bool ends = !(nv != newVal && abs(nv - v) <= maxDiff);
+            if (ends) runlen[base + cur] = x - cur + 1;
+        } else {
+            label[p] = -1;
+        }
+        pv = v;
+    }
 }
 
-__global__ void k_speckle_merge(const int16_t* __restrict__ img, int* __restrict__ label, int W, int H,
-                                int newVal, int maxDiff)
+__global__ void k_speckle_vmerge(const int16_t* __restrict__ img, const int* __restrict__ label, int* __restrict__ parent,
+                                 int W, int H, int newVal, int maxDiff)
 {
-    int x = blockIdx.x * blockDim.x + threadIdx.x;
-    int y = blockIdx.y;
-    if (x >= W) return;
-    int i = y * W + x;
-    int v = img[i];
-    if (v == newVal) return;
-    if (x + 1 < W) { int u = img[i + 1]; if (u != newVal && abs(u - v) <= maxDiff) uf_union(label, i, i + 1); }
-    if (y + 1 < H) { int u = img[i + W]; if (u != newVal && abs(u - v) <= maxDiff) uf_union(label, i, i + W); }
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = blockIdx.y;
+    if (x >= W || y + 1 >= H) return;
+    const int p = y * W + x;
+    const int v = img[p], u = img[p + W];
+    if (v == newVal || u == newVal || abs(u - v) > maxDiff) return;
+    if (x > 0) {   // the pair one pixel to the left already unites the same two runs
+        const int vl = img[p - 1], ul = img[p + W - 1];
+        if (vl != newVal && ul != newVal && abs(vl - v) <= maxDiff && abs(ul - u) <= maxDiff && abs(ul - vl) <= maxDiff) return;
+    }
+    uf_union(parent, label[p], label[p + W]);
 }
 
-__global__ void k_speckle_count(int* __restrict__ label, int* __restrict__ size, int n)
+__global__ void k_speckle_size(const int* __restrict__ label, int* __restrict__ parent, const int* __restrict__ runlen,
+                               int* __restrict__ csize, int n)
 {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    if (label[i] < 0) return;
-    int r = uf_find(label, i);
-    label[i] = r;  // flatten (roots keep label[r] == r, so concurrent finds stay correct)
-    atomicAdd(&size[r], 1);
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n || label[p] != p) return;   // run starts only
+    const int r = uf_find(parent, p);
+    parent[p] = r;                          // flatten (roots keep parent[r] == r)
+    atomicAdd(&csize[r], runlen[p]);
 }
 
-__global__ void k_speckle_apply(int16_t* __restrict__ img, const int* __restrict__ label, const int* __restrict__ size,
-                                int n, int newVal, int maxSize)
+__global__ void k_speckle_apply(int16_t* __restrict__ img, const int* __restrict__ label, const int* __restrict__ parent,
+                                const int* __restrict__ csize, int n, int newVal, int maxSize)
 {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    int r = label[i];
-    if (r >= 0 && size[r] <= maxSize) img[i] = int16_t(newVal);
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n) return;
+    const int s = label[p];
+    if (s >= 0 && csize[parent[s]] <= maxSize) img[p] = int16_t(newVal);
 }
 
 // ---- a10: CV_16S -> CV_32F, value unchanged (matcherOpenCVSGBM.cpp:34, abstractStereoMatcher.cpp:49)
