@@ -192,15 +192,15 @@ VertPlan plan_vert(const b200sgm_engine* h, const Eff& e)
     return p;
 }
 
-template <int N, bool UP, bool DO_WTA>
-int launch_vert(b200sgm_engine* h, Lane& ln, const Eff& e, const VertPlan& vp, cudaStream_t st)
+template <int N, bool UP, bool DO_WTA, bool FULL, bool CLAMP_EACH>
+int launch_vert_t(b200sgm_engine* h, Lane& ln, const Eff& e, const VertPlan& vp, cudaStream_t st)
 {
     VertGeom g;
     g.w = WtaGeom{e.W, e.H, e.W1, e.minX1, e.minD, e.D, e.Dp, e.uniq, e.d12, e.INVALID};
     g.nstrips = vp.nstrips; g.twmax = vp.twmax;
     g.P1x2 = uint32_t(e.P1) * 0x10001u; g.P2x2 = uint32_t(e.P2) * 0x10001u;
     g.spin_limit = (long long)h->clock_khz * 500;   // ~0.5 s of SM clock ticks
-    auto kern = k_vert<N, UP, DO_WTA>;
+    auto kern = k_vert<N, UP, DO_WTA, FULL, CLAMP_EACH>;
     CUDA_TRY(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(vp.smem)));
     CUDA_TRY(h, cudaMemsetAsync(ln.xbuf, 0, size_t(2) * vp.nstrips * kXbufGen * (e.Dp / 2) * sizeof(uint2), st));
     const uint16_t* Cp = ln.C; uint16_t* Sp = ln.S; int16_t* dp = ln.disp_wta; uint32_t* kp = ln.disp2key;
@@ -215,6 +215,22 @@ int launch_vert(b200sgm_engine* h, Lane& ln, const Eff& e, const VertPlan& vp, c
         h->coop_prev = ln.coop_ev;
     }
     return B200SGM_OK;
+}
+
+template <int N, bool UP, bool DO_WTA>
+int launch_vert(b200sgm_engine* h, Lane& ln, const Eff& e, const VertPlan& vp, cudaStream_t st)
+{
+    const bool full = e.Dp == e.D && e.D == 64 * N;
+    // worst-case cost of a cell: bs^2 * (2*ftzero + 63) (A.5 value bounds); one final clamp is enough when
+    // kMaxCost + 3 * (Cmax + P2) cannot wrap 16 bits
+    const long long bs = 2 * e.SW2 + 1;
+    const long long cmax = bs * bs * (2 * e.ftzero + 63) + e.P2;
+    const bool clamp_each = kMaxCost + 3 * cmax > 65535;
+    if (full) {
+        if (clamp_each) return launch_vert_t<N, UP, DO_WTA, true, true>(h, ln, e, vp, st);
+        return launch_vert_t<N, UP, DO_WTA, true, false>(h, ln, e, vp, st);
+    }
+    return launch_vert_t<N, UP, DO_WTA, false, true>(h, ln, e, vp, st);
 }
 
 template <int N>

@@ -11,6 +11,7 @@
 //             each row, so the flag latency hides behind the row's own work.  The summed cost feeds the
 //             winner-take-all directly from registers (no S volume in MODE_SGBM).
 #pragma once
+#include <type_traits>
 #include "sgm_types.h"
 #include "k_path.cuh"
 #include "k_wta.cuh"
@@ -199,10 +200,61 @@ __device__ __forceinline__ uint2 ld_volatile_v2(const uint2* p)
     return v;
 }
 
-template <int N, bool UP, bool DO_WTA>
+// Tight WTA on registers.  `S` holds 0xFFFF in cells >= D.  Returns the output value for the pixel.
+//   umagic = floor(2^32 / f) + 1 with f = 100 - uniq > 0 (exact quotient for minS*100 + f - 1 < 2^32 / f)
+template <int N>
+__device__ __forceinline__ int wta_fast(const uint32_t (&S)[N], const WtaGeom& g, uint32_t umagic, int x1, int lane,
+                                        uint32_t* __restrict__ disp2key_row)
+{
+    const int kbase = lane * 2 * N;
+    uint32_t key = 0xFFFFFFFFu;
+#pragma unroll
+    for (int q = 0; q < N; q++) {
+        const uint32_t k = uint32_t(kbase + 2 * q);
+        key = min(key, min((S[q] << 16) | k, (S[q] & 0xFFFF0000u) | (k + 1)));
+    }
+    key = __reduce_min_sync(kFullMask, key);
+    const int minS = int(key >> 16), best = int(key & 0xFFFFu);
+    int out = g.INVALID;
+    if (minS < kMaxCost) {
+        const int f = 100 - g.uniq;
+        // S[k] * f < minS * 100  <=>  S[k] < ceil(minS*100 / f); cells best-1..best+1 are exempt
+        const uint32_t thr = min(__umulhi(uint32_t(minS * 100 + f - 1), umagic), 0xFFFFu);
+        const int rel = best - kbase;     // local index of the winner inside this lane (may be out of range)
+        uint32_t mm = 0xFFFFFFFFu;
+#pragma unroll
+        for (int q = 0; q < N; q++) {
+            uint32_t v = S[q];
+            if (uint32_t(2 * q - rel + 1) <= 2u) v |= 0x0000FFFFu;
+            if (uint32_t(2 * q + 1 - rel + 1) <= 2u) v |= 0xFFFF0000u;
+            mm = __vminu2(mm, v);
+        }
+        const bool bad = min(mm & 0xFFFFu, mm >> 16) < thr;
+        if (!__any_sync(kFullMask, bad)) {
+            int dfix = best * 16;
+            if (best > 0 && best < g.D - 1) {
+                const int sm = cell_value<N>(S, best - 1, lane), sp = cell_value<N>(S, best + 1, lane);
+                const int den = max(sm + sp - 2 * minS, 1);
+                // |quotient| <= 8.5 and numerator, denominator < 2^24: IEEE float division then truncation is exact
+                dfix += __float2int_rz(__fdiv_rn(float((sm - sp) * 16 + den), float(den * 2)));
+            }
+            if (lane == 0) {
+                const int x = x1 + g.minX1;
+                const int x2 = x - best - g.minD;
+                if (x2 >= 0 && x2 < g.W) atomicMin(disp2key_row + x2, (uint32_t(minS) << 16) | uint32_t(0xFFFF - x));
+            }
+            out = dfix + g.minD * 16;
+        }
+    }
+    return out;
+}
+
+// FULL      : Dp == D == 64*N (no padded cells, every lane active)
+// CLAMP_EACH: saturate after every addition of the sum (needed when kMaxCost + 3*(Cmax+P2) could exceed 65535)
+template <int N, bool UP, bool DO_WTA, bool FULL, bool CLAMP_EACH>
 __global__ void __launch_bounds__(512, 1) k_vert(const uint16_t* __restrict__ Cvol, uint16_t* __restrict__ Svol, VertGeom g,
-                                                  int16_t* __restrict__ disp, uint32_t* __restrict__ disp2key,
-                                                  uint2* __restrict__ xbuf, int* __restrict__ err)
+                                                 int16_t* __restrict__ disp, uint32_t* __restrict__ disp2key,
+                                                 uint2* __restrict__ xbuf, int* __restrict__ err)
 {
     extern __shared__ __align__(16) uint16_t smem_v[];
     const int W1 = g.w.W1, H = g.w.H, Dp = g.w.Dp;
@@ -211,143 +263,162 @@ __global__ void __launch_bounds__(512, 1) k_vert(const uint16_t* __restrict__ Cv
     const int x0 = int((long long)b * W1 / n), x1e = int((long long)(b + 1) * W1 / n);
     const int TW = x1e - x0;
     const int slots = g.twmax + 2;
-    // smem: Ld[parity][dir][slot][Dp] then mins[parity][dir][slot] (uint32)
+    // smem: Ld[parity][dir][slot][Dp] costs, then Md[parity][dir][slot] minima.  Everything starts at zero: a zero
+    // predecessor vector with minimum 0 is exactly "predecessor outside the image" (first row, border columns).
     uint16_t* Ld = smem_v;
     uint32_t* Md = reinterpret_cast<uint32_t*>(smem_v + size_t(4) * slots * Dp);
-    auto ld_ptr = [&](int par, int dir, int slot) { return Ld + (size_t((par * 2 + dir) * slots + slot)) * Dp + lane * 2 * N; };
-    auto md_ptr = [&](int par, int dir, int slot) { return Md + (par * 2 + dir) * slots + slot; };
-    const bool col = j < TW;
-    const bool active = lane * 2 * N < Dp;
-    const int x = x0 + j;
-    const bool left_edge = col && j == 0, right_edge = col && j == TW - 1;
-    const bool has_left_nb = b > 0, has_right_nb = b < n - 1;
-
-    uint32_t Lv[N], Cc[N], Cn[N], Sc[N], Sn[N];
-#pragma unroll
-    for (int q = 0; q < N; q++) { Lv[q] = 0; Cc[q] = Cn[q] = kMaxCostX2; Sc[q] = Sn[q] = 0; }
-    uint32_t mv = 0;
-    const size_t colOff = size_t(x) * Dp + lane * 2 * N;
-    const size_t rowStride = size_t(W1) * Dp;
     {
-        const int y = UP ? H - 1 : 0;
-        if (col && active) { ldg_regs<N>(Cvol + size_t(y) * rowStride + colOff, Cc); ld_regs<N>(Svol + size_t(y) * rowStride + colOff, Sc); }
+        uint32_t* z = reinterpret_cast<uint32_t*>(smem_v);
+        const int nz = 2 * slots * Dp + 4 * slots;
+        for (int i = threadIdx.x; i < nz; i += blockDim.x) z[i] = 0;
     }
+    __syncthreads();
+    if (j >= TW) return;                 // the row barrier below only counts the column warps
+    const int nbar = 32 * TW;
+    const bool active = FULL || lane * 2 * N < Dp;
+    const int x = x0 + j;
+    const int lo = lane * 2 * N;
+    // direction 0: predecessor column x-1 (slot j); direction 1: predecessor column x+1 (slot j+2).
+    // The left-edge warp runs direction 1 first (it publishes it), every other warp direction 0 first.
+    const int dirA = j == 0 ? 1 : 0, dirB = 1 - dirA;
+    const int slotA = dirA == 0 ? j : j + 2, slotB = dirB == 0 ? j : j + 2;
+    const bool pubA = (j == 0 && b > 0) || (j == TW - 1 && j != 0 && b < n - 1);
+    const bool haloB = (j == 0 && b > 0) || (j == TW - 1 && j != 0 && b < n - 1);   // same warps consume the other direction
+    const int dirStride = slots * Dp, parStride = 2 * slots * Dp;
+    const uint16_t* rdA[2]; uint16_t* wrA[2]; const uint16_t* rdB[2]; uint16_t* wrB[2];
+    const uint32_t* mrA[2]; uint32_t* mwA[2]; const uint32_t* mrB[2]; uint32_t* mwB[2];
+#pragma unroll
+    for (int pz = 0; pz < 2; pz++) {
+        rdA[pz] = Ld + pz * parStride + dirA * dirStride + slotA * Dp + lo;
+        wrA[pz] = Ld + pz * parStride + dirA * dirStride + (j + 1) * Dp + lo;
+        rdB[pz] = Ld + pz * parStride + dirB * dirStride + slotB * Dp + lo;
+        wrB[pz] = Ld + pz * parStride + dirB * dirStride + (j + 1) * Dp + lo;
+        mrA[pz] = Md + (pz * 2 + dirA) * slots + slotA;
+        mwA[pz] = Md + (pz * 2 + dirA) * slots + j + 1;
+        mrB[pz] = Md + (pz * 2 + dirB) * slots + slotB;
+        mwB[pz] = Md + (pz * 2 + dirB) * slots + j + 1;
+    }
+    // exchange records: I publish side dirA of my strip, I consume side dirB of the neighbour
+    const int nb = dirB == 0 ? b - 1 : b + 1;
+    uint2* pub_base = xrec(xbuf, n, Dp, dirA, b, 0) + lane * N;
+    const uint2* con_base = xrec(xbuf, n, Dp, dirB, haloB ? nb : b, 0) + lane * N;
+    const int gen_stride = Dp / 2;
+
+    const ptrdiff_t rowStride = (UP ? -1 : 1) * ptrdiff_t(W1) * Dp;
+    const int ystart = UP ? H - 1 : 0;
+    const uint16_t* gC = Cvol + (size_t(ystart) * W1 + x) * Dp + lo;
+    uint16_t* gS = Svol + (size_t(ystart) * W1 + x) * Dp + lo;
+    int16_t* dptr = disp + size_t(ystart) * g.w.W + x + g.w.minX1;
+    uint32_t* kptr = disp2key + size_t(ystart) * g.w.W;
+    const ptrdiff_t dStride = (UP ? -1 : 1) * ptrdiff_t(g.w.W);
+    const int f = 100 - g.w.uniq;
+    const uint32_t umagic = f > 0 ? uint32_t((1ull << 32) / uint32_t(f)) + 1u : 0u;
+
+    uint32_t Lv[N], C0[N], C1[N], S0[N], S1[N];
+#pragma unroll
+    for (int q = 0; q < N; q++) { Lv[q] = 0; C0[q] = C1[q] = kMaxCostX2; S0[q] = S1[q] = 0; }
+    uint32_t mv = 0;
+    if (active) { ldg_regs<N>(gC, C0); ld_regs<N>(gS, S0); }
     bool dead = false;
 
-    for (int r = 0; r < H; r++) {
-        const int y = UP ? H - 1 - r : r;
-        const int cur = r & 1, prv = cur ^ 1;
-        if (col) {
-            if (r + 1 < H && active) {
-                const int yn = UP ? y - 1 : y + 1;
-                ldg_regs<N>(Cvol + size_t(yn) * rowStride + colOff, Cn);
-                ld_regs<N>(Svol + size_t(yn) * rowStride + colOff, Sn);
-            }
-            // direction 0: predecessor column x-1 (slot j); direction 1: predecessor column x+1 (slot j+2)
-            const int dirA = left_edge ? 1 : 0, dirB = 1 - dirA;
-            uint32_t LA[N], LB[N];
-            uint32_t mA = 0, mB = 0;
-            // ---- step A: never needs a halo unless the strip is a single column wide (excluded by the host)
-            {
-                const int slot = dirA == 0 ? j : j + 2;
+    // one row; PAR = parity of r (buffer written), reads the other one
+    auto row = [&](auto par_tag, int r, uint32_t (&Cc)[N], uint32_t (&Sc)[N], uint32_t (&Cn)[N], uint32_t (&Sn)[N]) {
+        constexpr int PAR = decltype(par_tag)::value;
+        if (r + 1 < H && active) { ldg_regs<N>(gC + rowStride, Cn); ld_regs<N>(gS + rowStride, Sn); }
+        uint32_t LA[N], LB[N];
+        uint32_t mA, mB;
+        // ---- step A
+        if (active) ld_regs<N>(rdA[PAR ^ 1], LA);
+        else {
 #pragma unroll
-                for (int q = 0; q < N; q++) LA[q] = 0;
-                if (r > 0 && !(dirA == 0 && x == 0) && !(dirA == 1 && x == W1 - 1)) {
-                    if (active) ld_regs<N>(ld_ptr(prv, dirA, slot), LA);
-                    else {
+            for (int q = 0; q < N; q++) LA[q] = kMaxCostX2;
+        }
+        mA = *mrA[PAR ^ 1];
+        path_step<N>(Cc, LA, mA, g.P1x2, g.P2x2, lane);
+        if (active) st_regs<N>(wrA[PAR], LA);
+        if (lane == 0) *mwA[PAR] = mA;
+        if (pubA && active) {
+            uint2* rec = pub_base + (r & (kXbufGen - 1)) * gen_stride;
 #pragma unroll
-                        for (int q = 0; q < N; q++) LA[q] = kMaxCostX2;
+            for (int q = 0; q < N; q++) st_volatile_v2(rec + q, LA[q], uint32_t(r + 1));
+        }
+        // ---- vertical path: registers only
+        path_step<N>(Cc, Lv, mv, g.P1x2, g.P2x2, lane);
+        // ---- step B
+        if (haloB && r > 0) {
+            const uint2* rec = con_base + ((r - 1) & (kXbufGen - 1)) * gen_stride;
+#pragma unroll
+            for (int q = 0; q < N; q++) LB[q] = kMaxCostX2;
+            if (active && !dead) {
+                const long long t0 = clock64();
+                int spins = 0;
+                while (true) {
+                    bool ok = true;
+#pragma unroll
+                    for (int q = 0; q < N; q++) {
+                        uint2 v = ld_volatile_v2(rec + q);
+                        LB[q] = v.x;
+                        ok = ok && v.y == uint32_t(r);
                     }
-                    mA = *md_ptr(prv, dirA, slot);
-                }
-                path_step<N>(Cc, LA, mA, g.P1x2, g.P2x2, lane);
-                if (active) st_regs<N>(ld_ptr(cur, dirA, j + 1), LA);
-                if (lane == 0) *md_ptr(cur, dirA, j + 1) = mA;
-                // publish to the neighbouring strip: left edge sends dir 1 to strip b-1, right edge sends dir 0 to b+1
-                const bool pub = (left_edge && has_left_nb) || (right_edge && has_right_nb && dirA == 0);
-                if (pub && active) {
-                    // record side 1 = left-edge (<-down) values, side 0 = right-edge (->down) values
-                    uint2* rec = xrec(xbuf, n, Dp, dirA, b, r) + lane * N;
-#pragma unroll
-                    for (int q = 0; q < N; q++) st_volatile_v2(rec + q, LA[q], uint32_t(r + 1));
-                }
-            }
-            // ---- vertical path: registers only
-            path_step<N>(Cc, Lv, mv, g.P1x2, g.P2x2, lane);
-            // ---- step B: may need the halo published by the neighbouring strip for row r-1
-            {
-                const int slot = dirB == 0 ? j : j + 2;
-#pragma unroll
-                for (int q = 0; q < N; q++) LB[q] = 0;
-                const bool outside = (dirB == 0 && x == 0) || (dirB == 1 && x == W1 - 1);
-                if (r > 0 && !outside) {
-                    const bool halo = (dirB == 0 && j == 0) || (dirB == 1 && j == TW - 1);
-                    if (halo) {
-                        const int nb = dirB == 0 ? b - 1 : b + 1;
-                        // want nb's right-edge record (side 0) for direction 0, its left-edge record (side 1) for direction 1
-                        const uint2* rec = xrec(xbuf, n, Dp, dirB, nb, r - 1) + lane * N;
-#pragma unroll
-                        for (int q = 0; q < N; q++) LB[q] = kMaxCostX2;
-                        if (active && !dead) {
-                            const long long t0 = clock64();
-                            int spins = 0;
-                            while (true) {
-                                bool ok = true;
-#pragma unroll
-                                for (int q = 0; q < N; q++) {
-                                    uint2 v = ld_volatile_v2(rec + q);
-                                    LB[q] = v.x;
-                                    ok = ok && v.y == uint32_t(r);
-                                }
-                                if (ok) break;
-                                if ((++spins & 255) == 0 &&
-                                    (clock64() - t0 > g.spin_limit || *reinterpret_cast<volatile int*>(err))) {
-                                    atomicExch(err, 1);
-                                    dead = true;
-                                    break;
-                                }
-                            }
-                        }
-                        dead = __any_sync(kFullMask, dead);
-                        mB = warp_min16<N>(LB);
-                    } else {
-                        if (active) ld_regs<N>(ld_ptr(prv, dirB, slot), LB);
-                        else {
-#pragma unroll
-                            for (int q = 0; q < N; q++) LB[q] = kMaxCostX2;
-                        }
-                        mB = *md_ptr(prv, dirB, slot);
+                    if (ok) break;
+                    if ((++spins & 255) == 0 && (clock64() - t0 > g.spin_limit || *reinterpret_cast<volatile int*>(err))) {
+                        atomicExch(err, 1);
+                        dead = true;
+                        break;
                     }
                 }
-                path_step<N>(Cc, LB, mB, g.P1x2, g.P2x2, lane);
-                if (active) st_regs<N>(ld_ptr(cur, dirB, j + 1), LB);
-                if (lane == 0) *md_ptr(cur, dirB, j + 1) = mB;
             }
-            // ---- sum: S = sat(S_h + L_v + L_A + L_B)
-            uint32_t S[N];
+            dead = __any_sync(kFullMask, dead);
+            mB = warp_min16<N>(LB);
+        } else {
+            if (active) ld_regs<N>(rdB[PAR ^ 1], LB);
+            else {
 #pragma unroll
-            for (int q = 0; q < N; q++) {
-                uint32_t s = __vminu2(Sc[q] + Lv[q], kMaxCostX2);
-                s = __vminu2(s + LA[q], kMaxCostX2);
-                S[q] = __vminu2(s + LB[q], kMaxCostX2);
+                for (int q = 0; q < N; q++) LB[q] = kMaxCostX2;
             }
-            if (DO_WTA) {
+            mB = *mrB[PAR ^ 1];
+        }
+        path_step<N>(Cc, LB, mB, g.P1x2, g.P2x2, lane);
+        if (active) st_regs<N>(wrB[PAR], LB);
+        if (lane == 0) *mwB[PAR] = mB;
+        // ---- S = sat(S_h + L_v + L_A + L_B)
+        uint32_t S[N];
+#pragma unroll
+        for (int q = 0; q < N; q++) {
+            if (CLAMP_EACH) {
+                uint32_t t = __vminu2(Sc[q] + Lv[q], kMaxCostX2);
+                t = __vminu2(t + LA[q], kMaxCostX2);
+                S[q] = __vminu2(t + LB[q], kMaxCostX2);
+            } else {
+                S[q] = __vminu2(Sc[q] + Lv[q] + LA[q] + LB[q], kMaxCostX2);
+            }
+        }
+        if (DO_WTA) {
+            if (!FULL) {
 #pragma unroll
                 for (int q = 0; q < N; q++) {   // cells beyond D never win and never veto
-                    const int k = lane * 2 * N + 2 * q;
+                    const int k = lo + 2 * q;
                     if (k >= g.w.D) S[q] = 0xFFFFFFFFu;
                     else if (k + 1 >= g.w.D) S[q] |= 0xFFFF0000u;
                 }
-                int d = wta_regs<N>(S, g.w, x, lane, disp2key + size_t(y) * g.w.W);
-                if (lane == 0) disp[size_t(y) * g.w.W + x + g.w.minX1] = int16_t(d);
-            } else if (active) {
-                st_regs<N>(Svol + size_t(y) * rowStride + colOff, S);
             }
-#pragma unroll
-            for (int q = 0; q < N; q++) { Cc[q] = Cn[q]; Sc[q] = Sn[q]; }
+            int d;
+            if (f > 0) d = wta_fast<N>(S, g.w, umagic, x, lane, kptr);
+            else d = wta_regs<N>(S, g.w, x, lane, kptr);
+            if (lane == 0) *dptr = int16_t(d);
+        } else if (active) {
+            st_regs<N>(gS, S);
         }
-        __syncthreads();
+        gC += rowStride; gS += rowStride; dptr += dStride; kptr += dStride;
+        asm volatile("bar.sync 1, %0;" ::"r"(nbar) : "memory");
+    };
+
+    int r = 0;
+    for (; r + 1 < H; r += 2) {
+        row(std::integral_constant<int, 0>{}, r, C0, S0, C1, S1);
+        row(std::integral_constant<int, 1>{}, r + 1, C1, S1, C0, S0);
     }
+    if (r < H) row(std::integral_constant<int, 0>{}, r, C0, S0, C1, S1);
 }
 
 }  // namespace b200sgm
