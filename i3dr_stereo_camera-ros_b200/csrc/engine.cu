@@ -200,6 +200,7 @@ int launch_vert_t(b200sgm_engine* h, Lane& ln, const Eff& e, const VertPlan& vp,
     g.nstrips = vp.nstrips; g.twmax = vp.twmax;
     g.P1x2 = uint32_t(e.P1) * 0x10001u; g.P2x2 = uint32_t(e.P2) * 0x10001u;
     g.spin_limit = (long long)h->clock_khz * 500;   // ~0.5 s of SM clock ticks
+    if (getenv("B200SGM_DEBUG_NO_WAIT")) g.spin_limit = 0;   // timing experiment only: results are garbage
     auto kern = k_vert<N, UP, DO_WTA, FULL, CLAMP_EACH>;
     CUDA_TRY(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(vp.smem)));
     CUDA_TRY(h, cudaMemsetAsync(ln.xbuf, 0, size_t(2) * vp.nstrips * kXbufGen * (e.Dp / 2) * sizeof(uint2), st));
@@ -344,10 +345,11 @@ int run_pipeline(b200sgm_engine* h, Lane& ln, const Eff& e, const uint8_t* dL, s
         if (e.SW2 <= 10 && h->path != 1) {
             CostFastGeom fg{W, H, e.W1, e.minX1, e.minD, e.D, e.Dp, e.SW2, 128};
             const size_t smem = cost_fast_smem(e.SW2);
-            CUDA_TRY(h, cudaFuncSetAttribute(k_cost_fast, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
             const int TX = kCfTXH - 2 * e.SW2;
             dim3 grid((e.W1 + TX - 1) / TX, (e.Dp / 2 + kCfDCP - 1) / kCfDCP, (H + fg.RS - 1) / fg.RS);
-            k_cost_fast<<<grid, 256, smem, st>>>(ln.feat_l, ln.feat_r, ln.C, fg);
+            auto kern = e.SW2 == 4 ? k_cost_fast<4> : (e.SW2 == 2 ? k_cost_fast<2> : k_cost_fast<0>);
+            CUDA_TRY(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+            kern<<<grid, 256, smem, st>>>(ln.feat_l, ln.feat_r, ln.C, fg);
             LAUNCH_CHECK(h);
         } else {
             CostGeom cg;

@@ -168,12 +168,15 @@ inline size_t cost_fast_smem(int SW2)
 
 __device__ __forceinline__ uint32_t pk16(int a, int b) { return (uint32_t(a) & 0xFFFFu) | (uint32_t(b) << 16); }
 
+// SW2T > 0: blockSize/2 known at compile time (loops unrolled); SW2T == 0: taken from the geometry.
+template <int SW2T>
 __global__ void __launch_bounds__(256, 2) k_cost_fast(const Feat* __restrict__ fl, const Feat* __restrict__ fr,
                                                       uint16_t* __restrict__ Cvol, CostFastGeom g)
 {
     extern __shared__ uint4 cf_smem[];
-    const int bs = 2 * g.SW2 + 1;
-    const int TX = kCfTXH - 2 * g.SW2;
+    const int SW2 = SW2T > 0 ? SW2T : g.SW2;
+    const int bs = 2 * SW2 + 1;
+    const int TX = kCfTXH - 2 * SW2;
     uint4* Rs = cf_smem;                       // [2][NRP]  sobel: (v, lo, -hi, -v) pairs
     uint4* Rr = Rs + 2 * kCfNRP;               // [2][NRP]  raw x64
     uint4* Ls = Rr + 2 * kCfNRP;               // [2][TXH]  sobel: (u, -u, lo, -hi) replicated
@@ -185,7 +188,7 @@ __global__ void __launch_bounds__(256, 2) k_cost_fast(const Feat* __restrict__ f
     const int tx0 = blockIdx.x * TX;
     const int k0 = blockIdx.y * kCfDCP * 2;
     const int ya = blockIdx.z * g.RS, yb = min(ya + g.RS, g.H);
-    auto col_x = [&](int c) { return min(max(tx0 - g.SW2 + c, 0), g.W1 - 1) + g.minX1; };
+    auto col_x = [&](int c) { return min(max(tx0 - SW2 + c, 0), g.W1 - 1) + g.minX1; };
     const int xr_min = col_x(0) - g.minD - k0 - 2 * (kCfDCP - 1);
     const int nR = col_x(kCfTXH - 1) - col_x(0) + 2 * (kCfDCP - 1) + 1;
 
@@ -198,7 +201,7 @@ __global__ void __launch_bounds__(256, 2) k_cost_fast(const Feat* __restrict__ f
     for (int i = t; i < bs * kCfDCP * kCfTXH; i += 256) ring[i] = 0;
 
     auto stage = [&](int s, int buf) {
-        const int e = min(max(ya - g.SW2 + s, 0), g.H - 1);
+        const int e = min(max(ya - SW2 + s, 0), g.H - 1);
         if (t < nR) {
             const int xr = xr_min + t;
             const Feat a = __ldg(fr + size_t(e) * g.W + min(max(xr, 0), g.W - 1));
@@ -229,12 +232,17 @@ __global__ void __launch_bounds__(256, 2) k_cost_fast(const Feat* __restrict__ f
     const uint32_t pad_or = kk >= g.D ? kMaxCostX2 : (kk + 1 >= g.D ? (uint32_t(kMaxCost) << 16) : 0u);
     const uint32_t pad_and = kk >= g.D ? 0u : (kk + 1 >= g.D ? 0x0000FFFFu : 0xFFFFFFFFu);
 
+    // phase-2 output pointer of this lane: row y, column tx0 + c_lo, disparity pair kk
+    const bool lane_ok = kk < g.Dp;
+    const size_t colBytes = size_t(g.Dp) * 2;
+    int slot = 0;
     for (int s = 0; s < nsteps; s++) {
         const int buf = s & 1;
         // ---- phase 1
         {
             const uint4 ls = Ls[buf * kCfTXH + col], lr = Lr[buf * kCfTXH + col];
-            uint32_t* rrow = ring + size_t(s % bs) * kCfDCP * kCfTXH + col;
+            uint32_t* rrow = ring + size_t(slot) * kCfDCP * kCfTXH + col;
+            slot = slot + 1 == bs ? 0 : slot + 1;
             const uint4* rs_p = Rs + buf * kCfNRP + rbase;
             const uint4* rr_p = Rr + buf * kCfNRP + rbase;
 #pragma unroll
@@ -260,15 +268,30 @@ __global__ void __launch_bounds__(256, 2) k_cost_fast(const Feat* __restrict__ f
         }
         __syncthreads();
         // ---- phase 2 (once the vertical window is full) + staging of the next row
-        if (s >= bs - 1 && c_lo < c_hi) {
+        if (s >= bs - 1 && c_lo < c_hi && lane_ok) {
             const int y = ya + s - (bs - 1);
-            const uint32_t* vrow = vs + lane * (kCfTXH + 1);
+            const uint32_t* vrow = vs + lane * (kCfTXH + 1) + c_lo;
+            char* out = reinterpret_cast<char*>(Cvol + (size_t(y) * g.W1 + tx0 + c_lo) * g.Dp + kk);
+            const int ncol = min(c_hi, g.W1 - tx0) - c_lo;     // columns of this run that exist in the image
             uint32_t hs = 0;
-            for (int jj = 0; jj < bs; jj++) hs += vrow[c_lo + jj];
-            for (int c = c_lo; c < c_hi; c++) {
-                if (c > c_lo) hs = hs + vrow[c + bs - 1] - vrow[c - 1];
-                if (tx0 + c < g.W1 && kk < g.Dp)
-                    *reinterpret_cast<uint32_t*>(Cvol + (size_t(y) * g.W1 + tx0 + c) * g.Dp + kk) = (hs & pad_and) | pad_or;
+            if (SW2T > 0) {
+                constexpr int BS = 2 * SW2T + 1, CPW = (kCfTXH - 2 * SW2T + 7) / 8;
+                uint32_t v[CPW + BS - 1];
+#pragma unroll
+                for (int jj = 0; jj < CPW + BS - 1; jj++) v[jj] = vrow[jj];   // may read a few words of the next run: harmless
+#pragma unroll
+                for (int jj = 0; jj < BS; jj++) hs += v[jj];
+#pragma unroll
+                for (int c = 0; c < CPW; c++) {
+                    if (c > 0) hs = hs + v[c + BS - 1] - v[c - 1];
+                    if (c < ncol) *reinterpret_cast<uint32_t*>(out + c * colBytes) = (hs & pad_and) | pad_or;
+                }
+            } else {
+                for (int jj = 0; jj < bs; jj++) hs += vrow[jj];
+                for (int c = 0; c < ncol; c++) {
+                    if (c > 0) hs = hs + vrow[c + bs - 1] - vrow[c - 1];
+                    *reinterpret_cast<uint32_t*>(out + c * colBytes) = (hs & pad_and) | pad_or;
+                }
             }
         }
         if (s + 1 < nsteps) stage(s + 1, buf ^ 1);

@@ -369,7 +369,7 @@ __global__ void __launch_bounds__(512, 1) k_vert(const uint16_t* __restrict__ Cv
                 }
             }
             dead = __any_sync(kFullMask, dead);
-            mB = warp_min16<N>(LB);
+            mB = warp_min16x2<N>(LB);
         } else {
             if (active) ld_regs<N>(rdB[PAR ^ 1], LB);
             else {

@@ -55,29 +55,31 @@ __device__ __forceinline__ void st_regs(uint16_t* p, const uint32_t (&r)[N])
     }
 }
 
-// Warp-wide minimum over all uint16 halves of r[0..N).
+// Warp-wide minimum over all uint16 halves of r[0..N), returned replicated in both halves (m * 0x10001):
+// after the in-lane tree both halves of every lane's word are made equal, so the 32-bit CREDUX.MIN of
+// those words is the word with the smallest half.
 template <int N>
-__device__ __forceinline__ uint32_t warp_min16(const uint32_t (&r)[N])
+__device__ __forceinline__ uint32_t warp_min16x2(const uint32_t (&r)[N])
 {
     uint32_t mm = r[0];
 #pragma unroll
     for (int j = 1; j < N; j++) mm = __vminu2(mm, r[j]);
-    uint32_t m16 = min(mm & 0xFFFFu, mm >> 16);
-    return __reduce_min_sync(kFullMask, m16);
+    mm = __vminu2(mm, __byte_perm(mm, 0, 0x1032));
+    return __reduce_min_sync(kFullMask, mm);
 }
 
 // One step of  L[k] = C[k] + min(Lp[k], Lp[k-1]+P1, Lp[k+1]+P1, m+P2) - m  on the lane's 2N disparities.
-// Lp is replaced by L; m (the warp-uniform minimum of Lp) is replaced by min(L).  Out-of-range
-// neighbours and padded cells hold kMaxCost ("infinity"; kMaxCost + P1 + P2 < 65536 is validated on the host).
+// Lp is replaced by L; m2 (the warp-uniform minimum of Lp, replicated in both halves) is replaced by that
+// of L.  Out-of-range neighbours and padded cells hold kMaxCost ("infinity"; kMaxCost + P1 + P2 < 65536 is
+// validated on the host).
 template <int N>
-__device__ __forceinline__ void path_step(const uint32_t (&C)[N], uint32_t (&Lp)[N], uint32_t& m,
+__device__ __forceinline__ void path_step(const uint32_t (&C)[N], uint32_t (&Lp)[N], uint32_t& m2,
                                           uint32_t P1x2, uint32_t P2x2, int lane)
 {
     uint32_t up = __shfl_up_sync(kFullMask, Lp[N - 1], 1);
     uint32_t dn = __shfl_down_sync(kFullMask, Lp[0], 1);
     if (lane == 0) up = kMaxCostX2;
     if (lane == 31) dn = kMaxCostX2;
-    const uint32_t m2 = m * 0x10001u;
     const uint32_t mP2 = m2 + P2x2;
     uint32_t q_lo = __byte_perm(up, Lp[0], 0x5432) + P1x2;  // (Lp[2j-1], Lp[2j]) + P1
     uint32_t L[N];
@@ -92,7 +94,7 @@ __device__ __forceinline__ void path_step(const uint32_t (&C)[N], uint32_t (&Lp)
     }
 #pragma unroll
     for (int j = 0; j < N; j++) Lp[j] = L[j];
-    m = warp_min16<N>(L);
+    m2 = warp_min16x2<N>(L);
 }
 
 struct PathGeom {
