@@ -175,11 +175,12 @@ int launch_paths_generic(b200sgm_engine* h, Lane& ln, const Eff& e, cudaStream_t
 }
 
 // ---- fused path: k_horiz + cooperative k_vert ---------------------------------------------------------
-struct VertPlan { bool ok; int nstrips, twmax; size_t smem; };
+struct VertPlan { bool ok; int nstrips, twmax; size_t smem; bool two_warps; };
 
 VertPlan plan_vert(const b200sgm_engine* h, const Eff& e)
 {
-    VertPlan p{false, 0, 0, 0};
+    VertPlan p{false, 0, 0, 0, false};
+    static const bool two = [] { const char* v = getenv("B200SGM_VERT_ONE_WARP"); return !(v && atoi(v)); }();
     if (e.W1 < 2) return p;
     static const int per_sm = [] { const char* v = getenv("B200SGM_VERT_STRIPS_PER_SM"); return v ? std::max(1, atoi(v)) : 1; }();
     int n = std::min(h->num_sms * per_sm, e.W1 / 2);
@@ -187,7 +188,9 @@ VertPlan plan_vert(const b200sgm_engine* h, const Eff& e)
     int tw = (e.W1 + n - 1) / n;
     if (tw > kVertMaxWarps) return p;      // wider than one co-resident wave of strips: use the hybrid path
     p.nstrips = n; p.twmax = tw;
-    p.smem = size_t(4) * (tw + 2) * e.Dp * sizeof(uint16_t) + size_t(4) * (tw + 2) * sizeof(uint32_t);
+    p.two_warps = two && e.nreg <= 4;     // two warps per column: 2*tw <= 32 warps, 64 registers per thread
+    p.smem = size_t(4) * (tw + 2) * e.Dp * sizeof(uint16_t) + size_t(4) * (tw + 2) * sizeof(uint32_t) +
+             (p.two_warps ? 16 + size_t(2 * kVertRing + kSoutRing) * tw * e.Dp * sizeof(uint16_t) : 0);
     p.ok = p.smem <= 200 * 1024;
     return p;
 }
@@ -201,7 +204,8 @@ int launch_vert_t(b200sgm_engine* h, Lane& ln, const Eff& e, const VertPlan& vp,
     g.P1x2 = uint32_t(e.P1) * 0x10001u; g.P2x2 = uint32_t(e.P2) * 0x10001u;
     g.spin_limit = (long long)h->clock_khz * 500;   // ~0.5 s of SM clock ticks
     if (getenv("B200SGM_DEBUG_NO_WAIT")) g.spin_limit = 0;   // timing experiment only: results are garbage
-    auto kern = k_vert<N, UP, DO_WTA, FULL, CLAMP_EACH>;
+    g.debug_no_exchange = getenv("B200SGM_DEBUG_NO_EXCHANGE") ? 1 : 0;
+    auto kern = vp.two_warps ? k_vert3<N, UP, DO_WTA, FULL, CLAMP_EACH> : k_vert<N, UP, DO_WTA, FULL, CLAMP_EACH>;
     CUDA_TRY(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(vp.smem)));
     CUDA_TRY(h, cudaMemsetAsync(ln.xbuf, 0, size_t(2) * vp.nstrips * kXbufGen * (e.Dp / 2) * sizeof(uint2), st));
     const uint16_t* Cp = ln.C; uint16_t* Sp = ln.S; int16_t* dp = ln.disp_wta; uint32_t* kp = ln.disp2key;
@@ -210,7 +214,7 @@ int launch_vert_t(b200sgm_engine* h, Lane& ln, const Eff& e, const VertPlan& vp,
     {
         std::lock_guard<std::mutex> lk(h->mu);
         if (h->coop_prev) CUDA_TRY(h, cudaStreamWaitEvent(st, h->coop_prev, 0));
-        CUDA_TRY(h, cudaLaunchCooperativeKernel((void*)kern, dim3(vp.nstrips), dim3(32 * vp.twmax), args, vp.smem, st));
+        CUDA_TRY(h, cudaLaunchCooperativeKernel((void*)kern, dim3(vp.nstrips), dim3((vp.two_warps ? 64 : 32) * vp.twmax), args, vp.smem, st));
         h->launches++;
         CUDA_TRY(h, cudaEventRecord(ln.coop_ev, st));
         h->coop_prev = ln.coop_ev;

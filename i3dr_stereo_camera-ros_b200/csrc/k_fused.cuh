@@ -176,6 +176,7 @@ struct VertGeom {
     int twmax;            // warps per CTA = widest strip
     uint32_t P1x2, P2x2;
     long long spin_limit; // clock64 ticks before a flag wait gives up
+    int debug_no_exchange; // timing experiments only: never wait for / publish to neighbours (wrong results)
 };
 
 // Inter-strip exchange, "low latency" protocol: a record is Dp/2 entries of {two packed costs, tag}; each
@@ -419,6 +420,256 @@ __global__ void __launch_bounds__(512, 1) k_vert(const uint16_t* __restrict__ Cv
         row(std::integral_constant<int, 1>{}, r + 1, C1, S1, C0, S0);
     }
     if (r < H) row(std::integral_constant<int, 0>{}, r, C0, S0, C1, S1);
+}
+
+constexpr int kVertRing = 4;   // rows of C / S_h in flight per column (cp.async ring in shared memory)
+
+template <int BYTES>
+__device__ __forceinline__ void cp_async(void* smem_dst, const void* gsrc)
+{
+    const uint32_t d = uint32_t(__cvta_generic_to_shared(smem_dst));
+    if constexpr (BYTES == 16) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc) : "memory");
+    else if constexpr (BYTES == 8) asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(gsrc) : "memory");
+    else asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d), "l"(gsrc) : "memory");
+}
+// copies this lane's 2N costs
+template <int N>
+__device__ __forceinline__ void cp_async_lane(uint16_t* smem_dst, const uint16_t* gsrc)
+{
+    if constexpr (N <= 4) cp_async<4 * N>(smem_dst, gsrc);
+    else {
+#pragma unroll
+        for (int q = 0; q < N / 4; q++) cp_async<16>(smem_dst + 8 * q, gsrc + 8 * q);
+    }
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int PENDING>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(PENDING) : "memory"); }
+
+// ------------------------------------------------------------------------------------------------
+// Vertical sweep, warp specialised (the default for D <= 256):
+//   path warps (0 .. TW-1)   : one per column; the three path updates of a row (the only work on the
+//                              row-to-row dependency chain), the sum S, which they park in a 4-deep shared
+//                              memory ring; they run in lock step with one 32*TW-thread barrier per row.
+//   WTA warps  (TW .. 2TW-1) : one per column; take S from the ring and do the winner-take-all (or store S in
+//                              the first pass of MODE_HH).  They trail the path warps by up to 4 rows and fill
+//                              the issue slots the path warps leave idle while they wait for each other.
+// Ring hand-over uses named barriers: full[q] (path warps arrive, WTA warps sync) and empty[q] (reverse).
+// ------------------------------------------------------------------------------------------------
+constexpr int kSoutRing = 4;
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
+__device__ __forceinline__ void named_bar_arrive(int id, int nthreads) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
+
+template <int N, bool UP, bool DO_WTA, bool FULL, bool CLAMP_EACH>
+__global__ void __launch_bounds__(1024, 1) k_vert3(const uint16_t* __restrict__ Cvol, uint16_t* __restrict__ Svol, VertGeom g,
+                                                   int16_t* __restrict__ disp, uint32_t* __restrict__ disp2key,
+                                                   uint2* __restrict__ xbuf, int* __restrict__ err)
+{
+    extern __shared__ __align__(16) uint16_t smem_v[];
+    const int W1 = g.w.W1, H = g.w.H, Dp = g.w.Dp;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int b = blockIdx.x, n = g.nstrips;
+    const int x0 = int((long long)b * W1 / n), x1e = int((long long)(b + 1) * W1 / n);
+    const int TW = x1e - x0;
+    const int slots = g.twmax + 2;
+    // smem: Ld[parity][dir][slot][Dp], Md[parity][dir][slot] (zero at start), Cring/Sring[kVertRing][twmax][Dp],
+    //       Sout[kSoutRing][twmax][Dp]
+    uint16_t* Ld = smem_v;
+    uint32_t* Md = reinterpret_cast<uint32_t*>(Ld + size_t(4) * slots * Dp);
+    uint16_t* Cring = reinterpret_cast<uint16_t*>(Md + ((4 * slots + 3) & ~3));
+    uint16_t* Sring = Cring + size_t(kVertRing) * g.twmax * Dp;
+    uint16_t* Sout = Sring + size_t(kVertRing) * g.twmax * Dp;
+    {
+        uint32_t* z = reinterpret_cast<uint32_t*>(smem_v);
+        const int nz = 2 * slots * Dp + 4 * slots;
+        for (int i = threadIdx.x; i < nz; i += blockDim.x) z[i] = 0;
+    }
+    __syncthreads();
+    if (w >= 2 * TW) return;
+    const bool wta_role = w >= TW;
+    const int j = wta_role ? w - TW : w;
+    const bool active = FULL || lane * 2 * N < Dp;
+    const int x = x0 + j;
+    const int lo = lane * 2 * N;
+    const int ringStride = g.twmax * Dp;
+    const ptrdiff_t rowStride = (UP ? -1 : 1) * ptrdiff_t(W1) * Dp;
+    const int ystart = UP ? H - 1 : 0;
+    const int nall = 64 * TW;
+    uint16_t* sout = Sout + size_t(j) * Dp + lo;
+    constexpr int BAR_ROW = 1, BAR_FULL = 2, BAR_EMPTY = 2 + kSoutRing;
+
+    if (wta_role) {
+        // ================================ WTA warps ================================
+        uint16_t* gSo = Svol + (size_t(ystart) * W1 + x) * Dp + lo;
+        int16_t* dptr = disp + size_t(ystart) * g.w.W + x + g.w.minX1;
+        uint32_t* kptr = disp2key + size_t(ystart) * g.w.W;
+        const ptrdiff_t dStride = (UP ? -1 : 1) * ptrdiff_t(g.w.W);
+        const int f = 100 - g.w.uniq;
+        const uint32_t umagic = f > 0 ? uint32_t((1ull << 32) / uint32_t(f)) + 1u : 0u;
+        for (int r = 0; r < H; r++) {
+            const int q = r & (kSoutRing - 1);
+            named_bar_sync(BAR_FULL + q, nall);
+            uint32_t S[N];
+            if (active) ld_regs<N>(sout + q * ringStride, S);
+            else {
+#pragma unroll
+                for (int i = 0; i < N; i++) S[i] = 0xFFFFFFFFu;
+            }
+            if (r + kSoutRing < H) named_bar_arrive(BAR_EMPTY + q, nall);
+            if (DO_WTA) {
+                if (!FULL) {
+#pragma unroll
+                    for (int i = 0; i < N; i++) {
+                        const int k = lo + 2 * i;
+                        if (k >= g.w.D) S[i] = 0xFFFFFFFFu;
+                        else if (k + 1 >= g.w.D) S[i] |= 0xFFFF0000u;
+                    }
+                }
+                int d;
+                if (f > 0) d = wta_fast<N>(S, g.w, umagic, x, lane, kptr);
+                else d = wta_regs<N>(S, g.w, x, lane, kptr);
+                if (lane == 0) *dptr = int16_t(d);
+            } else if (active) {
+                st_regs<N>(gSo, S);
+            }
+            gSo += rowStride; dptr += dStride; kptr += dStride;
+        }
+        return;
+    }
+
+    // ================================ path warps ================================
+    const int nrow = 32 * TW;
+    const int dirA = j == 0 ? 1 : 0, dirB = 1 - dirA;
+    const int slotA = dirA == 0 ? j : j + 2, slotB = dirB == 0 ? j : j + 2;
+    const bool edge = !g.debug_no_exchange && ((j == 0 && b > 0) || (j == TW - 1 && j != 0 && b < n - 1));
+    const int dirStride = slots * Dp, parStride = 2 * slots * Dp;
+    const int nb = dirB == 0 ? b - 1 : b + 1;
+    const int gen_stride = Dp / 2;
+    const uint16_t* rdA[2]; uint16_t* wrA[2]; const uint16_t* rdB[2]; uint16_t* wrB[2];
+    const uint32_t* mrA[2]; uint32_t* mwA[2]; const uint32_t* mrB[2]; uint32_t* mwB[2];
+#pragma unroll
+    for (int pz = 0; pz < 2; pz++) {
+        rdA[pz] = Ld + pz * parStride + dirA * dirStride + slotA * Dp + lo;
+        wrA[pz] = Ld + pz * parStride + dirA * dirStride + (j + 1) * Dp + lo;
+        rdB[pz] = Ld + pz * parStride + dirB * dirStride + slotB * Dp + lo;
+        wrB[pz] = Ld + pz * parStride + dirB * dirStride + (j + 1) * Dp + lo;
+        mrA[pz] = Md + (pz * 2 + dirA) * slots + slotA;
+        mwA[pz] = Md + (pz * 2 + dirA) * slots + j + 1;
+        mrB[pz] = Md + (pz * 2 + dirB) * slots + slotB;
+        mwB[pz] = Md + (pz * 2 + dirB) * slots + j + 1;
+    }
+    uint2* pub_base = xrec(xbuf, n, Dp, dirA, b, 0) + lane * N;
+    const uint2* con_base = xrec(xbuf, n, Dp, dirB, edge ? nb : b, 0) + lane * N;
+    const uint16_t* gC = Cvol + (size_t(ystart) * W1 + x) * Dp + lo;
+    const uint16_t* gS = Svol + (size_t(ystart) * W1 + x) * Dp + lo;
+    uint16_t* cring = Cring + size_t(j) * Dp + lo;
+    uint16_t* sring = Sring + size_t(j) * Dp + lo;
+    int issue_row = 0;
+    auto issue = [&]() {   // one commit group per row, even past the end (keeps the wait arithmetic uniform)
+        if (issue_row < H && active) {
+            const int sl = (issue_row & (kVertRing - 1)) * ringStride;
+            cp_async_lane<N>(cring + sl, gC);
+            cp_async_lane<N>(sring + sl, gS);
+        }
+        cp_async_commit();
+        gC += rowStride; gS += rowStride;
+        issue_row++;
+    };
+#pragma unroll
+    for (int i = 0; i < kVertRing - 1; i++) issue();
+    uint32_t Lv[N];
+#pragma unroll
+    for (int i = 0; i < N; i++) Lv[i] = 0;
+    uint32_t mv = 0;
+    bool dead = false;
+
+    auto row = [&](auto par_tag, int r) {
+        constexpr int PAR = decltype(par_tag)::value;
+        issue();
+        cp_async_wait<kVertRing - 1>();     // this thread's copies of row r have landed (each lane reads only its own bytes)
+        const int sl = (r & (kVertRing - 1)) * ringStride;
+        uint32_t LA[N], LB[N], Cc[N], Sc[N];
+        uint32_t mA, mB;
+        if (active) { ld_regs<N>(rdA[PAR ^ 1], LA); ld_regs<N>(cring + sl, Cc); }
+        else {
+#pragma unroll
+            for (int i = 0; i < N; i++) { LA[i] = kMaxCostX2; Cc[i] = kMaxCostX2; }
+        }
+        mA = *mrA[PAR ^ 1];
+        path_step<N>(Cc, LA, mA, g.P1x2, g.P2x2, lane);
+        if (active) st_regs<N>(wrA[PAR], LA);
+        if (lane == 0) *mwA[PAR] = mA;
+        if (edge && active) {
+            uint2* rec = pub_base + (r & (kXbufGen - 1)) * gen_stride;
+#pragma unroll
+            for (int i = 0; i < N; i++) st_volatile_v2(rec + i, LA[i], uint32_t(r + 1));
+        }
+        path_step<N>(Cc, Lv, mv, g.P1x2, g.P2x2, lane);
+        if (edge && r > 0) {
+            const uint2* rec = con_base + ((r - 1) & (kXbufGen - 1)) * gen_stride;
+#pragma unroll
+            for (int i = 0; i < N; i++) LB[i] = kMaxCostX2;
+            if (active && !dead) {
+                const long long t0 = clock64();
+                int spins = 0;
+                while (true) {
+                    bool ok = true;
+#pragma unroll
+                    for (int i = 0; i < N; i++) {
+                        uint2 v = ld_volatile_v2(rec + i);
+                        LB[i] = v.x;
+                        ok = ok && v.y == uint32_t(r);
+                    }
+                    if (ok) break;
+                    if ((++spins & 255) == 0 && (clock64() - t0 > g.spin_limit || *reinterpret_cast<volatile int*>(err))) {
+                        atomicExch(err, 1);
+                        dead = true;
+                        break;
+                    }
+                }
+            }
+            dead = __any_sync(kFullMask, dead);
+            mB = warp_min16x2<N>(LB);
+        } else {
+            if (active) ld_regs<N>(rdB[PAR ^ 1], LB);
+            else {
+#pragma unroll
+                for (int i = 0; i < N; i++) LB[i] = kMaxCostX2;
+            }
+            mB = *mrB[PAR ^ 1];
+        }
+        path_step<N>(Cc, LB, mB, g.P1x2, g.P2x2, lane);
+        if (active) st_regs<N>(wrB[PAR], LB);
+        if (lane == 0) *mwB[PAR] = mB;
+        if (active) ld_regs<N>(sring + sl, Sc);
+        else {
+#pragma unroll
+            for (int i = 0; i < N; i++) Sc[i] = 0;
+        }
+        uint32_t S[N];
+#pragma unroll
+        for (int i = 0; i < N; i++) {
+            if (CLAMP_EACH) {
+                uint32_t t = __vminu2(Sc[i] + Lv[i], kMaxCostX2);
+                t = __vminu2(t + LA[i], kMaxCostX2);
+                S[i] = __vminu2(t + LB[i], kMaxCostX2);
+            } else {
+                S[i] = __vminu2(Sc[i] + Lv[i] + LA[i] + LB[i], kMaxCostX2);
+            }
+        }
+        const int q = r & (kSoutRing - 1);
+        if (r >= kSoutRing) named_bar_sync(BAR_EMPTY + q, nall);    // the WTA warps have taken row r - kSoutRing
+        if (active) st_regs<N>(sout + q * ringStride, S);
+        named_bar_arrive(BAR_FULL + q, nall);
+        named_bar_sync(BAR_ROW, nrow);
+    };
+    int r = 0;
+    for (; r + 1 < H; r += 2) {
+        row(std::integral_constant<int, 0>{}, r);
+        row(std::integral_constant<int, 1>{}, r + 1);
+    }
+    if (r < H) row(std::integral_constant<int, 0>{}, r);
+    cp_async_wait<0>();
 }
 
 }  // namespace b200sgm
