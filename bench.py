@@ -43,7 +43,7 @@ def parse():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--config", default="c3", choices=sorted(CONFIGS))
     ap.add_argument("--frames", type=int, default=16, help="distinct frames per step per GPU")
-    ap.add_argument("--lanes", type=int, default=4, help="frames in flight per GPU")
+    ap.add_argument("--lanes", type=int, default=2, help="frames in flight per GPU")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--cpu-frames", type=int, default=0, help="frames in the CPU sample (default: one per core)")
@@ -300,8 +300,9 @@ def run_b200(args, cfg):
         st_ms, nfr = eng.stage_times(0)
         eng.profile(False)
         stages = {k: v / max(nfr, 1) for k, v in st_ms.items()}
-        total = sum(stages.values())
-        dom = max(stages, key=stages.get)
+        stages["aggregate_wta"] = stages.get("horizontal", 0.0) + stages.get("vertical_wta", 0.0)
+        total = sum(v for k, v in stages.items() if k != "aggregate_wta")
+        dom = max((k for k in stages if k != "aggregate_wta"), key=stages.get)
         peaks = {}
         try:
             peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))

@@ -45,11 +45,12 @@ struct Lane {
     // stage profiling (b200sgm_profile): ring of event sets, harvested by b200sgm_stage_times
     std::vector<cudaEvent_t> prof_events;           // kProfRing * (kStages + 1)
     int prof_head = 0, prof_count = 0;
-    double stage_ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    double stage_ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // >= kStages
+    std::vector<float> timeline;                    // (kStages+1) timestamps per harvested frame, ms since prof_ref
     uint64_t stage_frames = 0;
 };
 
-constexpr int kStages = 6;    // prefilter, cost, aggregate+wta, lrcheck, median, speckle
+constexpr int kStages = 7;    // prefilter, cost, horizontal, vertical+wta, lrcheck, median, speckle
 constexpr int kProfRing = 256;
 constexpr int kMaxStrips = 1024;
 constexpr int kVertMaxWarps = 16;
@@ -66,6 +67,7 @@ struct b200sgm_engine {
     std::atomic<uint64_t> launches{0};
     int path = 0;
     bool profile = false;
+    cudaEvent_t prof_ref = nullptr;   // time origin of the stage timeline
     int num_sms = 148;
     cudaEvent_t coop_prev = nullptr;   // last cooperative (k_vert) launch of any lane: such kernels never overlap
     int clock_khz = 1965000;
@@ -92,6 +94,13 @@ namespace {
             return B200SGM_ECUDA;                                                              \
         }                                                                                      \
     } while (0)
+
+// Stage profiling: records event `idx` of the current frame's event set (no-op unless profiling is on).
+inline void prof_mark(b200sgm_engine* h, Lane& ln, int idx, cudaStream_t st)
+{
+    if (!h->profile || ln.prof_events.empty()) return;
+    cudaEventRecord(ln.prof_events[size_t(ln.prof_head) * (kStages + 1) + idx], st);
+}
 
 int fail(b200sgm_engine* h, int code, const std::string& msg)
 {
@@ -180,7 +189,10 @@ struct VertPlan { bool ok; int nstrips, twmax; size_t smem; bool two_warps; };
 VertPlan plan_vert(const b200sgm_engine* h, const Eff& e)
 {
     VertPlan p{false, 0, 0, 0, false};
-    static const bool two = [] { const char* v = getenv("B200SGM_VERT_ONE_WARP"); return !(v && atoi(v)); }();
+    // The warp-specialised sweep (k_vert3) is not faster on its own and fills the register file, which keeps the
+    // other lanes' kernels off the SMs; the one-warp-per-column sweep (k_vert) co-runs with them and wins on
+    // throughput.  B200SGM_VERT_WARPSPEC=1 selects k_vert3 for experiments.
+    static const bool two = [] { const char* v = getenv("B200SGM_VERT_WARPSPEC"); return v && atoi(v); }();
     if (e.W1 < 2) return p;
     static const int per_sm = [] { const char* v = getenv("B200SGM_VERT_STRIPS_PER_SM"); return v ? std::max(1, atoi(v)) : 1; }();
     int n = std::min(h->num_sms * per_sm, e.W1 / 2);
@@ -242,9 +254,13 @@ template <int N>
 int launch_fused(b200sgm_engine* h, Lane& ln, const Eff& e, cudaStream_t st, bool hybrid)
 {
     const uint32_t P1x2 = uint32_t(e.P1) * 0x10001u, P2x2 = uint32_t(e.P2) * 0x10001u;
-    const int wpb = 4;
-    k_horiz<N><<<(e.H + wpb - 1) / wpb, 32 * wpb, 0, st>>>(ln.C, ln.S, e.W1, e.H, e.Dp, P1x2, P2x2);
+    int wpb = 4;
+    while (wpb > 1 && size_t(wpb) * 4 * kHorizRing * e.Dp * sizeof(uint16_t) > 200 * 1024) wpb /= 2;
+    const size_t hsmem = size_t(wpb) * 4 * kHorizRing * e.Dp * sizeof(uint16_t);
+    CUDA_TRY(h, cudaFuncSetAttribute(k_horiz<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(hsmem)));
+    k_horiz<N><<<(e.H + wpb - 1) / wpb, 32 * wpb, hsmem, st>>>(ln.C, ln.S, e.W1, e.H, e.Dp, P1x2, P2x2);
     LAUNCH_CHECK(h);
+    prof_mark(h, ln, 3, st);
     VertPlan vp = plan_vert(h, e);
     if (hybrid || !vp.ok) {
         static const int dirs_sgbm[3][2] = {{1, 1}, {0, 1}, {-1, 1}};
@@ -282,7 +298,7 @@ int launch_fused(b200sgm_engine* h, Lane& ln, const Eff& e, cudaStream_t st, boo
 template <int N>
 int launch_agg_n(b200sgm_engine* h, Lane& ln, const Eff& e, cudaStream_t st)
 {
-    if (h->path == 1) return launch_paths_generic<N>(h, ln, e, st);
+    if (h->path == 1) { prof_mark(h, ln, 3, st); return launch_paths_generic<N>(h, ln, e, st); }
     return launch_fused<N>(h, ln, e, st, h->path == 2);
 }
 
@@ -299,14 +315,7 @@ int launch_aggregation(b200sgm_engine* h, Lane& ln, const Eff& e, cudaStream_t s
     return fail(h, B200SGM_EINVAL, "bad nreg");
 }
 
-// Stage profiling: records event `idx` of the current frame's event set (no-op unless profiling is on).
-inline void prof_mark(b200sgm_engine* h, Lane& ln, int idx, cudaStream_t st)
-{
-    if (!h->profile || ln.prof_events.empty()) return;
-    cudaEventRecord(ln.prof_events[size_t(ln.prof_head) * (kStages + 1) + idx], st);
-}
-
-void prof_harvest(Lane& ln)
+void prof_harvest(Lane& ln, cudaEvent_t ref = nullptr)
 {
     // all recorded sets are complete once the stream is synchronised
     int first = (ln.prof_head - ln.prof_count + kProfRing) % kProfRing;
@@ -315,6 +324,13 @@ void prof_harvest(Lane& ln)
         for (int s = 0; s < kStages; s++) {
             float ms = 0;
             if (cudaEventElapsedTime(&ms, ln.prof_events[base + s], ln.prof_events[base + s + 1]) == cudaSuccess) ln.stage_ms[s] += ms;
+        }
+        if (ref && ln.timeline.size() < size_t(4096) * (kStages + 1)) {
+            for (int s = 0; s <= kStages; s++) {
+                float ms = 0;
+                cudaEventElapsedTime(&ms, ref, ln.prof_events[base + s]);
+                ln.timeline.push_back(ms);
+            }
         }
         ln.stage_frames++;
     }
@@ -331,7 +347,7 @@ int run_pipeline(b200sgm_engine* h, Lane& ln, const Eff& e, const uint8_t* dL, s
             ln.prof_events.resize(size_t(kProfRing) * (kStages + 1));
             for (auto& ev : ln.prof_events) CUDA_TRY(h, cudaEventCreate(&ev));
         }
-        if (ln.prof_count == kProfRing) { CUDA_TRY(h, cudaStreamSynchronize(st)); prof_harvest(ln); }
+        if (ln.prof_count == kProfRing) { CUDA_TRY(h, cudaStreamSynchronize(st)); prof_harvest(ln, h->prof_ref); }
     }
     prof_mark(h, ln, 0, st);
     {
@@ -377,21 +393,23 @@ int run_pipeline(b200sgm_engine* h, Lane& ln, const Eff& e, const uint8_t* dL, s
     if (e.W1 > 0) {
         int rc = launch_aggregation(h, ln, e, st);
         if (rc) return rc;
+    } else {
+        prof_mark(h, ln, 3, st);
     }
-    prof_mark(h, ln, 3, st);
+    prof_mark(h, ln, 4, st);
     if (e.W1 > 0) {
         WtaGeom wg{e.W, e.H, e.W1, e.minX1, e.minD, e.D, e.Dp, e.uniq, e.d12, e.INVALID};
         dim3 block(256), grid2((e.W1 + 255) / 256, H);
         k_lrcheck<<<grid2, block, 0, st>>>(ln.disp_wta, ln.disp2key, wg);
         LAUNCH_CHECK(h);
     }
-    prof_mark(h, ln, 4, st);
+    prof_mark(h, ln, 5, st);
     {
         dim3 block(256), grid((W + 255) / 256, H);
         k_median3<<<grid, block, 0, st>>>(ln.disp_wta, ln.disp_med, W, H);
         LAUNCH_CHECK(h);
     }
-    prof_mark(h, ln, 5, st);
+    prof_mark(h, ln, 6, st);
     CUDA_TRY(h, cudaMemcpyAsync(ln.disp_out, ln.disp_med, size_t(npix) * 2, cudaMemcpyDeviceToDevice, st));
     if (e.speckleWin > 0) {
         const int maxDiff = 16 * e.speckleRange;
@@ -405,7 +423,7 @@ int run_pipeline(b200sgm_engine* h, Lane& ln, const Eff& e, const uint8_t* dL, s
         k_speckle_apply<<<(npix + 255) / 256, 256, 0, st>>>(ln.disp_out, ln.label, ln.parent, ln.csize, npix, e.INVALID, e.speckleWin);
         LAUNCH_CHECK(h);
     }
-    prof_mark(h, ln, 6, st);
+    prof_mark(h, ln, 7, st);
     if (h->profile && !ln.prof_events.empty()) { ln.prof_head = (ln.prof_head + 1) % kProfRing; ln.prof_count++; }
     return B200SGM_OK;
 }
@@ -670,6 +688,14 @@ int b200sgm_profile(b200sgm_handle h, int enable)
 {
     if (!h) return B200SGM_EINVAL;
     h->profile = enable != 0;
+    if (h->profile) {
+        cudaSetDevice(h->device);
+        if (!h->prof_ref) cudaEventCreate(&h->prof_ref);
+        cudaDeviceSynchronize();
+        cudaEventRecord(h->prof_ref, h->lanes[0].stream);
+        cudaStreamSynchronize(h->lanes[0].stream);
+        for (Lane& ln : h->lanes) ln.timeline.clear();
+    }
     return B200SGM_OK;
 }
 
@@ -682,10 +708,22 @@ int b200sgm_stage_times(b200sgm_handle h, int lane, double* ms, int n, uint64_t*
     Lane& ln = h->lanes[lane];
     CUDA_TRY(h, cudaStreamSynchronize(ln.stream));
     CUDA_TRY(h, cudaDeviceSynchronize());   // frames may have been enqueued on caller-provided streams
-    prof_harvest(ln);
+    prof_harvest(ln, h->prof_ref);
     for (int s = 0; s < kStages; s++) { ms[s] = ln.stage_ms[s]; ln.stage_ms[s] = 0; }
     if (frames) *frames = ln.stage_frames;
     ln.stage_frames = 0;
+    return B200SGM_OK;
+}
+
+int b200sgm_stage_timeline(b200sgm_handle h, int lane, float* out, int max_floats, int* n_floats)
+{
+    if (!h || !n_floats) return B200SGM_EINVAL;
+    int rc = lane_check(h, lane);
+    if (rc) return rc;
+    Lane& ln = h->lanes[lane];
+    const int n = int(std::min<size_t>(ln.timeline.size(), size_t(std::max(max_floats, 0))));
+    if (out) memcpy(out, ln.timeline.data(), size_t(n) * sizeof(float));
+    *n_floats = int(ln.timeline.size());
     return B200SGM_OK;
 }
 

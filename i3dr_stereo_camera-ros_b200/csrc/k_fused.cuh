@@ -18,75 +18,104 @@
 
 namespace b200sgm {
 
+constexpr int kVertRing = 4;   // rows of C / S_h in flight per column (cp.async ring in shared memory)
+
+template <int BYTES>
+__device__ __forceinline__ void cp_async(void* smem_dst, const void* gsrc)
+{
+    const uint32_t d = uint32_t(__cvta_generic_to_shared(smem_dst));
+    if constexpr (BYTES == 16) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc) : "memory");
+    else if constexpr (BYTES == 8) asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(gsrc) : "memory");
+    else asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d), "l"(gsrc) : "memory");
+}
+// copies this lane's 2N costs
+template <int N>
+__device__ __forceinline__ void cp_async_lane(uint16_t* smem_dst, const uint16_t* gsrc)
+{
+    if constexpr (N <= 4) cp_async<4 * N>(smem_dst, gsrc);
+    else {
+#pragma unroll
+        for (int q = 0; q < N / 4; q++) cp_async<16>(smem_dst + 8 * q, gsrc + 8 * q);
+    }
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int PENDING>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(PENDING) : "memory"); }
+
+
 // ------------------------------------------------------------------------------------------------
 // Horizontal pair.  Launch: one warp per row.
 // ------------------------------------------------------------------------------------------------
+constexpr int kHorizRing = 6;   // steps of C (and S_h) in flight per chain: cp.async ring in shared memory
+
+// dynamic smem: warps * 4 * kHorizRing * Dp * 2 bytes
 template <int N>
 __global__ void __launch_bounds__(128) k_horiz(const uint16_t* __restrict__ Cvol, uint16_t* __restrict__ Sh,
                                                int W1, int H, int Dp, uint32_t P1x2, uint32_t P2x2)
 {
-    const int lane = threadIdx.x & 31;
-    const int y = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    extern __shared__ __align__(16) uint16_t smem_h[];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int y = blockIdx.x * (blockDim.x >> 5) + wib;
     if (y >= H) return;
     const bool active = lane * 2 * N < Dp;
-    const uint16_t* Crow = Cvol + size_t(y) * W1 * Dp + lane * 2 * N;
-    uint16_t* Srow = Sh + size_t(y) * W1 * Dp + lane * 2 * N;
-    uint32_t La[N], Lb[N], Ca[N], Cb[N], Cna[N], Cnb[N];
-#pragma unroll
-    for (int j = 0; j < N; j++) { La[j] = 0; Lb[j] = 0; Ca[j] = Cb[j] = Cna[j] = Cnb[j] = kMaxCostX2; }
-    uint32_t ma = 0, mb = 0;
-    if (active) { ldg_regs<N>(Crow, Ca); ldg_regs<N>(Crow + size_t(W1 - 1) * Dp, Cb); }
+    const int lo = lane * 2 * N;
+    const uint16_t* Crow = Cvol + size_t(y) * W1 * Dp + lo;
+    uint16_t* Srow = Sh + size_t(y) * W1 * Dp + lo;
+    // per-warp rings: [array: Ca, Cb, Sa, Sb][slot][Dp]
+    uint16_t* ring = smem_h + size_t(wib) * 4 * kHorizRing * Dp + lo;
+    auto slot = [&](int arr, int s) { return ring + size_t(arr * kHorizRing + (s % kHorizRing)) * Dp; };
+    constexpr int PF = kHorizRing - 1;
     const int half = W1 >> 1;
-    // first visits: xa = i < xb = W1-1-i
-    for (int i = 0; i < half; i++) {
+    const int sec = half + (W1 & 1);                 // first second-visit step
+    auto issue = [&](int s) {                        // one commit group per step, even past the end
+        if (s < W1 && active) {
+            const int xa = s, xb = W1 - 1 - s;
+            cp_async_lane<N>(slot(0, s), Crow + size_t(xa) * Dp);
+            cp_async_lane<N>(slot(1, s), Crow + size_t(xb) * Dp);
+            if (s >= sec + PF) {                     // both first-visit stores are >= PF+1 steps old by now
+                cp_async_lane<N>(slot(2, s), Srow + size_t(xa) * Dp);
+                cp_async_lane<N>(slot(3, s), Srow + size_t(xb) * Dp);
+            }
+        }
+        cp_async_commit();
+    };
+    for (int s = 0; s < PF; s++) issue(s);
+    uint32_t La[N], Lb[N];
+#pragma unroll
+    for (int j = 0; j < N; j++) { La[j] = 0; Lb[j] = 0; }
+    uint32_t ma = 0, mb = 0;
+    for (int i = 0; i < W1; i++) {
+        issue(i + PF);
+        cp_async_wait<PF>();                         // this lane's copies for step i have landed
         const int xa = i, xb = W1 - 1 - i;
-        if (active) {   // next columns: xa+1 <= xb-1 unless the chains meet; both stay inside the row
-            ldg_regs<N>(Crow + size_t(xa + 1) * Dp, Cna);
-            ldg_regs<N>(Crow + size_t(xb - 1) * Dp, Cnb);
+        uint32_t Ca[N], Cb[N];
+        if (active) { ld_regs<N>(slot(0, i), Ca); ld_regs<N>(slot(1, i), Cb); }
+        else {
+#pragma unroll
+            for (int j = 0; j < N; j++) { Ca[j] = kMaxCostX2; Cb[j] = kMaxCostX2; }
         }
         path_step<N>(Ca, La, ma, P1x2, P2x2, lane);
         path_step<N>(Cb, Lb, mb, P1x2, P2x2, lane);
-        if (active) { st_regs<N>(Srow + size_t(xa) * Dp, La); st_regs<N>(Srow + size_t(xb) * Dp, Lb); }
-#pragma unroll
-        for (int j = 0; j < N; j++) { Ca[j] = Cna[j]; Cb[j] = Cnb[j]; }
-    }
-    int i = half;
-    if (W1 & 1) {   // both chains stand on the middle column: Ca == Cb == C[half]
-        path_step<N>(Ca, La, ma, P1x2, P2x2, lane);
-        path_step<N>(Cb, Lb, mb, P1x2, P2x2, lane);
-        if (active) {
+        if (!active) continue;
+        if (i < half) {                              // first visits: park L in S_h
+            st_regs<N>(Srow + size_t(xa) * Dp, La);
+            st_regs<N>(Srow + size_t(xb) * Dp, Lb);
+        } else if (xa == xb) {                       // odd width: both chains on the middle column
             uint32_t S[N];
 #pragma unroll
             for (int j = 0; j < N; j++) S[j] = __vminu2(La[j] + Lb[j], kMaxCostX2);
-            st_regs<N>(Srow + size_t(half) * Dp, S);
-            if (half + 1 < W1) { ldg_regs<N>(Crow + size_t(half + 1) * Dp, Ca); ldg_regs<N>(Crow + size_t(half - 1) * Dp, Cb); }
-        }
-        i = half + 1;
-    } else if (active && half < W1) {
-        // even width: after the loop Ca holds C[half] and Cb holds C[half-1], exactly the next columns
-    }
-    // second visits: xa = i > xb = W1-1-i; S_h[xa] holds L<-, S_h[xb] holds L->
-    for (; i < W1; i++) {
-        const int xa = i, xb = W1 - 1 - i;
-        uint32_t Sa[N], Sb[N];
-#pragma unroll
-        for (int j = 0; j < N; j++) { Sa[j] = 0; Sb[j] = 0; }
-        if (active) {
-            ld_regs<N>(Srow + size_t(xa) * Dp, Sa);
-            ld_regs<N>(Srow + size_t(xb) * Dp, Sb);
-            if (i + 1 < W1) { ldg_regs<N>(Crow + size_t(xa + 1) * Dp, Cna); ldg_regs<N>(Crow + size_t(xb - 1) * Dp, Cnb); }
-        }
-        path_step<N>(Ca, La, ma, P1x2, P2x2, lane);
-        path_step<N>(Cb, Lb, mb, P1x2, P2x2, lane);
-        if (active) {
+            st_regs<N>(Srow + size_t(xa) * Dp, S);
+        } else {                                     // second visits: S_h[xa] holds L<-, S_h[xb] holds L->
+            uint32_t Sa[N], Sb[N];
+            if (i >= sec + PF) { ld_regs<N>(slot(2, i), Sa); ld_regs<N>(slot(3, i), Sb); }
+            else { ld_regs<N>(Srow + size_t(xa) * Dp, Sa); ld_regs<N>(Srow + size_t(xb) * Dp, Sb); }
 #pragma unroll
             for (int j = 0; j < N; j++) { Sa[j] = __vminu2(Sa[j] + La[j], kMaxCostX2); Sb[j] = __vminu2(Sb[j] + Lb[j], kMaxCostX2); }
             st_regs<N>(Srow + size_t(xa) * Dp, Sa);
             st_regs<N>(Srow + size_t(xb) * Dp, Sb);
         }
-#pragma unroll
-        for (int j = 0; j < N; j++) { Ca[j] = Cna[j]; Cb[j] = Cnb[j]; }
     }
+    cp_async_wait<0>();
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -421,30 +450,6 @@ __global__ void __launch_bounds__(512, 1) k_vert(const uint16_t* __restrict__ Cv
     }
     if (r < H) row(std::integral_constant<int, 0>{}, r, C0, S0, C1, S1);
 }
-
-constexpr int kVertRing = 4;   // rows of C / S_h in flight per column (cp.async ring in shared memory)
-
-template <int BYTES>
-__device__ __forceinline__ void cp_async(void* smem_dst, const void* gsrc)
-{
-    const uint32_t d = uint32_t(__cvta_generic_to_shared(smem_dst));
-    if constexpr (BYTES == 16) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc) : "memory");
-    else if constexpr (BYTES == 8) asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(gsrc) : "memory");
-    else asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d), "l"(gsrc) : "memory");
-}
-// copies this lane's 2N costs
-template <int N>
-__device__ __forceinline__ void cp_async_lane(uint16_t* smem_dst, const uint16_t* gsrc)
-{
-    if constexpr (N <= 4) cp_async<4 * N>(smem_dst, gsrc);
-    else {
-#pragma unroll
-        for (int q = 0; q < N / 4; q++) cp_async<16>(smem_dst + 8 * q, gsrc + 8 * q);
-    }
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int PENDING>
-__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(PENDING) : "memory"); }
 
 // ------------------------------------------------------------------------------------------------
 // Vertical sweep, warp specialised (the default for D <= 256):

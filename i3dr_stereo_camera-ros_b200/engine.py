@@ -20,10 +20,10 @@ SYMBOLS = (
     "b200sgm_create", "b200sgm_destroy", "b200sgm_set_params", "b200sgm_get_effective_params", "b200sgm_compute",
     "b200sgm_compute_f32", "b200sgm_compute_device", "b200sgm_enqueue", "b200sgm_wait", "b200sgm_compute_xyz",
     "b200sgm_last_error", "b200sgm_version", "b200sgm_launch_count", "b200sgm_lane_stream", "b200sgm_debug_read",
-    "b200sgm_debug_set_path", "b200sgm_profile", "b200sgm_stage_times", "b200sgm_alu_peak",
+    "b200sgm_debug_set_path", "b200sgm_profile", "b200sgm_stage_times", "b200sgm_alu_peak", "b200sgm_stage_timeline",
 )
 
-STAGES = ("prefilter", "cost", "aggregate_wta", "lrcheck", "median", "speckle")
+STAGES = ("prefilter", "cost", "horizontal", "vertical_wta", "lrcheck", "median", "speckle")
 
 
 class B200SGMError(RuntimeError):
@@ -182,6 +182,14 @@ class Engine:
         fr = ctypes.c_uint64(0)
         self._check(self.lib.b200sgm_stage_times(self.h, int(lane), ms, len(STAGES), ctypes.byref(fr)))
         return {k: ms[i] for i, k in enumerate(STAGES)}, fr.value
+
+    def stage_timeline(self, lane=0):
+        """(frames, 7) array of stage-boundary timestamps in ms since profile(True); call stage_times first."""
+        n = ctypes.c_int(0)
+        self._check(self.lib.b200sgm_stage_timeline(self.h, int(lane), None, 0, ctypes.byref(n)))
+        buf = np.zeros(n.value, np.float32)
+        self._check(self.lib.b200sgm_stage_timeline(self.h, int(lane), buf.ctypes.data_as(ctypes.c_void_p), n.value, ctypes.byref(n)))
+        return buf.reshape(-1, len(STAGES) + 1)
 
     def set_path(self, path: int):
         self._check(self.lib.b200sgm_debug_set_path(self.h, int(path)))

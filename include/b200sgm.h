@@ -130,11 +130,14 @@ int b200sgm_launch_count(b200sgm_handle h, uint64_t *count);
  * stream the kernels are launched on. */
 int b200sgm_lane_stream(b200sgm_handle h, int lane, void **cuda_stream);
 /* Stage profiling: when enabled every frame records CUDA events at the stage boundaries on the stream it
- * runs on.  b200sgm_stage_times synchronises, returns the accumulated milliseconds of the 6 stages
- * {prefilter, cost, aggregate+wta, lrcheck, median, speckle} since the previous call, the number of frames
+ * runs on.  b200sgm_stage_times synchronises, returns the accumulated milliseconds of the 7 stages
+ * {prefilter, cost, horizontal, vertical+wta, lrcheck, median, speckle} since the previous call, the number of frames
  * they cover, and resets the accumulators. */
 int b200sgm_profile(b200sgm_handle h, int enable);
 int b200sgm_stage_times(b200sgm_handle h, int lane, double *ms, int n, uint64_t *frames);
+/* Timeline of the frames harvested by b200sgm_stage_times since profiling was enabled: 8 stage-boundary
+ * timestamps per frame, in ms since b200sgm_profile(h, 1).  *n_floats receives the number available. */
+int b200sgm_stage_timeline(b200sgm_handle h, int lane, float *out, int max_floats, int *n_floats);
 /* Measures the packed 16-bit integer issue peak of `device` with a register-resident VIMNMX3.U16x2 /
  * VIADD.16x2 microbenchmark (the ALU roofline denominator).  Results in 1e12
  * elementary 16-bit ops per second: [0] = 3-input min (4 ops per lane-instruction), [1] = 2-input min
