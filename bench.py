@@ -32,7 +32,7 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 import b200sgm  # noqa: E402
-from b200sgm import CONFIGS, synth  # noqa: E402
+from b200sgm import CONFIGS, synth, stream  # noqa: E402
 
 
 def parse():
@@ -267,13 +267,9 @@ def run_b200(args, cfg):
     e2e = None
     if not args.no_e2e:
         def host_step():
-            for i in range(NF):
-                ln = i % lanes
-                if i >= lanes:
-                    eng.wait(ln)
-                eng.enqueue_ptr(ln, hostL[i].data_ptr(), W, hostR[i].data_ptr(), W, W, H, hostD[i].data_ptr(), W * 2)
-            for ln in range(min(lanes, NF)):
-                eng.wait(ln)
+            stream.run_lanes(lanes, range(NF),
+                             lambda ln, i: eng.enqueue_ptr(ln, hostL[i].data_ptr(), W, hostR[i].data_ptr(), W, W, H, hostD[i].data_ptr(), W * 2),
+                             eng.wait)
         for _ in range(max(1, args.warmup)):
             host_step()
         barrier()

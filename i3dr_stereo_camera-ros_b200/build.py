@@ -41,6 +41,24 @@ def build(force: bool = False, verbose: bool = False) -> str:
     return LIB
 
 
+HOST = os.path.join(HERE, "host")
+HARNESS = os.path.join(HOST, "harness")
+
+
+def build_host(force: bool = False) -> str:
+    """Builds the ROS/OpenCV-free harness around the C++ matcher adapter (host/matcherB200SGM.cpp)."""
+    srcs = [os.path.join(HOST, "harness.cpp"), os.path.join(HOST, "matcherB200SGM.cpp")]
+    deps = srcs + [os.path.join(HOST, f) for f in ("matcherB200SGM.h", "matcher_interface.h", "cv_stub.h")] + [LIB]
+    if not force and os.path.exists(HARNESS) and all(os.path.getmtime(d) <= os.path.getmtime(HARNESS) for d in deps):
+        return HARNESS
+    cmd = ["g++", "-std=c++17", "-O2", "-DB200SGM_STANDALONE", "-I" + os.path.join(HERE, "..", "include"), "-I" + HOST,
+           "-o", HARNESS] + srcs + ["-L" + HERE, "-lb200sgm", "-Wl,-rpath,$ORIGIN/.."]
+    print("[b200sgm] " + " ".join(cmd), file=sys.stderr)
+    subprocess.check_call(cmd)
+    return HARNESS
+
+
 if __name__ == "__main__":
     build(force="--force" in sys.argv, verbose="-v" in sys.argv)
+    build_host(force="--force" in sys.argv)
     print(LIB)
