@@ -30,7 +30,8 @@ struct Lane {
     // device buffers
     uint8_t *left = nullptr, *right = nullptr;      // W x H, pitch = W
     Feat *feat_l = nullptr, *feat_r = nullptr;      // W x H
-    uint16_t *C = nullptr, *S = nullptr;            // [H][W1][Dp]
+    uint16_t *C = nullptr, *S = nullptr;            // [H][W1][Dp], paired layout (k_path.cuh)
+    uint16_t *ckpt = nullptr;                       // k_horiz checkpoints [H][ceil(W1/kHT)][Dp]
     uint32_t* disp2key = nullptr;                   // W x H
     int16_t *disp_wta = nullptr, *disp_med = nullptr, *disp_out = nullptr;  // W x H
     int *label = nullptr, *csize = nullptr, *parent = nullptr, *runlen = nullptr;   // W x H (speckle filter)
@@ -169,7 +170,7 @@ int launch_paths_generic(b200sgm_engine* h, Lane& ln, const Eff& e, cudaStream_t
         g.dx = e.mode == B200SGM_MODE_HH ? dirs_hh[r][0] : dirs_sgbm[r][0];
         g.dy = e.mode == B200SGM_MODE_HH ? dirs_hh[r][1] : dirs_sgbm[r][1];
         g.nchains = chain_count(e.W1, e.H, g.dx, g.dy);
-        g.P1x2 = uint32_t(e.P1) * 0x10001u; g.P2x2 = uint32_t(e.P2) * 0x10001u;
+        g.P1 = e.P1; g.P2 = e.P2;
         const int wpb = 4;
         dim3 grid((g.nchains + wpb - 1) / wpb), block(32 * wpb);
         if (r == 0) k_path_generic<N, true><<<grid, block, 0, st>>>(ln.C, ln.S, g);
@@ -184,25 +185,18 @@ int launch_paths_generic(b200sgm_engine* h, Lane& ln, const Eff& e, cudaStream_t
 }
 
 // ---- fused path: k_horiz + cooperative k_vert ---------------------------------------------------------
-struct VertPlan { bool ok; int nstrips, twmax; size_t smem; bool two_warps; };
+struct VertPlan { bool ok; int nstrips, twmax; size_t smem; };
 
 VertPlan plan_vert(const b200sgm_engine* h, const Eff& e)
 {
-    VertPlan p{false, 0, 0, 0, false};
-    // The warp-specialised sweep (k_vert3) is not faster on its own and fills the register file, which keeps the
-    // other lanes' kernels off the SMs; the one-warp-per-column sweep (k_vert) co-runs with them and wins on
-    // throughput.  B200SGM_VERT_WARPSPEC=1 selects k_vert3 for experiments.
-    static const bool two = [] { const char* v = getenv("B200SGM_VERT_WARPSPEC"); return v && atoi(v); }();
+    VertPlan p{false, 0, 0, 0};
     if (e.W1 < 2) return p;
-    static const int per_sm = [] { const char* v = getenv("B200SGM_VERT_STRIPS_PER_SM"); return v ? std::max(1, atoi(v)) : 1; }();
-    int n = std::min(h->num_sms * per_sm, e.W1 / 2);
+    int n = std::min(h->num_sms, e.W1 / 2);
     n = std::min(n, kMaxStrips);
     int tw = (e.W1 + n - 1) / n;
     if (tw > kVertMaxWarps) return p;      // wider than one co-resident wave of strips: use the hybrid path
     p.nstrips = n; p.twmax = tw;
-    p.two_warps = two && e.nreg <= 4;     // two warps per column: 2*tw <= 32 warps, 64 registers per thread
-    p.smem = size_t(4) * (tw + 2) * e.Dp * sizeof(uint16_t) + size_t(4) * (tw + 2) * sizeof(uint32_t) +
-             (p.two_warps ? 16 + size_t(2 * kVertRing + kSoutRing) * tw * e.Dp * sizeof(uint16_t) : 0);
+    p.smem = vert_smem_bytes(tw, e.Dp);
     p.ok = p.smem <= 200 * 1024;
     return p;
 }
@@ -213,11 +207,9 @@ int launch_vert_t(b200sgm_engine* h, Lane& ln, const Eff& e, const VertPlan& vp,
     VertGeom g;
     g.w = WtaGeom{e.W, e.H, e.W1, e.minX1, e.minD, e.D, e.Dp, e.uniq, e.d12, e.INVALID};
     g.nstrips = vp.nstrips; g.twmax = vp.twmax;
-    g.P1x2 = uint32_t(e.P1) * 0x10001u; g.P2x2 = uint32_t(e.P2) * 0x10001u;
+    g.P1 = e.P1; g.P2 = e.P2;
     g.spin_limit = (long long)h->clock_khz * 500;   // ~0.5 s of SM clock ticks
-    if (getenv("B200SGM_DEBUG_NO_WAIT")) g.spin_limit = 0;   // timing experiment only: results are garbage
-    g.debug_no_exchange = getenv("B200SGM_DEBUG_NO_EXCHANGE") ? 1 : 0;
-    auto kern = vp.two_warps ? k_vert3<N, UP, DO_WTA, FULL, CLAMP_EACH> : k_vert<N, UP, DO_WTA, FULL, CLAMP_EACH>;
+    auto kern = k_vert<N, UP, DO_WTA, FULL, CLAMP_EACH>;
     CUDA_TRY(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(vp.smem)));
     CUDA_TRY(h, cudaMemsetAsync(ln.xbuf, 0, size_t(2) * vp.nstrips * kXbufGen * (e.Dp / 2) * sizeof(uint2), st));
     const uint16_t* Cp = ln.C; uint16_t* Sp = ln.S; int16_t* dp = ln.disp_wta; uint32_t* kp = ln.disp2key;
@@ -226,7 +218,7 @@ int launch_vert_t(b200sgm_engine* h, Lane& ln, const Eff& e, const VertPlan& vp,
     {
         std::lock_guard<std::mutex> lk(h->mu);
         if (h->coop_prev) CUDA_TRY(h, cudaStreamWaitEvent(st, h->coop_prev, 0));
-        CUDA_TRY(h, cudaLaunchCooperativeKernel((void*)kern, dim3(vp.nstrips), dim3((vp.two_warps ? 64 : 32) * vp.twmax), args, vp.smem, st));
+        CUDA_TRY(h, cudaLaunchCooperativeKernel((void*)kern, dim3(vp.nstrips), dim3(32 * vp.twmax), args, vp.smem, st));
         h->launches++;
         CUDA_TRY(h, cudaEventRecord(ln.coop_ev, st));
         h->coop_prev = ln.coop_ev;
@@ -253,12 +245,12 @@ int launch_vert(b200sgm_engine* h, Lane& ln, const Eff& e, const VertPlan& vp, c
 template <int N>
 int launch_fused(b200sgm_engine* h, Lane& ln, const Eff& e, cudaStream_t st, bool hybrid)
 {
-    const uint32_t P1x2 = uint32_t(e.P1) * 0x10001u, P2x2 = uint32_t(e.P2) * 0x10001u;
-    int wpb = 4;
-    while (wpb > 1 && size_t(wpb) * 4 * kHorizRing * e.Dp * sizeof(uint16_t) > 200 * 1024) wpb /= 2;
-    const size_t hsmem = size_t(wpb) * 4 * kHorizRing * e.Dp * sizeof(uint16_t);
+    int wpb = 2;
+    while (wpb > 1 && size_t(wpb) * horiz_smem_per_warp(e.Dp) > 200 * 1024) wpb /= 2;
+    const size_t hsmem = size_t(wpb) * horiz_smem_per_warp(e.Dp);
+    if (hsmem > 200 * 1024) return fail(h, B200SGM_EINVAL, "numDisparities too large for the horizontal kernel");
     CUDA_TRY(h, cudaFuncSetAttribute(k_horiz<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(hsmem)));
-    k_horiz<N><<<(e.H + wpb - 1) / wpb, 32 * wpb, hsmem, st>>>(ln.C, ln.S, e.W1, e.H, e.Dp, P1x2, P2x2);
+    k_horiz<N><<<(e.H + wpb - 1) / wpb, 32 * wpb, hsmem, st>>>(ln.C, ln.S, ln.ckpt, e.W1, e.H, e.Dp, e.P1, e.P2);
     LAUNCH_CHECK(h);
     prof_mark(h, ln, 3, st);
     VertPlan vp = plan_vert(h, e);
@@ -272,8 +264,8 @@ int launch_fused(b200sgm_engine* h, Lane& ln, const Eff& e, cudaStream_t st, boo
             g.dx = e.mode == B200SGM_MODE_HH ? dirs_hh[r][0] : dirs_sgbm[r][0];
             g.dy = e.mode == B200SGM_MODE_HH ? dirs_hh[r][1] : dirs_sgbm[r][1];
             g.nchains = chain_count(e.W1, e.H, g.dx, g.dy);
-            g.P1x2 = P1x2; g.P2x2 = P2x2;
-            k_path_generic<N, false><<<(g.nchains + wpb - 1) / wpb, 32 * wpb, 0, st>>>(ln.C, ln.S, g);
+            g.P1 = e.P1; g.P2 = e.P2;
+            k_path_generic<N, false><<<(g.nchains + 3) / 4, 128, 0, st>>>(ln.C, ln.S, g);
             LAUNCH_CHECK(h);
         }
         WtaGeom wg{e.W, e.H, e.W1, e.minX1, e.minD, e.D, e.Dp, e.uniq, e.d12, e.INVALID};
@@ -438,7 +430,7 @@ int lane_check(b200sgm_engine* h, int lane)
 
 void free_lane(Lane& ln)
 {
-    cudaFree(ln.left); cudaFree(ln.right); cudaFree(ln.feat_l); cudaFree(ln.feat_r); cudaFree(ln.C); cudaFree(ln.S);
+    cudaFree(ln.left); cudaFree(ln.right); cudaFree(ln.feat_l); cudaFree(ln.feat_r); cudaFree(ln.C); cudaFree(ln.S); cudaFree(ln.ckpt);
     cudaFree(ln.disp2key); cudaFree(ln.disp_wta); cudaFree(ln.disp_med); cudaFree(ln.disp_out); cudaFree(ln.label);
     cudaFree(ln.csize); cudaFree(ln.parent); cudaFree(ln.runlen); cudaFree(ln.f32a); cudaFree(ln.f32b); cudaFree(ln.points); cudaFree(ln.block_count); cudaFree(ln.total);
     if (ln.h_total) cudaFreeHost(ln.h_total);
@@ -481,6 +473,7 @@ int b200sgm_create(int device, int max_width, int max_height, int max_disparitie
         ok = ok && cudaMalloc(&ln.left, npix) == cudaSuccess && cudaMalloc(&ln.right, npix) == cudaSuccess;
         ok = ok && cudaMalloc(&ln.feat_l, npix * sizeof(Feat)) == cudaSuccess && cudaMalloc(&ln.feat_r, npix * sizeof(Feat)) == cudaSuccess;
         ok = ok && cudaMalloc(&ln.C, vol) == cudaSuccess && cudaMalloc(&ln.S, vol) == cudaSuccess;
+        ok = ok && cudaMalloc(&ln.ckpt, horiz_ckpt_elems(max_width, max_height, int(Dp)) * sizeof(uint16_t)) == cudaSuccess;
         ok = ok && cudaMalloc(&ln.disp2key, npix * 4) == cudaSuccess;
         ok = ok && cudaMalloc(&ln.disp_wta, npix * 2) == cudaSuccess && cudaMalloc(&ln.disp_med, npix * 2) == cudaSuccess && cudaMalloc(&ln.disp_out, npix * 2) == cudaSuccess;
         ok = ok && cudaMalloc(&ln.label, npix * 4) == cudaSuccess && cudaMalloc(&ln.csize, npix * 4) == cudaSuccess;
@@ -746,6 +739,19 @@ int b200sgm_debug_read(b200sgm_handle h, int lane, const char* what, void* host,
         if (make_eff(h, 1, 1, e) == 0) *dp = e.Dp;
     }
     CUDA_TRY(h, cudaMemcpy(host, src, bytes, cudaMemcpyDeviceToHost));
+    if (src == ln.C || src == ln.S) {
+        // device volumes use the paired layout (word w = cell w | cell Dh+w << 16): hand back natural order
+        Eff e;
+        if (make_eff(h, 1, 1, e) == 0 && e.Dp > 0) {
+            const size_t Dp = size_t(e.Dp), Dh = Dp / 2;
+            std::vector<uint16_t> tmp(Dp);
+            uint16_t* v = static_cast<uint16_t*>(host);
+            for (size_t px = 0; px + 1 <= bytes / (Dp * 2); px++, v += Dp) {
+                for (size_t w = 0; w < Dh; w++) { tmp[w] = v[2 * w]; tmp[Dh + w] = v[2 * w + 1]; }
+                memcpy(v, tmp.data(), Dp * 2);
+            }
+        }
+    }
     return B200SGM_OK;
 }
 

@@ -61,8 +61,8 @@ __device__ __forceinline__ int bt_pixel_cost(Feat a, Feat b)
 // A.3 + A.4, generic version: one CTA owns TX valid columns x DCP disparity pairs and slides down a
 // segment of rows.  Per entering row: pixel costs for TX+2*SW2 columns (x1-domain replicate clamp) go
 // to shared memory, a sliding horizontal window produces hsum, and a ring of `bs` hsum rows in shared
-// memory gives the vertical sliding sum C.  Output volume layout: C[y][x1][Dp] uint16, cells with
-// disparity index >= D hold kMaxCost.
+// memory gives the vertical sliding sum C.  Output volume layout: C[y][x1][Dp/2] uint32 words in the paired
+// layout of k_path.cuh (word w = cell w | cell Dh+w << 16); cells with disparity index >= D hold kMaxCost.
 // dynamic smem: ((TX + 2*SW2) + bs*TX + TX) * DCP * 4 bytes.
 // ------------------------------------------------------------------------------------------------
 struct CostGeom {
@@ -80,7 +80,8 @@ __global__ void __launch_bounds__(256) k_cost_generic(const Feat* __restrict__ f
     uint32_t* ring = pd + TXH * g.DCP;            // [bs][TX][DCP]
     uint32_t* crun = ring + bs * g.TX * g.DCP;    // [TX][DCP]
     const int tx0 = blockIdx.x * g.TX;
-    const int k0 = blockIdx.y * g.DCP * 2;        // first disparity index of this chunk
+    const int k0 = blockIdx.y * g.DCP;            // first word (= low-half disparity index) of this chunk
+    const int Dh = g.Dp >> 1;
     const int ya = blockIdx.z * g.RS;
     const int yb = min(ya + g.RS, g.H);
     const int t = threadIdx.x;
@@ -100,13 +101,13 @@ __global__ void __launch_bounds__(256) k_cost_generic(const Feat* __restrict__ f
             int col = i / g.DCP, p = i - col * g.DCP;
             int x1 = min(max(tx0 - g.SW2 + col, 0), g.W1 - 1);
             int x = x1 + g.minX1;
-            int k = k0 + 2 * p;
+            int k = k0 + p;
             uint32_t v = 0;
-            if (k < g.D) {
+            if (k < g.D && k < Dh) {
                 Feat a = __ldg(frow_l + x);
                 int xr = x - (k + g.minD);
                 v = uint32_t(bt_pixel_cost(a, __ldg(frow_r + xr)));
-                if (k + 1 < g.D) v |= uint32_t(bt_pixel_cost(a, __ldg(frow_r + xr - 1))) << 16;
+                if (k + Dh < g.D) v |= uint32_t(bt_pixel_cost(a, __ldg(frow_r + xr - Dh))) << 16;
             }
             pd[i] = v;
         }
@@ -123,11 +124,11 @@ __global__ void __launch_bounds__(256) k_cost_generic(const Feat* __restrict__ f
                 uint32_t cr = crun[c * g.DCP + dp] + hs - old;
                 crun[c * g.DCP + dp] = cr;
                 int y = ya + s - (bs - 1);
-                int k = k0 + 2 * dp;
-                if (y >= ya && tx0 + c < g.W1 && k < g.Dp) {
+                int k = k0 + dp;
+                if (y >= ya && tx0 + c < g.W1 && k < Dh) {
                     if (k >= g.D) cr = kMaxCostX2;
-                    else if (k + 1 >= g.D) cr = (cr & 0xFFFFu) | (uint32_t(kMaxCost) << 16);
-                    *reinterpret_cast<uint32_t*>(Cvol + (size_t(y) * g.W1 + tx0 + c) * g.Dp + k) = cr;
+                    else if (k + Dh >= g.D) cr = (cr & 0xFFFFu) | (uint32_t(kMaxCost) << 16);
+                    *reinterpret_cast<uint32_t*>(Cvol + (size_t(y) * g.W1 + tx0 + c) * g.Dp + 2 * k) = cr;
                 }
             }
         }
@@ -141,7 +142,8 @@ __global__ void __launch_bounds__(256) k_cost_generic(const Feat* __restrict__ f
 //
 // Per entering row:
 //   stage   : the row's prefiltered pixels are repacked into shared memory as signed 16x2 operands:
-//             right image: for every xr the pair (f[xr], f[xr-1]) that a disparity pair (d, d+1) needs;
+//             right image: for every xr the pair (f[xr], f[xr-Dh]) that a disparity pair (d, d+Dh) of the
+//             paired volume layout (k_path.cuh) needs;
 //             left image: every field replicated into both halves.  The raw channel is pre-scaled by 64
 //             so that (cost >> 2) is the high byte of each half (one PRMT).
 //   phase 1 : lanes <-> columns.  Birchfield-Tomasi cost of a disparity pair = 2 x {VIADD.16x2,
@@ -156,7 +158,7 @@ struct CostFastGeom {
 
 constexpr int kCfTXH = 64;    // tile columns incl. halo
 constexpr int kCfDCP = 32;    // disparity pairs per CTA
-constexpr int kCfNRP = 128;   // right-image pair records per row (>= TXH + 2*DCP - 2)
+constexpr int kCfNRP = 128;   // right-image pair records per row (>= TXH + DCP - 1)
 constexpr int kCfPPT = 8;     // disparity pairs per thread in phase 1
 
 inline size_t cost_fast_smem(int SW2)
@@ -186,15 +188,16 @@ __global__ void __launch_bounds__(256, 2) k_cost_fast(const Feat* __restrict__ f
 
     const int t = threadIdx.x, lane = t & 31, w = t >> 5;
     const int tx0 = blockIdx.x * TX;
-    const int k0 = blockIdx.y * kCfDCP * 2;
+    const int k0 = blockIdx.y * kCfDCP;          // first word of this chunk: cells k0+p and Dh+k0+p
+    const int Dh = g.Dp >> 1;
     const int ya = blockIdx.z * g.RS, yb = min(ya + g.RS, g.H);
     auto col_x = [&](int c) { return min(max(tx0 - SW2 + c, 0), g.W1 - 1) + g.minX1; };
-    const int xr_min = col_x(0) - g.minD - k0 - 2 * (kCfDCP - 1);
-    const int nR = col_x(kCfTXH - 1) - col_x(0) + 2 * (kCfDCP - 1) + 1;
+    const int xr_min = col_x(0) - g.minD - k0 - (kCfDCP - 1);
+    const int nR = col_x(kCfTXH - 1) - col_x(0) + (kCfDCP - 1) + 1;
 
     // phase-1 role
     const int col = (w & 1) * 32 + lane, pg = w >> 1;
-    const int rbase = col_x(col) - g.minD - k0 - xr_min;   // record index of pair p: rbase - 2p
+    const int rbase = col_x(col) - g.minD - k0 - xr_min;   // record index of pair p: rbase - p
     uint32_t V[kCfPPT];
 #pragma unroll
     for (int i = 0; i < kCfPPT; i++) V[i] = 0;
@@ -205,7 +208,7 @@ __global__ void __launch_bounds__(256, 2) k_cost_fast(const Feat* __restrict__ f
         if (t < nR) {
             const int xr = xr_min + t;
             const Feat a = __ldg(fr + size_t(e) * g.W + min(max(xr, 0), g.W - 1));
-            const Feat b = __ldg(fr + size_t(e) * g.W + min(max(xr - 1, 0), g.W - 1));
+            const Feat b = __ldg(fr + size_t(e) * g.W + min(max(xr - Dh, 0), g.W - 1));
             int va = a.x & 0xFF, la = (a.x >> 8) & 0xFF, ha = (a.x >> 16) & 0xFF;
             int vb = b.x & 0xFF, lb = (b.x >> 8) & 0xFF, hb = (b.x >> 16) & 0xFF;
             Rs[buf * kCfNRP + t] = make_uint4(pk16(va, vb), pk16(la, lb), pk16(-ha, -hb), pk16(-va, -vb));
@@ -228,12 +231,12 @@ __global__ void __launch_bounds__(256, 2) k_cost_fast(const Feat* __restrict__ f
     // phase-2 role: lanes <-> pairs, warp -> run of output columns
     const int cpw = (TX + 7) / 8;
     const int c_lo = w * cpw, c_hi = min(c_lo + cpw, TX);
-    const int kk = k0 + 2 * lane;
-    const uint32_t pad_or = kk >= g.D ? kMaxCostX2 : (kk + 1 >= g.D ? (uint32_t(kMaxCost) << 16) : 0u);
-    const uint32_t pad_and = kk >= g.D ? 0u : (kk + 1 >= g.D ? 0x0000FFFFu : 0xFFFFFFFFu);
+    const int kk = k0 + lane;                                  // this lane's word: cells kk and Dh + kk
+    const uint32_t pad_or = kk >= g.D ? kMaxCostX2 : (kk + Dh >= g.D ? (uint32_t(kMaxCost) << 16) : 0u);
+    const uint32_t pad_and = kk >= g.D ? 0u : (kk + Dh >= g.D ? 0x0000FFFFu : 0xFFFFFFFFu);
 
     // phase-2 output pointer of this lane: row y, column tx0 + c_lo, disparity pair kk
-    const bool lane_ok = kk < g.Dp;
+    const bool lane_ok = kk < Dh;
     const size_t colBytes = size_t(g.Dp) * 2;
     int slot = 0;
     for (int s = 0; s < nsteps; s++) {
@@ -248,7 +251,7 @@ __global__ void __launch_bounds__(256, 2) k_cost_fast(const Feat* __restrict__ f
 #pragma unroll
             for (int i = 0; i < kCfPPT; i++) {
                 const int p = pg + 4 * i;
-                const uint4 rs = rs_p[-2 * p], rr = rr_p[-2 * p];
+                const uint4 rs = rs_p[-p], rr = rr_p[-p];
                 uint32_t X = __vadd2(rs.y, ls.y);
                 uint32_t c0 = __viaddmax_s16x2_relu(ls.x, rs.z, X);
                 uint32_t Y = __vadd2(ls.z, rs.w);
@@ -271,7 +274,7 @@ __global__ void __launch_bounds__(256, 2) k_cost_fast(const Feat* __restrict__ f
         if (s >= bs - 1 && c_lo < c_hi && lane_ok) {
             const int y = ya + s - (bs - 1);
             const uint32_t* vrow = vs + lane * (kCfTXH + 1) + c_lo;
-            char* out = reinterpret_cast<char*>(Cvol + (size_t(y) * g.W1 + tx0 + c_lo) * g.Dp + kk);
+            char* out = reinterpret_cast<char*>(Cvol + (size_t(y) * g.W1 + tx0 + c_lo) * g.Dp + 2 * kk);
             const int ncol = min(c_hi, g.W1 - tx0) - c_lo;     // columns of this run that exist in the image
             uint32_t hs = 0;
             if (SW2T > 0) {

@@ -1,7 +1,15 @@
-// Min-plus path aggregation (A.5): warp-per-chain kernels over the materialised cost volume.
-// One warp walks one 1-D chain (row, column or diagonal); the D disparities are spread over the 32
-// lanes, 2*N per lane, packed two uint16 per register.  All arithmetic is unsigned 16x2 SIMD
-// (VIADD / VIMNMX3.U16x2 / VIMNMX.U16x2) with a CREDUX.MIN warp reduction per step.
+// Min-plus path aggregation (A.5): the warp-per-chain step and the generic per-direction kernels.
+//
+// Volume layout ("paired"): a pixel's Dp costs are stored as Dh = Dp/2 uint32 words; word w holds cell w in its
+// low half and cell Dh + w in its high half.  One warp owns a pixel's vector; lane l holds words l*N .. l*N+N-1,
+// i.e. cells l*N+j (low halves) and Dh+l*N+j (high halves).  With this pairing the d-1 / d+1 neighbours of BOTH
+// halves of register j are simply registers j-1 / j+1 (one shuffle per side at the lane boundary, which wraps
+// from the last active lane to lane 0 where the low half ends and the high half begins) -- no byte permutes.
+//
+// The chain state is kept NORMALISED: Lt = L - min_k L.  With it
+//     L_new[k] = C[k] + min(Lt[k], Lt[k-1] + P1, Lt[k+1] + P1, P2)
+//              = C[k] + min(min3(Lt[k-1], Lt[k+1], P2 - P1) + P1, Lt[k])           (VIMNMX3 + VIADDMNMX)
+// which is cv::StereoSGBM's update with the "- min" folded into the state.
 #pragma once
 #include "sgm_types.h"
 
@@ -68,40 +76,67 @@ __device__ __forceinline__ uint32_t warp_min16x2(const uint32_t (&r)[N])
     return __reduce_min_sync(kFullMask, mm);
 }
 
-// One step of  L[k] = C[k] + min(Lp[k], Lp[k-1]+P1, Lp[k+1]+P1, m+P2) - m  on the lane's 2N disparities.
-// Lp is replaced by L; m2 (the warp-uniform minimum of Lp, replicated in both halves) is replaced by that
-// of L.  Out-of-range neighbours and padded cells hold kMaxCost ("infinity"; kMaxCost + P1 + P2 < 65536 is
-// validated on the host).
+// Per-thread constants of the paired layout.
+struct LaneCtx {
+    int lane;
+    int src_up, src_dn;      // lanes that hold cells k-1 of my first word / k+1 of my last word
+    uint32_t sel_up, sel_dn; // byte-permute selectors fixing the two wrap points (identity elsewhere)
+    bool active;             // lane * N < Dh
+    uint32_t P1x2, P2mP1x2;  // P1 and P2 - P1 replicated in both halves
+};
+
 template <int N>
-__device__ __forceinline__ void path_step(const uint32_t (&C)[N], uint32_t (&Lp)[N], uint32_t& m2,
-                                          uint32_t P1x2, uint32_t P2x2, int lane)
+__device__ __forceinline__ LaneCtx make_lane_ctx(int lane, int Dp, int P1, int P2)
 {
-    uint32_t up = __shfl_up_sync(kFullMask, Lp[N - 1], 1);
-    uint32_t dn = __shfl_down_sync(kFullMask, Lp[0], 1);
-    if (lane == 0) up = kMaxCostX2;
-    if (lane == 31) dn = kMaxCostX2;
-    const uint32_t mP2 = m2 + P2x2;
-    uint32_t q_lo = __byte_perm(up, Lp[0], 0x5432) + P1x2;  // (Lp[2j-1], Lp[2j]) + P1
-    uint32_t L[N];
+    LaneCtx c;
+    const int Dh = Dp >> 1;
+    const int last = Dh / N - 1;               // last active lane
+    c.lane = lane;
+    c.active = lane <= last;
+    c.src_up = lane == 0 ? last : lane - 1;
+    c.src_dn = lane >= last ? 0 : lane + 1;
+    // lane 0: low half has no k-1 (-> 0xFFFF), high half's k-1 is the LOW half fetched from the last lane
+    c.sel_up = lane == 0 ? 0x1054u : 0x3210u;
+    // last lane: low half's k+1 is the HIGH half fetched from lane 0, high half has no k+1 (-> 0xFFFF)
+    c.sel_dn = lane == last ? 0x5432u : 0x3210u;
+    c.P1x2 = uint32_t(P1) * 0x10001u;
+    c.P2mP1x2 = uint32_t(P2 - P1) * 0x10001u;
+    return c;
+}
+
+// The add that the compiler should place on the FMA pipe (IMAD) when `one` is an opaque 1: the ALU pipe is the
+// busy one in these kernels (VIMNMX / PRMT / LOP3 all live there).
+__device__ __forceinline__ uint32_t add_fma(uint32_t a, uint32_t b, uint32_t one) { return a * one + b; }
+
+// One chain step on normalised state.  In: C (costs of this pixel), Lt (normalised L of the predecessor).
+// Out: Ln = L of this pixel (what cv::StereoSGBM stores / sums), Lt = Ln - min(Ln).  Padded cells and inactive
+// lanes must carry C = kMaxCost; out-of-range neighbours are 0xFFFF ("infinity": min3 caps at P2 - P1 first, so
+// nothing can wrap).
+template <int N>
+__device__ __forceinline__ void path_step(const uint32_t (&C)[N], uint32_t (&Lt)[N], uint32_t (&Ln)[N], const LaneCtx& c)
+{
+    uint32_t up = __shfl_sync(kFullMask, Lt[N - 1], c.src_up);
+    uint32_t dn = __shfl_sync(kFullMask, Lt[0], c.src_dn);
+    up = __byte_perm(up, 0xFFFFFFFFu, c.sel_up);
+    dn = __byte_perm(dn, 0xFFFFFFFFu, c.sel_dn);
 #pragma unroll
     for (int j = 0; j < N; j++) {
-        uint32_t nxt = (j + 1 < N) ? Lp[j + 1] : dn;
-        uint32_t q_hi = __byte_perm(Lp[j], nxt, 0x5432) + P1x2;  // (Lp[2j+1], Lp[2j+2]) + P1
-        uint32_t t = __vimin3_u16x2(Lp[j], q_lo, q_hi);
-        t = __vminu2(t, mP2);
-        L[j] = C[j] + t - m2;
-        q_lo = q_hi;
+        const uint32_t a = j > 0 ? Lt[j - 1] : up;
+        const uint32_t b = j + 1 < N ? Lt[j + 1] : dn;
+        const uint32_t t = __vimin3_u16x2(a, b, c.P2mP1x2);
+        const uint32_t u = __viaddmin_u16x2(t, c.P1x2, Lt[j]);
+        Ln[j] = C[j] + u;
     }
+    const uint32_t m2 = warp_min16x2<N>(Ln);
 #pragma unroll
-    for (int j = 0; j < N; j++) Lp[j] = L[j];
-    m2 = warp_min16x2<N>(L);
+    for (int j = 0; j < N; j++) Lt[j] = Ln[j] - m2;
 }
 
 struct PathGeom {
     int W1, H, Dp;
     int dx, dy;       // step of the chain (predecessor of (x,y) is (x-dx, y-dy))
     int nchains;
-    uint32_t P1x2, P2x2;
+    int P1, P2;
 };
 
 __device__ __forceinline__ void chain_start(const PathGeom& g, int c, int& x0, int& y0, int& len)
@@ -121,8 +156,8 @@ inline int chain_count(int W1, int H, int dx, int dy)
     return W1 + H - 1;
 }
 
-// Generic per-direction kernel: S (+)= L_r.  FIRST writes S, otherwise read-modify-write with the
-// int16 saturation of A.5 (min(32767, sum); all terms are non-negative).
+// Generic per-direction kernel (validation path): S (+)= L_r.  FIRST writes S, otherwise read-modify-write with
+// the int16 saturation of A.5 (min(32767, sum); all terms are non-negative).
 template <int N, bool FIRST>
 __global__ void __launch_bounds__(128) k_path_generic(const uint16_t* __restrict__ Cvol, uint16_t* __restrict__ Svol, PathGeom g)
 {
@@ -131,23 +166,22 @@ __global__ void __launch_bounds__(128) k_path_generic(const uint16_t* __restrict
     if (c >= g.nchains) return;
     int x0, y0, len;
     chain_start(g, c, x0, y0, len);
-    const bool active = lane * 2 * N < g.Dp;
+    const LaneCtx lc = make_lane_ctx<N>(lane, g.Dp, g.P1, g.P2);
     const ptrdiff_t stride = (ptrdiff_t(g.dy) * g.W1 + g.dx) * g.Dp;
     size_t off = (size_t(y0) * g.W1 + x0) * g.Dp + lane * 2 * N;
-    uint32_t Lp[N], Cc[N], Cn[N], Sc[N];
+    uint32_t Lt[N], Ln[N], Cc[N], Cn[N], Sc[N];
 #pragma unroll
-    for (int j = 0; j < N; j++) { Lp[j] = 0; Cc[j] = kMaxCostX2; Cn[j] = kMaxCostX2; Sc[j] = 0; }
-    uint32_t m = 0;
-    if (active) ldg_regs<N>(Cvol + off, Cc);
+    for (int j = 0; j < N; j++) { Lt[j] = 0; Cc[j] = kMaxCostX2; Cn[j] = kMaxCostX2; Sc[j] = 0; }
+    if (lc.active) ldg_regs<N>(Cvol + off, Cc);
     for (int i = 0; i < len; i++) {
-        if (active && i + 1 < len) ldg_regs<N>(Cvol + off + stride, Cn);
-        if (!FIRST && active) ld_regs<N>(Svol + off, Sc);
-        path_step<N>(Cc, Lp, m, g.P1x2, g.P2x2, lane);
-        if (active) {
-            if (FIRST) st_regs<N>(Svol + off, Lp);
+        if (lc.active && i + 1 < len) ldg_regs<N>(Cvol + off + stride, Cn);
+        if (!FIRST && lc.active) ld_regs<N>(Svol + off, Sc);
+        path_step<N>(Cc, Lt, Ln, lc);
+        if (lc.active) {
+            if (FIRST) st_regs<N>(Svol + off, Ln);
             else {
 #pragma unroll
-                for (int j = 0; j < N; j++) Sc[j] = __vminu2(Sc[j] + Lp[j], kMaxCostX2);
+                for (int j = 0; j < N; j++) Sc[j] = __vminu2(Sc[j] + Ln[j], kMaxCostX2);
                 st_regs<N>(Svol + off, Sc);
             }
         }

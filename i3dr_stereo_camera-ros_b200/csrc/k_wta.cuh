@@ -11,7 +11,10 @@ struct WtaGeom {
     int uniq, d12, INVALID;
 };
 
-// Warp-level WTA on the lane-distributed aggregated cost S (2N disparities per lane, lane-major).
+// Index of cell k inside a pixel's paired vector (uint16 units): word k (low half) or word k - Dh (high half).
+__device__ __forceinline__ int cell_u16_index(int k, int Dh) { return k < Dh ? 2 * k : 2 * (k - Dh) + 1; }
+
+// Warp-level WTA on the lane-distributed aggregated cost S (paired layout, see k_path.cuh).
 // `Srow` points at the pixel's Dp uint16 costs in memory (used to fetch the two sub-pixel neighbours).
 // Returns the fixed-point disparity (already offset by minD*16) or INVALID; on a unique winner also
 // posts (minS, x) to the right-image pixel x - d with the tie rule "larger x wins".
@@ -21,14 +24,15 @@ __device__ __forceinline__ int wta_pixel(const uint32_t (&S)[N], const uint16_t*
 {
     // key = S<<16 | k : the warp minimum is the smallest cost and, among equals, the FIRST disparity.
     uint32_t key = 0xFFFFFFFFu;
-    const int kbase = lane * 2 * N;
+    const int Dh = g.Dp >> 1;
+    const int kbase = lane * N;
 #pragma unroll
     for (int j = 0; j < N; j++) {
-        int k = kbase + 2 * j;
+        int k = kbase + j;
         uint32_t klo = (S[j] << 16) | uint32_t(k);
-        uint32_t khi = (S[j] & 0xFFFF0000u) | uint32_t(k + 1);
-        if (k < g.D) key = min(key, klo);
-        if (k + 1 < g.D) key = min(key, khi);
+        uint32_t khi = (S[j] & 0xFFFF0000u) | uint32_t(k + Dh);
+        if (k < Dh && k < g.D) key = min(key, klo);
+        if (k < Dh && k + Dh < g.D) key = min(key, khi);
     }
     key = __reduce_min_sync(kFullMask, key);
     const int minS = int(key >> 16), best = int(key & 0xFFFFu);
@@ -38,10 +42,10 @@ __device__ __forceinline__ int wta_pixel(const uint32_t (&S)[N], const uint16_t*
     bool bad = false;
 #pragma unroll
     for (int j = 0; j < N; j++) {
-        int k = kbase + 2 * j;
+        int k = kbase + j;
         int s0 = int(S[j] & 0xFFFFu), s1 = int(S[j] >> 16);
-        if (k < g.D && abs(k - best) > 1 && s0 * f < T) bad = true;
-        if (k + 1 < g.D && abs(k + 1 - best) > 1 && s1 * f < T) bad = true;
+        if (k < Dh && k < g.D && abs(k - best) > 1 && s0 * f < T) bad = true;
+        if (k < Dh && k + Dh < g.D && abs(k + Dh - best) > 1 && s1 * f < T) bad = true;
     }
     if (__any_sync(kFullMask, bad)) return g.INVALID;
     int dfix = best * 16;
@@ -50,7 +54,7 @@ __device__ __forceinline__ int wta_pixel(const uint32_t (&S)[N], const uint16_t*
         const int x2 = x - best - g.minD;
         if (x2 >= 0 && x2 < g.W) atomicMin(disp2key_row + x2, (uint32_t(minS) << 16) | uint32_t(0xFFFF - x));
         if (best > 0 && best < g.D - 1) {
-            int sm = Srow[best - 1], sp = Srow[best + 1];
+            int sm = Srow[cell_u16_index(best - 1, Dh)], sp = Srow[cell_u16_index(best + 1, Dh)];
             int den = max(sm + sp - 2 * minS, 1);
             dfix += ((sm - sp) * 16 + den) / (den * 2);  // C division: truncation toward zero
         }
@@ -72,7 +76,7 @@ __global__ void __launch_bounds__(256) k_wta(const uint16_t* __restrict__ Svol, 
     uint32_t S[N];
 #pragma unroll
     for (int j = 0; j < N; j++) S[j] = kMaxCostX2;
-    if (lane * 2 * N < g.Dp) ld_regs<N>(Srow + lane * 2 * N, S);
+    if (lane * 2 * N < g.Dp) ld_regs<N>(Srow + lane * 2 * N, S);   // N paired words per lane
     int d = wta_pixel<N>(S, Srow, g, x1, lane, disp2key + size_t(y) * g.W);
     if (lane == 0) disp[size_t(y) * g.W + x1 + g.minX1] = int16_t(d);
 }
