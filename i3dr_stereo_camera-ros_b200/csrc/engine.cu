@@ -42,7 +42,8 @@ struct Lane {
     uint2* xbuf = nullptr;                          // k_vert exchange records (LL protocol)
     int* d_err = nullptr;                           // device error word of the fused kernels
     int* h_err = nullptr;                           // pinned copy
-    cudaEvent_t coop_ev = nullptr;
+    cudaEvent_t coop_ev[2] = {nullptr, nullptr};   // alternating: MODE_HH launches two sweeps per frame
+    int coop_idx = 0;
     // stage profiling (b200sgm_profile): ring of event sets, harvested by b200sgm_stage_times
     std::vector<cudaEvent_t> prof_events;           // kProfRing * (kStages + 1)
     int prof_head = 0, prof_count = 0;
@@ -70,7 +71,9 @@ struct b200sgm_engine {
     bool profile = false;
     cudaEvent_t prof_ref = nullptr;   // time origin of the stage timeline
     int num_sms = 148;
-    cudaEvent_t coop_prev = nullptr;   // last cooperative (k_vert) launch of any lane: such kernels never overlap
+    // cooperative (k_vert) launches of all lanes: two fit on the GPU at once (2 CTAs per SM), a third would not be
+    // co-resident while the first two spin on each other, so launch i waits for launch i-2
+    cudaEvent_t coop_prev[2] = {nullptr, nullptr};
     int clock_khz = 1965000;
     std::mutex mu;
 };
@@ -209,6 +212,7 @@ int launch_vert_t(b200sgm_engine* h, Lane& ln, const Eff& e, const VertPlan& vp,
     g.nstrips = vp.nstrips; g.twmax = vp.twmax;
     g.P1 = e.P1; g.P2 = e.P2;
     g.spin_limit = (long long)h->clock_khz * 500;   // ~0.5 s of SM clock ticks
+    { static const int dbg = [] { const char* v = getenv("B200SGM_DEBUG_VERT"); return v ? atoi(v) : 0; }(); g.debug_flags = dbg; }
     auto kern = k_vert<N, UP, DO_WTA, FULL, CLAMP_EACH>;
     CUDA_TRY(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(vp.smem)));
     CUDA_TRY(h, cudaMemsetAsync(ln.xbuf, 0, size_t(2) * vp.nstrips * kXbufGen * (e.Dp / 2) * sizeof(uint2), st));
@@ -217,11 +221,14 @@ int launch_vert_t(b200sgm_engine* h, Lane& ln, const Eff& e, const VertPlan& vp,
     void* args[] = {(void*)&Cp, (void*)&Sp, (void*)&g, (void*)&dp, (void*)&kp, (void*)&xb, (void*)&er};
     {
         std::lock_guard<std::mutex> lk(h->mu);
-        if (h->coop_prev) CUDA_TRY(h, cudaStreamWaitEvent(st, h->coop_prev, 0));
+        if (h->coop_prev[1]) CUDA_TRY(h, cudaStreamWaitEvent(st, h->coop_prev[1], 0));
         CUDA_TRY(h, cudaLaunchCooperativeKernel((void*)kern, dim3(vp.nstrips), dim3(32 * vp.twmax), args, vp.smem, st));
         h->launches++;
-        CUDA_TRY(h, cudaEventRecord(ln.coop_ev, st));
-        h->coop_prev = ln.coop_ev;
+        cudaEvent_t ev = ln.coop_ev[ln.coop_idx];
+        ln.coop_idx ^= 1;
+        CUDA_TRY(h, cudaEventRecord(ev, st));
+        h->coop_prev[1] = h->coop_prev[0];
+        h->coop_prev[0] = ev;
     }
     return B200SGM_OK;
 }
@@ -234,7 +241,8 @@ int launch_vert(b200sgm_engine* h, Lane& ln, const Eff& e, const VertPlan& vp, c
     // kMaxCost + 3 * (Cmax + P2) cannot wrap 16 bits
     const long long bs = 2 * e.SW2 + 1;
     const long long cmax = bs * bs * (2 * e.ftzero + 63) + e.P2;
-    const bool clamp_each = kMaxCost + 3 * cmax > 65535;
+    // S_h arrives unclamped (<= 2*cmax) in MODE_SGBM / first sweep, clamped (<= kMaxCost) in the second sweep of MODE_HH
+    const bool clamp_each = kMaxCost + 3 * cmax > 65535 || 5 * cmax > 65535;
     if (full) {
         if (clamp_each) return launch_vert_t<N, UP, DO_WTA, true, true>(h, ln, e, vp, st);
         return launch_vert_t<N, UP, DO_WTA, true, false>(h, ln, e, vp, st);
@@ -249,9 +257,15 @@ int launch_fused(b200sgm_engine* h, Lane& ln, const Eff& e, cudaStream_t st, boo
     while (wpb > 1 && size_t(wpb) * horiz_smem_per_warp(e.Dp) > 200 * 1024) wpb /= 2;
     const size_t hsmem = size_t(wpb) * horiz_smem_per_warp(e.Dp);
     if (hsmem > 200 * 1024) return fail(h, B200SGM_EINVAL, "numDisparities too large for the horizontal kernel");
-    CUDA_TRY(h, cudaFuncSetAttribute(k_horiz<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(hsmem)));
-    k_horiz<N><<<(e.H + wpb - 1) / wpb, 32 * wpb, hsmem, st>>>(ln.C, ln.S, ln.ckpt, e.W1, e.H, e.Dp, e.P1, e.P2);
-    LAUNCH_CHECK(h);
+    {
+        const bool full = e.Dp == 64 * N;
+        const long long bs = 2 * e.SW2 + 1;
+        const bool clamp = !full || 2 * (bs * bs * (2 * e.ftzero + 63) + e.P2) > 65535;
+        auto kern = !full ? k_horiz<N, false, true> : (clamp ? k_horiz<N, true, true> : k_horiz<N, true, false>);
+        CUDA_TRY(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(hsmem)));
+        kern<<<(e.H + wpb - 1) / wpb, 32 * wpb, hsmem, st>>>(ln.C, ln.S, ln.ckpt, e.W1, e.H, e.Dp, e.P1, e.P2);
+        LAUNCH_CHECK(h);
+    }
     prof_mark(h, ln, 3, st);
     VertPlan vp = plan_vert(h, e);
     if (hybrid || !vp.ok) {
@@ -436,7 +450,7 @@ void free_lane(Lane& ln)
     if (ln.h_total) cudaFreeHost(ln.h_total);
     cudaFree(ln.xbuf); cudaFree(ln.d_err);
     if (ln.h_err) cudaFreeHost(ln.h_err);
-    if (ln.coop_ev) cudaEventDestroy(ln.coop_ev);
+    for (auto ev : ln.coop_ev) if (ev) cudaEventDestroy(ev);
     for (auto ev : ln.prof_events) cudaEventDestroy(ev);
     if (ln.done) cudaEventDestroy(ln.done);
     if (ln.stream) cudaStreamDestroy(ln.stream);
@@ -486,7 +500,8 @@ int b200sgm_create(int device, int max_width, int max_height, int max_disparitie
         ok = ok && cudaMalloc(&ln.d_err, sizeof(int)) == cudaSuccess && cudaMemset(ln.d_err, 0, sizeof(int)) == cudaSuccess;
         ok = ok && cudaMallocHost(&ln.h_err, sizeof(int)) == cudaSuccess;
         if (ok) *ln.h_err = 0;
-        ok = ok && cudaEventCreateWithFlags(&ln.coop_ev, cudaEventDisableTiming) == cudaSuccess;
+        ok = ok && cudaEventCreateWithFlags(&ln.coop_ev[0], cudaEventDisableTiming) == cudaSuccess;
+        ok = ok && cudaEventCreateWithFlags(&ln.coop_ev[1], cudaEventDisableTiming) == cudaSuccess;
         if (!ok) break;
     }
     if (!ok) {

@@ -48,148 +48,172 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
 // Horizontal pair.  Launch: one warp per row.
 // ------------------------------------------------------------------------------------------------
 constexpr int kHT = 8;        // tile width = checkpoint spacing of the <- chain
-constexpr int kHRing = 6;     // steps of C in flight per chain (cp.async ring in shared memory)
+constexpr int kHRingB = 8;    // C columns in flight for the stream that reads DRAM (<-), prefetch distance 7
+constexpr int kHRingF = 4;    // C columns in flight for the -> stream of phase B (L2 hits: <- read them a tile earlier)
 
 inline size_t horiz_ckpt_elems(int W1, int H, int Dp) { return size_t(H) * ((W1 + kHT - 1) / kHT) * Dp; }
-inline size_t horiz_smem_per_warp(int Dp) { return size_t(2 * kHRing + 2 * kHT) * Dp * sizeof(uint16_t); }
+inline size_t horiz_smem_per_warp(int Dp) { return size_t(kHRingB + kHRingF + 2 * kHT) * Dp * sizeof(uint16_t); }
 
-// dynamic smem per warp: [2 streams][kHRing][Dp] C ring, then [2][kHT][Dp] tiles of L<-
-template <int N>
+// dynamic smem per warp: ringB[kHRingB][Dp] | ringF[kHRingF][Dp] | tiles[2][kHT][Dp]  (uint16)
+// FULL : Dp == 64*N (every lane active, all shared-memory offsets are immediates; enables the unrolled fast loops)
+// CLAMP: saturate S_h (needed when 2*(Cmax+P2) could exceed 65535; padded cells are masked again before the WTA)
+template <int N, bool FULL, bool CLAMP>
 __global__ void __launch_bounds__(64) k_horiz(const uint16_t* __restrict__ Cvol, uint16_t* __restrict__ Sh,
-                                              uint16_t* __restrict__ ckpt, int W1, int H, int Dp, int P1, int P2)
+                                              uint16_t* __restrict__ ckpt, int W1, int H, int Dp_rt, int P1, int P2)
 {
     extern __shared__ __align__(16) uint16_t smem_h[];
+    const int Dp = FULL ? 64 * N : Dp_rt;
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int y = blockIdx.x * (blockDim.x >> 5) + wib;
     if (y >= H) return;
     const LaneCtx lc = make_lane_ctx<N>(lane, Dp, P1, P2);
-    const bool active = lc.active;
+    const bool active = FULL || lc.active;
     const int lo = lane * 2 * N;
     const int nT = (W1 + kHT - 1) / kHT;
     const uint16_t* Crow = Cvol + size_t(y) * W1 * Dp + lo;
     uint16_t* Srow = Sh + size_t(y) * W1 * Dp + lo;
     uint16_t* ck = ckpt + size_t(y) * nT * Dp + lo;
-    uint16_t* ring = smem_h + size_t(wib) * (2 * kHRing + 2 * kHT) * Dp + lo;
-    uint16_t* tiles = ring + size_t(2 * kHRing) * Dp;
-    auto slot = [&](int stream, int s) { return ring + size_t(stream * kHRing + (s % kHRing)) * Dp; };
-    constexpr int PF = kHRing - 1;
+    uint16_t* ringB = smem_h + size_t(wib) * (kHRingB + kHRingF + 2 * kHT) * Dp + lo;
+    uint16_t* ringF = ringB + kHRingB * Dp;
+    uint16_t* tiles = ringF + kHRingF * Dp;
+    constexpr int PFB = kHRingB - 1, PFF = kHRingF - 1;
+
+    auto ldC = [&](const uint16_t* p, uint32_t (&c)[N]) {
+        if (active) ld_regs<N>(p, c);
+        else {
+#pragma unroll
+            for (int j = 0; j < N; j++) c[j] = kMaxCostX2;
+        }
+    };
 
     uint32_t Lt[N], Ln[N], Cc[N];
     // ---------------- phase A: <- chain from x = W1-1 down to kHT, checkpoints only ----------------
-    {
-        const int nA = W1 - kHT;                                  // steps; step s visits x = W1-1-s
-        auto issue = [&](int s) {
-            if (s < nA && active) cp_async_lane<N>(slot(0, s), Crow + size_t(W1 - 1 - s) * Dp);
+    // ring slot of column x is x & 7; column x - 7 is requested while column x is processed
+    if (W1 > kHT) {
+        auto issueA = [&](int x) {
+            if (x >= kHT && active) cp_async_lane<N>(ringB + (x & 7) * Dp, Crow + size_t(x) * Dp);
             cp_async_commit();
         };
-        if (nA > 0) {
-            for (int s = 0; s < PF; s++) issue(s);
+        auto stepA = [&](int x) {
+            issueA(x - PFB);
+            cp_async_wait<PFB>();
+            ldC(ringB + (x & 7) * Dp, Cc);
+            path_step<N>(Cc, Lt, Ln, lc);
+            if ((x & 7) == 0 && active) st_regs<N>(ck + size_t(x / kHT - 1) * Dp, Lt);   // entry state of tile x/kHT - 1
+        };
 #pragma unroll
-            for (int j = 0; j < N; j++) Lt[j] = 0;
-            for (int s = 0; s < nA; s++) {
-                issue(s + PF);
-                cp_async_wait<PF>();
-                if (active) ld_regs<N>(slot(0, s), Cc);
-                else {
+        for (int j = 0; j < N; j++) Lt[j] = 0;
+        int x = W1 - 1;
+        for (int i = 0; i < PFB; i++) issueA(x - i);
+        for (; (x & 7) != 7 && x >= kHT; x--) stepA(x);
+        if (FULL) {
+            // blocks of 8 columns x = xb+7 .. xb, all offsets immediate; needs the prefetched columns xb-7 .. xb-1 >= kHT
+            const uint16_t* gp = Crow + size_t(x - 7 - PFB) * Dp;      // column (xb - 7): first prefetch target of the block
+            uint16_t* ckp = ck + size_t((x - 7) / kHT - 1) * Dp;
+            for (; x - 7 - PFB >= kHT; x -= 8, gp -= 8 * Dp, ckp -= Dp) {
 #pragma unroll
-                    for (int j = 0; j < N; j++) Cc[j] = kMaxCostX2;
+                for (int i = 0; i < 8; i++) {
+                    // processing column xb + 7 - i (slot 7 - i); request column xb - i (slot (8 - i) & 7)
+                    cp_async_lane<N>(ringB + ((8 - i) & 7) * Dp, gp + (7 - i) * Dp);
+                    cp_async_commit();
+                    cp_async_wait<PFB>();
+                    ld_regs<N>(ringB + (7 - i) * Dp, Cc);
+                    path_step<N>(Cc, Lt, Ln, lc);
                 }
-                path_step<N>(Cc, Lt, Ln, lc);
-                const int x = W1 - 1 - s;
-                if ((x & (kHT - 1)) == 0 && active) st_regs<N>(ck + size_t(x / kHT - 1) * Dp, Lt);   // entry state of tile x/kHT - 1
+                st_regs<N>(ckp, Lt);
             }
-            cp_async_wait<0>();
         }
+        for (; x >= kHT; x--) stepA(x);
+        cp_async_wait<0>();
     }
     __syncwarp();
     // ---------------- phase B: -> chain; <- recomputed one tile ahead ----------------
-    // Step index u = t*kHT + i.  Stream 0 (->) visits x = u.  Stream 1 (<-) runs one tile ahead: at global step
-    // u it recomputes column xb(u + kHT) where xb(v) = (v/kHT)*kHT + kHT-1 - (v%kHT); columns >= W1 are skipped.
-    auto xb_of = [&](int v) { return (v / kHT) * kHT + (kHT - 1) - (v % kHT); };
-    const int nB = nT * kHT;
-    auto issue0 = [&](int u) { if (u < W1 && active) cp_async_lane<N>(slot(0, u), Crow + size_t(u) * Dp); };
-    auto issue1 = [&](int v) {
-        if (v < nB && active) { const int x = xb_of(v); if (x < W1) cp_async_lane<N>(slot(1, v), Crow + size_t(x) * Dp); }
+    // Iteration `it` runs -> on column u = it (if 0 <= u < W1) and <- on its step v = it + 8 (if v < W1).  <- visits
+    // the columns of tile v/8 from its right end: xb(v); the last tile may be partial.  Ring slots: <- step v uses
+    // slot v & 7 of ringB (requested 7 iterations earlier), -> column u uses slot u & 3 of ringF (requested 3 earlier).
+    // tiles[(c >> 3) & 1][c & 7] holds L<- of column c.  Every iteration commits exactly one cp.async group.
+    auto xb_of = [&](int v) {
+        const int base = v & ~7;
+        return base + 8 <= W1 ? base + 7 - (v & 7) : W1 - 1 - (v - base);
     };
-    uint32_t Ltb[N];                  // <- state
-    uint32_t Lck[N];                  // prefetched checkpoint of the next tile to recompute
+    auto issueB = [&](int v) { if (v < W1 && active) cp_async_lane<N>(ringB + (v & 7) * Dp, Crow + size_t(xb_of(v)) * Dp); };
+    auto issueF = [&](int u) { if (u >= 0 && u < W1 && active) cp_async_lane<N>(ringF + (u & 3) * Dp, Crow + size_t(u) * Dp); };
+    uint32_t Ltb[N], Lck[N];          // <- state; prefetched entry state of the next tile
 #pragma unroll
     for (int j = 0; j < N; j++) { Lt[j] = 0; Ltb[j] = 0; Lck[j] = 0; }
-    // prologue: recompute tile 0 (stream 1 steps v = 0 .. kHT-1)
-    for (int s = 0; s < PF; s++) { issue1(s); cp_async_commit(); }
-    if (nT > 1 && active) ld_regs<N>(ck, Ltb);                     // entry state of tile 0 (zeros if it is the last tile)
-    if (nT > 2 && active) ld_regs<N>(ck + Dp, Lck);                // (plain loads: written by this lane in phase A)
-    for (int v = 0; v < kHT; v++) {
-        issue1(v + PF); cp_async_commit();
-        cp_async_wait<PF>();
-        const int x = xb_of(v);
-        if (x < W1) {
-            if (active) ld_regs<N>(slot(1, v), Cc);
-            else {
+    if (nT > 1 && active) ld_regs<N>(ck, Lck);       // entry state of tile 0 (plain loads: written by this lane in phase A)
+    auto tile_entry = [&](int tv) {                 // called when <- enters tile tv: take its entry state, prefetch the next
 #pragma unroll
-                for (int j = 0; j < N; j++) Cc[j] = kMaxCostX2;
-            }
-            path_step<N>(Cc, Ltb, Ln, lc);
-            if (active) st_regs<N>(tiles + size_t(x & (kHT - 1)) * Dp, Ln);
+        for (int j = 0; j < N; j++) Ltb[j] = (tv + 1 < nT) ? Lck[j] : 0u;
+        if (tv + 2 < nT && active) ld_regs<N>(ck + size_t(tv + 1) * Dp, Lck);
+    };
+    auto iterB = [&](int it) {
+        const int u = it, v = it + 8;
+        issueB(v + PFB); issueF(u + PFF); cp_async_commit();
+        cp_async_wait<PFF>();            // groups older than the newest 3 have landed: <- step v (7 back), -> column u (3 back)
+        if (v < W1) {
+            if ((v & 7) == 0) tile_entry(v >> 3);
+            const int c = xb_of(v);
+            uint32_t Cb[N], Lnb[N];
+            ldC(ringB + (v & 7) * Dp, Cb);
+            path_step<N>(Cb, Ltb, Lnb, lc);
+            if (active) st_regs<N>(tiles + (((c >> 3) & 1) * kHT + (c & 7)) * Dp, Lnb);
         }
-    }
-    // stream 0 joins: its first PF steps are issued now; from here on every iteration commits one group holding
-    // one step of each stream
-    for (int s = 0; s < PF; s++) { issue0(s); cp_async_commit(); }
-    for (int t = 0; t < nT; t++) {
-        // entry state of tile t+1: its checkpoint, or zeros when t+1 is the last tile
-        const bool more = t + 1 < nT;
+        if (u >= 0 && u < W1) {
+            uint32_t Lb[N];
+            ldC(ringF + (u & 3) * Dp, Cc);
+            if (active) ld_regs<N>(tiles + (((u >> 3) & 1) * kHT + (u & 7)) * Dp, Lb);
+            path_step<N>(Cc, Lt, Ln, lc);
+            if (active) {
 #pragma unroll
-        for (int j = 0; j < N; j++) Ltb[j] = (t + 2 < nT) ? Lck[j] : 0u;
-        if (t + 3 < nT && active) ld_regs<N>(ck + size_t(t + 2) * Dp, Lck);
-        uint16_t* tile_cur = tiles + size_t(t & 1) * kHT * Dp;
-        uint16_t* tile_nxt = tiles + size_t((t + 1) & 1) * kHT * Dp;
-#pragma unroll 2
-        for (int i = 0; i < kHT; i++) {
-            const int u = t * kHT + i;
-            issue0(u + PF); issue1(u + kHT + PF); cp_async_commit();
-            // the PF newest groups carry stream-0 steps u+1 .. u+PF and stream-1 steps u+kHT+1 .. u+kHT+PF;
-            // everything older (in particular step u of stream 0 and step u+kHT of stream 1) has landed
-            cp_async_wait<PF>();
-            const int xb = xb_of(u + kHT);
-            uint32_t Cb[N];
-            const bool do_b = more && xb < W1;
-            if (do_b) {
-                if (active) ld_regs<N>(slot(1, u + kHT), Cb);
-                else {
-#pragma unroll
-                    for (int j = 0; j < N; j++) Cb[j] = kMaxCostX2;
-                }
+                for (int j = 0; j < N; j++) Ln[j] = CLAMP ? __vminu2(Ln[j] + Lb[j], kMaxCostX2) : Ln[j] + Lb[j];
+                st_regs<N>(Srow + size_t(u) * Dp, Ln);
             }
-            if (u < W1) {
-                if (active) ld_regs<N>(slot(0, u), Cc);
-                else {
+        }
+    };
+    for (int v = 0; v < PFB; v++) { issueB(v); cp_async_commit(); }
+    int it = -8;
+    for (; it < 0; it++) iterB(it);
+    if (FULL) {
+        // fast blocks: -> on full tile t = it/8, <- on full tile t+1, prefetches reach into tile t+2 (must be full too)
+        for (; it + 24 <= W1; it += 8) {
+            const int t = it >> 3;
+            tile_entry(t + 1);
+            const uint16_t* gF = Crow + size_t(it) * Dp;            // column it
+            uint16_t* gS = Srow + size_t(it) * Dp;
+            const uint16_t* tcur = tiles + (t & 1) * kHT * Dp;
+            uint16_t* tnxt = tiles + ((t + 1) & 1) * kHT * Dp;
 #pragma unroll
-                    for (int j = 0; j < N; j++) Cc[j] = kMaxCostX2;
-                }
-                uint32_t Lb[N];
-                if (active) ld_regs<N>(tile_cur + size_t(i) * Dp, Lb);
-                path_step<N>(Cc, Lt, Ln, lc);
-                if (active) {
-#pragma unroll
-                    for (int j = 0; j < N; j++) Ln[j] = __vminu2(Ln[j] + Lb[j], kMaxCostX2);
-                    st_regs<N>(Srow + size_t(u) * Dp, Ln);
-                }
-            }
-            if (do_b) {
-                uint32_t Lnb[N];
+            for (int i = 0; i < 8; i++) {
+                // <- step v = it+8+i on column it+15-i; its prefetch v+7: i == 0 -> column it+8 (same tile), else it+24-i
+                cp_async_lane<N>(ringB + ((i + 7) & 7) * Dp, gF + (i == 0 ? 8 : 24 - i) * Dp);
+                cp_async_lane<N>(ringF + ((i + 3) & 3) * Dp, gF + (i + 3) * Dp);
+                cp_async_commit();
+                cp_async_wait<PFF>();
+                uint32_t Cb[N], Lnb[N], Lb[N];
+                ld_regs<N>(ringB + i * Dp, Cb);
+                ld_regs<N>(ringF + (i & 3) * Dp, Cc);
+                ld_regs<N>(tcur + i * Dp, Lb);
                 path_step<N>(Cb, Ltb, Lnb, lc);
-                if (active) st_regs<N>(tile_nxt + size_t(xb & (kHT - 1)) * Dp, Lnb);
+                path_step<N>(Cc, Lt, Ln, lc);
+                st_regs<N>(tnxt + (7 - i) * Dp, Lnb);
+#pragma unroll
+                for (int j = 0; j < N; j++) Ln[j] = CLAMP ? __vminu2(Ln[j] + Lb[j], kMaxCostX2) : Ln[j] + Lb[j];
+                st_regs<N>(gS + i * Dp, Ln);
             }
         }
     }
+    for (; it < W1; it++) iterB(it);
     cp_async_wait<0>();
 }
 
 // ------------------------------------------------------------------------------------------------
-// Register/shared-memory WTA (A.6) used by the vertical sweep.  S must already hold 0xFFFF in cells >= D and in
-// inactive lanes.  `scratch` is this warp's private Dp-cell staging area (paired layout).
+// Batched shared-memory WTA (A.6) used by the vertical sweep.  The column warp parks the summed cost of kWB
+// consecutive rows in its private staging area and then resolves the kWB pixels TOGETHER: the kWB dependency
+// chains (arg-min reduction -> neighbours -> uniqueness -> sub-pixel) are independent, so they overlap instead of
+// each stalling the warp for its full latency.  Staged vectors must hold 0xFFFF in cells >= D.
 // ------------------------------------------------------------------------------------------------
+constexpr int kWB = 2;
 struct WtaCtx {
     uint32_t kk0;        // (lane*N) | (lane*N + Dh) << 16 : disparity indices of this lane's first word
     uint32_t umagic;     // floor(2^32 / f) + 1 with f = 100 - uniq > 0
@@ -197,71 +221,108 @@ struct WtaCtx {
     int Dh;
 };
 
+// uint16 index of cell k in a paired vector, branch-free
+__device__ __forceinline__ int cell_idx2(int k, int Dh, int Dp) { return 2 * k - (k >= Dh ? Dp - 1 : 0); }
+
+// scratch: [kWB][Dp] uint16 of this warp; cnt = number of valid staged rows (<= kWB); dptr/kptr = output row
+// pointers of staged row 0, advancing by dStride per row.
 template <int N>
-__device__ __forceinline__ int wta_staged(const uint32_t (&S)[N], uint16_t* __restrict__ scratch, const WtaGeom& g,
-                                          const WtaCtx& w, int x1, int lane, bool active, uint32_t* __restrict__ disp2key_row)
+__device__ __forceinline__ void wta_batch(uint16_t* __restrict__ scratch, int cnt, const WtaGeom& g, const WtaCtx& w,
+                                          int x1, int lane, bool active, int16_t* __restrict__ dptr,
+                                          uint32_t* __restrict__ kptr, ptrdiff_t dStride)
 {
-    // key = S << 16 | k: the warp minimum is the smallest cost and, among equals, the FIRST disparity
-    uint32_t key = 0xFFFFFFFFu;
-#pragma unroll
-    for (int j = 0; j < N; j++) {
-        const uint32_t kk = w.kk0 + uint32_t(j) * 0x10001u;
-        key = __vimin3_u32(key, __byte_perm(kk, S[j], 0x5410), __byte_perm(kk, S[j], 0x7632));
-    }
-    if (active) st_regs<N>(scratch + lane * 2 * N, S);
-    key = __reduce_min_sync(kFullMask, key);
-    const int minS = int(key >> 16), best = int(key & 0xFFFFu);
-    // sub-pixel neighbours (uniform addresses -> broadcast loads); garbage when best is at an end (unused then)
-    const int km = max(best - 1, 0), kp = min(best + 1, g.Dp - 1);
-    const int sm = scratch[cell_u16_index(km, w.Dh)], sp = scratch[cell_u16_index(kp, w.Dh)];
+    const int Dp = g.Dp;
     __syncwarp();
-    // uniqueness: S[k] * f < minS * 100  <=>  S[k] < ceil(minS*100 / f), cells best-1 .. best+1 exempt: lanes 0..2
-    // overwrite those three cells with 0xFFFF in the staged copy, then every lane re-reads its words
-    {
-        const int k = best - 1 + lane;
-        if (lane < 3 && k >= 0 && k < g.Dp) scratch[cell_u16_index(k, w.Dh)] = 0xFFFFu;
+    int best[kWB], minS[kWB], sm[kWB], sp[kWB], cidx[kWB];
+#pragma unroll
+    for (int q = 0; q < kWB; q++) {
+        uint32_t S[N];
+        if (active) ld_regs<N>(scratch + q * Dp + lane * 2 * N, S);
+        else {
+#pragma unroll
+            for (int j = 0; j < N; j++) S[j] = 0xFFFFFFFFu;
+        }
+        // key = S << 16 | k: the warp minimum is the smallest cost and, among equals, the FIRST disparity
+        uint32_t key = 0xFFFFFFFFu;
+#pragma unroll
+        for (int j = 0; j < N; j++) {
+            const uint32_t kk = w.kk0 + uint32_t(j) * 0x10001u;
+            key = __vimin3_u32(key, __byte_perm(kk, S[j], 0x5410), __byte_perm(kk, S[j], 0x7632));
+        }
+        key = __reduce_min_sync(kFullMask, key);
+        minS[q] = int(key >> 16); best[q] = int(key & 0xFFFFu);
+    }
+    // lanes 0,1,2 address cells best-1, best, best+1: lane 0 / 2 fetch the sub-pixel neighbours, then the three
+    // lanes overwrite their cell with 0xFFFF (cells exempt from the uniqueness test)
+    const int dl = min(lane, 2) - 1;
+    int val[kWB];
+#pragma unroll
+    for (int q = 0; q < kWB; q++) {
+        const int k = best[q] + dl;
+        cidx[q] = (k >= 0 && k < Dp) ? q * Dp + cell_idx2(k, w.Dh, Dp) : -1;
+        val[q] = scratch[max(cidx[q], 0)];
+    }
+#pragma unroll
+    for (int q = 0; q < kWB; q++) {
+        sm[q] = __shfl_sync(kFullMask, val[q], 0);
+        sp[q] = __shfl_sync(kFullMask, val[q], 2);
     }
     __syncwarp();
-    uint32_t T[N];
-    if (active) ld_regs<N>(scratch + lane * 2 * N, T);
-    else {
 #pragma unroll
-        for (int j = 0; j < N; j++) T[j] = 0xFFFFFFFFu;
-    }
-    uint32_t mm = T[0];
+    for (int q = 0; q < kWB; q++)
+        if (lane < 3 && cidx[q] >= 0) scratch[cidx[q]] = 0xFFFFu;
+    __syncwarp();
 #pragma unroll
-    for (int j = 1; j < N; j++) mm = __vminu2(mm, T[j]);
-    const uint32_t thr = min(__umulhi(uint32_t(minS * 100 + w.f - 1), w.umagic), 0xFFFFu);
-    const bool bad = min(mm & 0xFFFFu, mm >> 16) < thr;
-    const bool reject = __any_sync(kFullMask, bad) || minS >= kMaxCost;
-    int dfix = best * 16;
-    if (best > 0 && best < g.D - 1) {
-        const int den = max(sm + sp - 2 * minS, 1);
-        // |quotient| <= 8.5 and numerator, denominator < 2^24: IEEE float division then truncation is exact
-        dfix += __float2int_rz(__fdiv_rn(float((sm - sp) * 16 + den), float(den * 2)));
+    for (int q = 0; q < kWB; q++) {
+        uint32_t T[N];
+        if (active) ld_regs<N>(scratch + q * Dp + lane * 2 * N, T);
+        else {
+#pragma unroll
+            for (int j = 0; j < N; j++) T[j] = 0xFFFFFFFFu;
+        }
+        uint32_t mm = T[0];
+#pragma unroll
+        for (int j = 1; j < N; j++) mm = __vminu2(mm, T[j]);
+        // uniqueness: S[k] * f < minS * 100  <=>  S[k] < ceil(minS*100 / f)
+        const uint32_t thr = min(__umulhi(uint32_t(minS[q] * 100 + w.f - 1), w.umagic), 0xFFFFu);
+        const bool bad = min(mm & 0xFFFFu, mm >> 16) < thr;
+        const bool reject = __any_sync(kFullMask, bad) || minS[q] >= kMaxCost;
+        int dfix = best[q] * 16;
+        if (best[q] > 0 && best[q] < g.D - 1) {
+            const int den = max(sm[q] + sp[q] - 2 * minS[q], 1);
+            // |quotient| <= 8.5 and numerator, denominator < 2^24: IEEE float division then truncation is exact
+            dfix += __float2int_rz(__fdiv_rn(float((sm[q] - sp[q]) * 16 + den), float(den * 2)));
+        }
+        if (lane == 0 && q < cnt) {
+            if (!reject) {
+                const int x = x1 + g.minX1;
+                const int x2 = x - best[q] - g.minD;
+                if (x2 >= 0 && x2 < g.W) atomicMin(kptr + q * dStride + x2, (uint32_t(minS[q]) << 16) | uint32_t(0xFFFF - x));
+            }
+            dptr[q * dStride] = int16_t(reject ? g.INVALID : dfix + g.minD * 16);
+        }
     }
-    if (lane == 0 && !reject) {
-        const int x = x1 + g.minX1;
-        const int x2 = x - best - g.minD;
-        if (x2 >= 0 && x2 < g.W) atomicMin(disp2key_row + x2, (uint32_t(minS) << 16) | uint32_t(0xFFFF - x));
-    }
-    return reject ? g.INVALID : dfix + g.minD * 16;
+    __syncwarp();
 }
 
-// Exact fallback for uniquenessRatio >= 100 (f <= 0: the comparison cannot be turned into a threshold).
+// Exact fallback for uniquenessRatio >= 100 (f <= 0: the comparison cannot be turned into a threshold): one row.
 template <int N>
-__device__ __forceinline__ int wta_regs_slow(const uint32_t (&S)[N], uint16_t* __restrict__ scratch, const WtaGeom& g,
-                                             const WtaCtx& w, int x1, int lane, bool active, uint32_t* __restrict__ disp2key_row)
+__device__ __forceinline__ int wta_slow(const uint16_t* __restrict__ scratch, const WtaGeom& g, const WtaCtx& w, int x1,
+                                        int lane, bool active, uint32_t* __restrict__ disp2key_row)
 {
+    uint32_t S[N];
+    if (active) ld_regs<N>(scratch + lane * 2 * N, S);
+    else {
+#pragma unroll
+        for (int j = 0; j < N; j++) S[j] = 0xFFFFFFFFu;
+    }
     uint32_t key = 0xFFFFFFFFu;
 #pragma unroll
     for (int j = 0; j < N; j++) {
         const uint32_t kk = w.kk0 + uint32_t(j) * 0x10001u;
         key = __vimin3_u32(key, __byte_perm(kk, S[j], 0x5410), __byte_perm(kk, S[j], 0x7632));
     }
-    if (active) st_regs<N>(scratch + lane * 2 * N, S);
     key = __reduce_min_sync(kFullMask, key);
-    __syncwarp();
     const int minS = int(key >> 16), best = int(key & 0xFFFFu);
     int out = g.INVALID;
     if (minS < kMaxCost) {
@@ -277,7 +338,7 @@ __device__ __forceinline__ int wta_regs_slow(const uint32_t (&S)[N], uint16_t* _
         if (!__any_sync(kFullMask, bad)) {
             int dfix = best * 16;
             if (best > 0 && best < g.D - 1) {
-                const int sm = scratch[cell_u16_index(best - 1, w.Dh)], sp = scratch[cell_u16_index(best + 1, w.Dh)];
+                const int sm = scratch[cell_idx2(best - 1, w.Dh, g.Dp)], sp = scratch[cell_idx2(best + 1, w.Dh, g.Dp)];
                 const int den = max(sm + sp - 2 * minS, 1);
                 dfix += ((sm - sp) * 16 + den) / (den * 2);
             }
@@ -289,7 +350,6 @@ __device__ __forceinline__ int wta_regs_slow(const uint32_t (&S)[N], uint16_t* _
             out = dfix + g.minD * 16;
         }
     }
-    __syncwarp();
     return out;
 }
 
@@ -302,16 +362,20 @@ struct VertGeom {
     int twmax;            // warps per CTA = widest strip
     int P1, P2;
     long long spin_limit; // clock64 ticks before a record wait gives up
+    int debug_flags;      // timing experiments only (results are wrong): 1 = no inter-strip exchange, 2 = no WTA
 };
 
 // Inter-strip exchange, "low latency" protocol: a record is Dp/2 entries of {two packed costs, tag}; each
 // entry is one 8-byte volatile store, so data and flag arrive together and no fence or separate flag is
 // needed.  tag = row + 1 (the buffer is zeroed before the launch).  [side][strip][row & 3][Dp/2] uint2.
-// Four generations are live at once: a strip publishes row R at the START of its row R, having only
-// waited (end of row R-1) for the neighbour's record R-2 -- and that neighbour still reads our record
-// R-3 at the END of its row R-2.
+// Four generations are live at once: a strip publishes row R early in its row R, having only waited (late in row
+// R-1) for the neighbour's record R-2 -- and that neighbour still reads our record R-3 late in its row R-2.
+// The consumer issues its record load at the TOP of the row and only inspects the tags right before it needs
+// the data, so in the common case (the neighbour is not late) the L2 round trip is off the critical path.
 constexpr int kXbufGen = 4;
-constexpr int kVRing = 4;     // rows of C / S_h in flight per column (cp.async ring in shared memory)
+constexpr int kVRing = 4;     // rows of C in flight per column (cp.async ring in shared memory); the row loop is unrolled by it
+constexpr int kSRing = 2;     // rows of S_h in flight: S_h is consumed at the END of a row, one row of lead is enough
+static_assert(kXbufGen == kVRing && kVRing % kWB == 0 && kVRing % kSRing == 0, "the row loop is unrolled by one common period");
 __device__ __forceinline__ uint2* xrec(uint2* xbuf, int nstrips, int Dp, int side, int strip, int row)
 {
     return xbuf + (size_t((side * nstrips + strip) * kXbufGen + (row & (kXbufGen - 1)))) * (Dp / 2);
@@ -327,16 +391,16 @@ __device__ __forceinline__ uint2 ld_volatile_v2(const uint2* p)
     return v;
 }
 
-// dynamic smem: Ld[2 parity][2 dir][twmax+2][Dp] | ring[kVRing][2 (C,S_h)][twmax][Dp] | scratch[twmax][Dp]   (uint16)
+// dynamic smem: Ld[2 parity][2 dir][twmax+2][Dp] | Cring[kVRing][twmax][Dp] | Sring[kSRing][twmax][Dp] | scratch[twmax][kWB][Dp]   (uint16)
 inline size_t vert_smem_bytes(int twmax, int Dp)
 {
-    return (size_t(4) * (twmax + 2) + size_t(2 * kVRing) * twmax + size_t(twmax)) * Dp * sizeof(uint16_t);
+    return (size_t(4) * (twmax + 2) + size_t(kVRing + kSRing + kWB) * twmax) * Dp * sizeof(uint16_t);
 }
 
 // FULL      : Dp == D == 64*N (no padded cells, every lane active)
 // CLAMP_EACH: saturate after every addition of the sum (needed when kMaxCost + 3*(Cmax+P2) could exceed 65535)
 template <int N, bool UP, bool DO_WTA, bool FULL, bool CLAMP_EACH>
-__global__ void __launch_bounds__(512, 1) k_vert(const uint16_t* __restrict__ Cvol, uint16_t* __restrict__ Svol, VertGeom g,
+__global__ void __launch_bounds__(512, 2) k_vert(const uint16_t* __restrict__ Cvol, uint16_t* __restrict__ Svol, VertGeom g,
                                                  int16_t* __restrict__ disp, uint32_t* __restrict__ disp2key,
                                                  uint2* __restrict__ xbuf, int* __restrict__ err)
 {
@@ -350,7 +414,8 @@ __global__ void __launch_bounds__(512, 1) k_vert(const uint16_t* __restrict__ Cv
     // Ld holds the NORMALISED diagonal states; zero = "predecessor outside the image" (first row, border columns)
     uint16_t* Ld = smem_v;
     uint16_t* ringbase = Ld + size_t(4) * slots * Dp;
-    uint16_t* scratchbase = ringbase + size_t(2 * kVRing) * g.twmax * Dp;
+    uint16_t* sringbase = ringbase + size_t(kVRing) * g.twmax * Dp;
+    uint16_t* scratchbase = sringbase + size_t(kSRing) * g.twmax * Dp;
     {
         uint32_t* z = reinterpret_cast<uint32_t*>(smem_v);
         const int nz = 2 * slots * Dp;
@@ -367,7 +432,7 @@ __global__ void __launch_bounds__(512, 1) k_vert(const uint16_t* __restrict__ Cv
     // The left-edge warp runs direction 1 first (it publishes it), every other warp direction 0 first.
     const int dirA = j == 0 ? 1 : 0, dirB = 1 - dirA;
     const int slotA = dirA == 0 ? j : j + 2, slotB = dirB == 0 ? j : j + 2;
-    const bool edge = (j == 0 && b > 0) || (j == TW - 1 && j != 0 && b < n - 1);   // publishes dirA, consumes dirB
+    const bool edge = !(g.debug_flags & 1) && ((j == 0 && b > 0) || (j == TW - 1 && j != 0 && b < n - 1));   // publishes dirA, consumes dirB
     const int dirStride = slots * Dp, parStride = 2 * slots * Dp;
     const uint16_t* rdA[2]; uint16_t* wrA[2]; const uint16_t* rdB[2]; uint16_t* wrB[2];
 #pragma unroll
@@ -388,7 +453,7 @@ __global__ void __launch_bounds__(512, 1) k_vert(const uint16_t* __restrict__ Cv
     const uint16_t* gC = Cvol + (size_t(ystart) * W1 + x) * Dp + lo;      // next row to fetch
     const uint16_t* gSin = Svol + (size_t(ystart) * W1 + x) * Dp + lo;
     uint16_t* gSout = Svol + (size_t(ystart) * W1 + x) * Dp + lo;          // row being computed (first pass of MODE_HH)
-    int16_t* dptr = disp + size_t(ystart) * g.w.W + x + g.w.minX1;         // row of the pending WTA
+    int16_t* dptr = disp + size_t(ystart) * g.w.W + x + g.w.minX1;         // first row of the pending WTA batch
     uint32_t* kptr = disp2key + size_t(ystart) * g.w.W;
     const ptrdiff_t dStride = (UP ? -1 : 1) * ptrdiff_t(g.w.W);
     WtaCtx wc;
@@ -396,86 +461,107 @@ __global__ void __launch_bounds__(512, 1) k_vert(const uint16_t* __restrict__ Cv
     wc.kk0 = uint32_t(lane * N) | (uint32_t(lane * N + wc.Dh) << 16);
     wc.f = 100 - g.w.uniq;
     wc.umagic = wc.f > 0 ? uint32_t((1ull << 32) / uint32_t(wc.f)) + 1u : 0u;
-    uint16_t* scratch = scratchbase + size_t(j) * Dp;
-    // cp.async ring: [slot][array][warp][Dp]
+    uint16_t* scratch = scratchbase + size_t(j) * kWB * Dp;
+    // cp.async rings: [slot][warp][Dp].  Group G_r (committed at the top of row r) carries C of row r+kVRing-1 and
+    // S_h of row r+1; the prologue commits C rows 0..kVRing-2 and S_h row 0.
     uint16_t* ring = ringbase + size_t(j) * Dp + lo;
-    const int ringArr = g.twmax * Dp, ringSlot = 2 * g.twmax * Dp;
-    int issue_row = 0;
-    auto issue = [&]() {   // one commit group per row, even past the end (keeps the wait arithmetic uniform)
-        if (issue_row < H && active) {
-            uint16_t* dst = ring + (issue_row & (kVRing - 1)) * ringSlot;
-            cp_async_lane<N>(dst, gC);
-            cp_async_lane<N>(dst + ringArr, gSin);
-        }
-        cp_async_commit();
-        gC += rowStride; gSin += rowStride;
+    uint16_t* sring = sringbase + size_t(j) * Dp + lo;
+    const int ringSlot = g.twmax * Dp;
+    int issue_row = 0;   // row of the next C fetch
+    auto issue_c = [&](int slot) {
+        if (issue_row < H && active) cp_async_lane<N>(ring + slot * ringSlot, gC);
+        gC += rowStride;
         issue_row++;
     };
+    auto issue_s = [&](int row_, int slot) {
+        if (row_ < H && active) cp_async_lane<N>(sring + slot * ringSlot, gSin);
+        gSin += rowStride;
+    };
+    issue_s(0, 0);
 #pragma unroll
-    for (int i = 0; i < kVRing - 1; i++) issue();
+    for (int i = 0; i < kVRing - 1; i++) { issue_c(i); cp_async_commit(); }
 
-    uint32_t LtV[N], Sprev[N];
+    uint32_t LtV[N];
 #pragma unroll
-    for (int q = 0; q < N; q++) { LtV[q] = 0; Sprev[q] = 0xFFFFFFFFu; }
+    for (int q = 0; q < N; q++) LtV[q] = 0;
     bool dead = false;
+    const bool wta_on = DO_WTA && !(g.debug_flags & 2);
 
-    auto do_wta = [&](int xcol) {
-        int d;
-        if (wc.f > 0) d = wta_staged<N>(Sprev, scratch, g.w, wc, xcol, lane, active, kptr);
-        else d = wta_regs_slow<N>(Sprev, scratch, g.w, wc, xcol, lane, active, kptr);
-        if (lane == 0) *dptr = int16_t(d);
-        dptr += dStride; kptr += dStride;
+    auto flush_wta = [&](int cnt) {
+        if (wc.f > 0) {
+            wta_batch<N>(scratch, cnt, g.w, wc, x, lane, active, dptr, kptr, dStride);
+        } else {
+            __syncwarp();
+            for (int q = 0; q < cnt; q++) {
+                const int d = wta_slow<N>(scratch + q * Dp, g.w, wc, x, lane, active, kptr + q * dStride);
+                if (lane == 0) dptr[q * dStride] = int16_t(d);
+            }
+            __syncwarp();
+        }
+        dptr += cnt * dStride; kptr += cnt * dStride;
     };
 
-    // one row; PAR = parity of r (buffer written), reads the other one
-    auto row = [&](auto par_tag, int r) {
-        constexpr int PAR = decltype(par_tag)::value;
-        issue();
+    // one row; Q = r mod 4 (ring slot, record generation, staging slot; parity = Q & 1)
+    auto row = [&](auto q_tag, int r) {
+        constexpr int Q = decltype(q_tag)::value;
+        constexpr int PAR = Q & 1;
+        issue_c((Q + kVRing - 1) & (kVRing - 1)); issue_s(r + 1, (Q + 1) & (kSRing - 1)); cp_async_commit();
+        // incoming diagonal of the previous row: fire the loads now, look at the tags later
+        uint2 pre[N];
+        if (edge && r > 0 && active) {
+            const uint2* rec = con_base + ((Q + kXbufGen - 1) & (kXbufGen - 1)) * gen_stride;
+#pragma unroll
+            for (int q = 0; q < N; q++) pre[q] = ld_volatile_v2(rec + q);
+        }
         cp_async_wait<kVRing - 1>();     // this thread's copies of row r have landed (each lane reads only its own bytes)
-        const uint16_t* rs = ring + (r & (kVRing - 1)) * ringSlot;
         uint32_t Cc[N], Sc[N], LtA[N], LtB[N], LnA[N], LnV[N], LnB[N];
-        if (active) { ld_regs<N>(rs, Cc); ld_regs<N>(rs + ringArr, Sc); ld_regs<N>(rdA[PAR ^ 1], LtA); }
+        if (active) { ld_regs<N>(ring + Q * ringSlot, Cc); ld_regs<N>(rdA[PAR ^ 1], LtA); }
         else {
 #pragma unroll
-            for (int q = 0; q < N; q++) { Cc[q] = kMaxCostX2; Sc[q] = 0; LtA[q] = 0; }
+            for (int q = 0; q < N; q++) { Cc[q] = kMaxCostX2; LtA[q] = 0; }
         }
         // ---- step A (the direction this warp publishes)
         path_step<N>(Cc, LtA, LnA, lc);
         if (active) st_regs<N>(wrA[PAR], LtA);
         if (edge && active) {
-            uint2* rec = pub_base + (r & (kXbufGen - 1)) * gen_stride;
+            uint2* rec = pub_base + Q * gen_stride;
 #pragma unroll
             for (int q = 0; q < N; q++) st_volatile_v2(rec + q, LtA[q], uint32_t(r + 1));
         }
         // ---- vertical path: registers only
         path_step<N>(Cc, LtV, LnV, lc);
-        // ---- WTA of the previous row: independent work that overlaps the steps around it
-        if (DO_WTA && r > 0) do_wta(x);
         // ---- step B
         if (edge && r > 0) {
-            const uint2* rec = con_base + ((r - 1) & (kXbufGen - 1)) * gen_stride;
+            bool ok = true;
 #pragma unroll
             for (int q = 0; q < N; q++) LtB[q] = 0;
-            if (active && !dead) {
-                const long long t0 = clock64();
-                int spins = 0;
-                while (true) {
-                    bool ok = true;
+            if (active) {
 #pragma unroll
-                    for (int q = 0; q < N; q++) {
-                        uint2 v = ld_volatile_v2(rec + q);
-                        LtB[q] = v.x;
-                        ok = ok && v.y == uint32_t(r);
-                    }
-                    if (ok) break;
-                    if ((++spins & 255) == 0 && (clock64() - t0 > g.spin_limit || *reinterpret_cast<volatile int*>(err))) {
-                        atomicExch(err, 1);
-                        dead = true;
-                        break;
+                for (int q = 0; q < N; q++) { LtB[q] = pre[q].x; ok = ok && pre[q].y == uint32_t(r); }
+            }
+            if (!__all_sync(kFullMask, ok)) {       // the neighbour is late: poll
+                const uint2* rec = con_base + ((Q + kXbufGen - 1) & (kXbufGen - 1)) * gen_stride;
+                if (active && !dead) {
+                    const long long t0 = clock64();
+                    int spins = 0;
+                    while (true) {
+                        ok = true;
+#pragma unroll
+                        for (int q = 0; q < N; q++) {
+                            uint2 v = ld_volatile_v2(rec + q);
+                            LtB[q] = v.x;
+                            ok = ok && v.y == uint32_t(r);
+                        }
+                        if (ok) break;
+                        if ((++spins & 255) == 0 && (clock64() - t0 > g.spin_limit || *reinterpret_cast<volatile int*>(err))) {
+                            atomicExch(err, 1);
+                            dead = true;
+                            break;
+                        }
                     }
                 }
+                dead = __any_sync(kFullMask, dead);
             }
-            dead = __any_sync(kFullMask, dead);
         } else {
             if (active) ld_regs<N>(rdB[PAR ^ 1], LtB);
             else {
@@ -486,14 +572,21 @@ __global__ void __launch_bounds__(512, 1) k_vert(const uint16_t* __restrict__ Cv
         path_step<N>(Cc, LtB, LnB, lc);
         if (active) st_regs<N>(wrB[PAR], LtB);
         // ---- S = sat(S_h + L_v + L_A + L_B)
+        cp_async_wait<1>();              // S_h of this row travelled in the previous row's group
+        if (active) ld_regs<N>(sring + (Q & (kSRing - 1)) * ringSlot, Sc);
+        else {
+#pragma unroll
+            for (int q = 0; q < N; q++) Sc[q] = 0;
+        }
+        uint32_t S[N];
 #pragma unroll
         for (int q = 0; q < N; q++) {
             if (CLAMP_EACH) {
                 uint32_t t = __vminu2(Sc[q] + LnV[q], kMaxCostX2);
                 t = __vminu2(t + LnA[q], kMaxCostX2);
-                Sprev[q] = __vminu2(t + LnB[q], kMaxCostX2);
+                S[q] = __vminu2(t + LnB[q], kMaxCostX2);
             } else {
-                Sprev[q] = __vminu2(Sc[q] + LnV[q] + LnA[q] + LnB[q], kMaxCostX2);
+                S[q] = __vminu2(Sc[q] + LnV[q] + LnA[q] + LnB[q], kMaxCostX2);
             }
         }
         if (DO_WTA) {
@@ -501,24 +594,31 @@ __global__ void __launch_bounds__(512, 1) k_vert(const uint16_t* __restrict__ Cv
 #pragma unroll
                 for (int q = 0; q < N; q++) {   // cells beyond D never win and never veto
                     const int k = lane * N + q;
-                    if (!active || k >= g.w.D) Sprev[q] = 0xFFFFFFFFu;
-                    else if (k + wc.Dh >= g.w.D) Sprev[q] |= 0xFFFF0000u;
+                    if (k >= g.w.D) S[q] = 0xFFFFFFFFu;
+                    else if (k + wc.Dh >= g.w.D) S[q] |= 0xFFFF0000u;
                 }
             }
+            if (active) st_regs<N>(scratch + (Q & (kWB - 1)) * Dp + lo, S);
         } else {
-            if (active) st_regs<N>(gSout, Sprev);
+            if (active) st_regs<N>(gSout, S);
             gSout += rowStride;
         }
+        if ((Q & (kWB - 1)) == kWB - 1 && wta_on) flush_wta(kWB);
         asm volatile("bar.sync 1, %0;" ::"r"(nbar) : "memory");
     };
 
     int r = 0;
-    for (; r + 1 < H; r += 2) {
+    for (; r + 3 < H; r += 4) {
         row(std::integral_constant<int, 0>{}, r);
         row(std::integral_constant<int, 1>{}, r + 1);
+        row(std::integral_constant<int, 2>{}, r + 2);
+        row(std::integral_constant<int, 3>{}, r + 3);
     }
-    if (r < H) row(std::integral_constant<int, 0>{}, r);
-    if (DO_WTA) do_wta(x);
+    const int rem = H - r;
+    if (rem > 0) row(std::integral_constant<int, 0>{}, r);
+    if (rem > 1) row(std::integral_constant<int, 1>{}, r + 1);
+    if (rem > 2) row(std::integral_constant<int, 2>{}, r + 2);
+    if ((rem & (kWB - 1)) != 0 && wta_on) flush_wta(rem & (kWB - 1));
     cp_async_wait<0>();
 }
 
