@@ -71,8 +71,8 @@ struct b200sgm_engine {
     bool profile = false;
     cudaEvent_t prof_ref = nullptr;   // time origin of the stage timeline
     int num_sms = 148;
-    // cooperative (k_vert) launches of all lanes: two fit on the GPU at once (2 CTAs per SM), a third would not be
-    // co-resident while the first two spin on each other, so launch i waits for launch i-2
+    // cooperative (k_vert) launches of all lanes: one sweep fills the register file of every SM (1024 threads x 64
+    // registers), and two partially resident sweeps would spin on CTAs that can never be scheduled -> serialise them
     cudaEvent_t coop_prev[2] = {nullptr, nullptr};
     int clock_khz = 1965000;
     std::mutex mu;
@@ -221,8 +221,8 @@ int launch_vert_t(b200sgm_engine* h, Lane& ln, const Eff& e, const VertPlan& vp,
     void* args[] = {(void*)&Cp, (void*)&Sp, (void*)&g, (void*)&dp, (void*)&kp, (void*)&xb, (void*)&er};
     {
         std::lock_guard<std::mutex> lk(h->mu);
-        if (h->coop_prev[1]) CUDA_TRY(h, cudaStreamWaitEvent(st, h->coop_prev[1], 0));
-        CUDA_TRY(h, cudaLaunchCooperativeKernel((void*)kern, dim3(vp.nstrips), dim3(32 * vp.twmax), args, vp.smem, st));
+        if (h->coop_prev[0]) CUDA_TRY(h, cudaStreamWaitEvent(st, h->coop_prev[0], 0));
+        CUDA_TRY(h, cudaLaunchCooperativeKernel((void*)kern, dim3(vp.nstrips), dim3((DO_WTA ? 64 : 32) * vp.twmax), args, vp.smem, st));
         h->launches++;
         cudaEvent_t ev = ln.coop_ev[ln.coop_idx];
         ln.coop_idx ^= 1;
@@ -497,7 +497,7 @@ int b200sgm_create(int device, int max_width, int max_height, int max_disparitie
         ok = ok && cudaMalloc(&ln.block_count, ((npix + 255) / 256 + 1) * 4) == cudaSuccess && cudaMalloc(&ln.total, 4) == cudaSuccess;
         ok = ok && cudaMallocHost(&ln.h_total, 4) == cudaSuccess;
         ok = ok && cudaMalloc(&ln.xbuf, size_t(2) * kMaxStrips * kXbufGen * (Dp / 2) * sizeof(uint2)) == cudaSuccess;
-        ok = ok && cudaMalloc(&ln.d_err, sizeof(int)) == cudaSuccess && cudaMemset(ln.d_err, 0, sizeof(int)) == cudaSuccess;
+        ok = ok && cudaMalloc(&ln.d_err, 4 * sizeof(int)) == cudaSuccess && cudaMemset(ln.d_err, 0, 4 * sizeof(int)) == cudaSuccess;
         ok = ok && cudaMallocHost(&ln.h_err, sizeof(int)) == cudaSuccess;
         if (ok) *ln.h_err = 0;
         ok = ok && cudaEventCreateWithFlags(&ln.coop_ev[0], cudaEventDisableTiming) == cudaSuccess;
@@ -748,6 +748,7 @@ int b200sgm_debug_read(b200sgm_handle h, int lane, const char* what, void* host,
     else if (!strcmp(what, "S")) src = ln.S;
     else if (!strcmp(what, "wta")) src = ln.disp_wta;
     else if (!strcmp(what, "median")) src = ln.disp_med;
+    else if (!strcmp(what, "stats")) src = ln.d_err;     // {error flag, late exchange records, poll iterations, -}
     else return fail(h, B200SGM_EINVAL, "unknown debug buffer");
     if (dp) {
         Eff e;

@@ -224,48 +224,49 @@ struct WtaCtx {
 // uint16 index of cell k in a paired vector, branch-free
 __device__ __forceinline__ int cell_idx2(int k, int Dh, int Dp) { return 2 * k - (k >= Dh ? Dp - 1 : 0); }
 
-// scratch: [kWB][Dp] uint16 of this warp; cnt = number of valid staged rows (<= kWB); dptr/kptr = output row
-// pointers of staged row 0, advancing by dStride per row.
+// Per-lane accumulator of the deferred scalar part: lane l holds the reductions of row (base + l) of this column.
+struct WtaAcc {
+    uint32_t key;    // minS << 16 | best
+    uint32_t mm;     // minimum cost outside best-1 .. best+1 (both halves)
+    int sm, sp;      // S[best-1], S[best+1]
+};
+
+// Vector part for kWB staged rows of this column (`qs` uint16 apart); row0 = index of staged row 0 in the sweep.
+// Only the warp-wide reductions happen here; what is left per pixel is a handful of scalars, parked in lane
+// (row & 31) of `acc` and resolved for 32 rows at once by wta_flush32 (lane-parallel instead of warp-redundant).
 template <int N>
-__device__ __forceinline__ void wta_batch(uint16_t* __restrict__ scratch, int cnt, const WtaGeom& g, const WtaCtx& w,
-                                          int x1, int lane, bool active, int16_t* __restrict__ dptr,
-                                          uint32_t* __restrict__ kptr, ptrdiff_t dStride)
+__device__ __forceinline__ void wta_vec(uint16_t* __restrict__ scratch, int qs, int row0, const WtaGeom& g, const WtaCtx& w,
+                                        int lane, bool active, WtaAcc& acc)
 {
     const int Dp = g.Dp;
     __syncwarp();
-    int best[kWB], minS[kWB], sm[kWB], sp[kWB], cidx[kWB];
+    uint32_t key[kWB];
 #pragma unroll
     for (int q = 0; q < kWB; q++) {
         uint32_t S[N];
-        if (active) ld_regs<N>(scratch + q * Dp + lane * 2 * N, S);
+        if (active) ld_regs<N>(scratch + q * qs + lane * 2 * N, S);
         else {
 #pragma unroll
             for (int j = 0; j < N; j++) S[j] = 0xFFFFFFFFu;
         }
         // key = S << 16 | k: the warp minimum is the smallest cost and, among equals, the FIRST disparity
-        uint32_t key = 0xFFFFFFFFu;
+        uint32_t kq = 0xFFFFFFFFu;
 #pragma unroll
         for (int j = 0; j < N; j++) {
             const uint32_t kk = w.kk0 + uint32_t(j) * 0x10001u;
-            key = __vimin3_u32(key, __byte_perm(kk, S[j], 0x5410), __byte_perm(kk, S[j], 0x7632));
+            kq = __vimin3_u32(kq, S[j] * 0x10000u + (kk & 0xFFFFu), __byte_perm(kk, S[j], 0x7632));
         }
-        key = __reduce_min_sync(kFullMask, key);
-        minS[q] = int(key >> 16); best[q] = int(key & 0xFFFFu);
+        key[q] = __reduce_min_sync(kFullMask, kq);
     }
     // lanes 0,1,2 address cells best-1, best, best+1: lane 0 / 2 fetch the sub-pixel neighbours, then the three
     // lanes overwrite their cell with 0xFFFF (cells exempt from the uniqueness test)
     const int dl = min(lane, 2) - 1;
-    int val[kWB];
+    int val[kWB], cidx[kWB];
 #pragma unroll
     for (int q = 0; q < kWB; q++) {
-        const int k = best[q] + dl;
-        cidx[q] = (k >= 0 && k < Dp) ? q * Dp + cell_idx2(k, w.Dh, Dp) : -1;
+        const int k = int(key[q] & 0xFFFFu) + dl;
+        cidx[q] = (k >= 0 && k < Dp) ? q * qs + cell_idx2(k, w.Dh, Dp) : -1;
         val[q] = scratch[max(cidx[q], 0)];
-    }
-#pragma unroll
-    for (int q = 0; q < kWB; q++) {
-        sm[q] = __shfl_sync(kFullMask, val[q], 0);
-        sp[q] = __shfl_sync(kFullMask, val[q], 2);
     }
     __syncwarp();
 #pragma unroll
@@ -275,34 +276,39 @@ __device__ __forceinline__ void wta_batch(uint16_t* __restrict__ scratch, int cn
 #pragma unroll
     for (int q = 0; q < kWB; q++) {
         uint32_t T[N];
-        if (active) ld_regs<N>(scratch + q * Dp + lane * 2 * N, T);
+        if (active) ld_regs<N>(scratch + q * qs + lane * 2 * N, T);
         else {
 #pragma unroll
             for (int j = 0; j < N; j++) T[j] = 0xFFFFFFFFu;
         }
-        uint32_t mm = T[0];
-#pragma unroll
-        for (int j = 1; j < N; j++) mm = __vminu2(mm, T[j]);
-        // uniqueness: S[k] * f < minS * 100  <=>  S[k] < ceil(minS*100 / f)
-        const uint32_t thr = min(__umulhi(uint32_t(minS[q] * 100 + w.f - 1), w.umagic), 0xFFFFu);
-        const bool bad = min(mm & 0xFFFFu, mm >> 16) < thr;
-        const bool reject = __any_sync(kFullMask, bad) || minS[q] >= kMaxCost;
-        int dfix = best[q] * 16;
-        if (best[q] > 0 && best[q] < g.D - 1) {
-            const int den = max(sm[q] + sp[q] - 2 * minS[q], 1);
-            // |quotient| <= 8.5 and numerator, denominator < 2^24: IEEE float division then truncation is exact
-            dfix += __float2int_rz(__fdiv_rn(float((sm[q] - sp[q]) * 16 + den), float(den * 2)));
-        }
-        if (lane == 0 && q < cnt) {
-            if (!reject) {
-                const int x = x1 + g.minX1;
-                const int x2 = x - best[q] - g.minD;
-                if (x2 >= 0 && x2 < g.W) atomicMin(kptr + q * dStride + x2, (uint32_t(minS[q]) << 16) | uint32_t(0xFFFF - x));
-            }
-            dptr[q * dStride] = int16_t(reject ? g.INVALID : dfix + g.minD * 16);
-        }
+        const uint32_t mm = warp_min16x2<N>(T);
+        const int smv = __shfl_sync(kFullMask, val[q], 0), spv = __shfl_sync(kFullMask, val[q], 2);
+        if (lane == ((row0 + q) & 31)) { acc.key = key[q]; acc.mm = mm; acc.sm = smv; acc.sp = spv; }
     }
-    __syncwarp();
+}
+
+// Scalar part for up to 32 rows: lane l resolves row l of the block (cnt = valid rows).  dptr/kptr = output pointers
+// of the block's first row, advancing by dStride per row.
+__device__ __forceinline__ void wta_flush32(const WtaAcc& acc, int cnt, const WtaGeom& g, const WtaCtx& w, int x1, int lane,
+                                            int16_t* __restrict__ dptr, uint32_t* __restrict__ kptr, ptrdiff_t dStride)
+{
+    if (lane >= cnt) return;
+    const int minS = int(acc.key >> 16), best = int(acc.key & 0xFFFFu);
+    // uniqueness: S[k] * f < minS * 100  <=>  S[k] < ceil(minS*100 / f)
+    const uint32_t thr = min(__umulhi(uint32_t(minS * 100 + w.f - 1), w.umagic), 0xFFFFu);
+    const bool reject = (acc.mm & 0xFFFFu) < thr || minS >= kMaxCost;
+    int dfix = best * 16;
+    if (best > 0 && best < g.D - 1) {
+        const int den = max(acc.sm + acc.sp - 2 * minS, 1);
+        // |quotient| <= 8.5 and numerator, denominator < 2^24: IEEE float division then truncation is exact
+        dfix += __float2int_rz(__fdiv_rn(float((acc.sm - acc.sp) * 16 + den), float(den * 2)));
+    }
+    if (!reject) {
+        const int x = x1 + g.minX1;
+        const int x2 = x - best - g.minD;
+        if (x2 >= 0 && x2 < g.W) atomicMin(kptr + lane * dStride + x2, (uint32_t(minS) << 16) | uint32_t(0xFFFF - x));
+    }
+    dptr[lane * dStride] = int16_t(reject ? g.INVALID : dfix + g.minD * 16);
 }
 
 // Exact fallback for uniquenessRatio >= 100 (f <= 0: the comparison cannot be turned into a threshold): one row.
@@ -373,40 +379,53 @@ struct VertGeom {
 // The consumer issues its record load at the TOP of the row and only inspects the tags right before it needs
 // the data, so in the common case (the neighbour is not late) the L2 round trip is off the critical path.
 constexpr int kXbufGen = 4;
-constexpr int kVRing = 4;     // rows of C in flight per column (cp.async ring in shared memory); the row loop is unrolled by it
-constexpr int kSRing = 2;     // rows of S_h in flight: S_h is consumed at the END of a row, one row of lead is enough
-static_assert(kXbufGen == kVRing && kVRing % kWB == 0 && kVRing % kSRing == 0, "the row loop is unrolled by one common period");
+constexpr int kVRing = 8;     // rows of C in flight per column (cp.async ring in shared memory): DRAM latency x row rate
+constexpr int kSRing = 4;     // rows of S_h in flight (S_h is consumed at the END of a row)
+constexpr int kRowUnroll = 4; // the row loop is unrolled by this: record generation, stage slot, parity are immediates
 __device__ __forceinline__ uint2* xrec(uint2* xbuf, int nstrips, int Dp, int side, int strip, int row)
 {
     return xbuf + (size_t((side * nstrips + strip) * kXbufGen + (row & (kXbufGen - 1)))) * (Dp / 2);
 }
 __device__ __forceinline__ void st_volatile_v2(uint2* p, uint32_t a, uint32_t b)
 {
-    asm volatile("st.volatile.global.v2.u32 [%0], {%1, %2};" ::"l"(p), "r"(a), "r"(b) : "memory");
+    asm volatile("st.relaxed.gpu.global.v2.u32 [%0], {%1, %2};" ::"l"(p), "r"(a), "r"(b) : "memory");
 }
 __device__ __forceinline__ uint2 ld_volatile_v2(const uint2* p)
 {
     uint2 v;
-    asm volatile("ld.volatile.global.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p) : "memory");
+    asm volatile("ld.relaxed.gpu.global.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p) : "memory");
     return v;
 }
 
-// dynamic smem: Ld[2 parity][2 dir][twmax+2][Dp] | Cring[kVRing][twmax][Dp] | Sring[kSRing][twmax][Dp] | scratch[twmax][kWB][Dp]   (uint16)
+constexpr int kStage = 4;     // rows of summed cost S parked for the WTA warps (ring, handed over with named barriers)
+static_assert(kStage == kRowUnroll && kXbufGen == kRowUnroll && kStage % kWB == 0, "stage slot = record generation = row & 3");
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
+__device__ __forceinline__ void named_bar_arrive(int id, int nthreads) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
+
+// dynamic smem: Ld[2 parity][2 dir][twmax+2][Dp] | Cring[kVRing][twmax][Dp] | Sring[kSRing][twmax][Dp] | stage[kStage][twmax][Dp]   (uint16)
 inline size_t vert_smem_bytes(int twmax, int Dp)
 {
-    return (size_t(4) * (twmax + 2) + size_t(kVRing + kSRing + kWB) * twmax) * Dp * sizeof(uint16_t);
+    return (size_t(4) * (twmax + 2) + size_t(kVRing + kSRing + kStage) * twmax) * Dp * sizeof(uint16_t);   // 155 KB at c3
 }
 
+// Warp-specialised vertical sweep.  Launch: 32 * twmax threads when !DO_WTA, else 64 * twmax:
+//   path warps (0 .. twmax-1)        : one per column; the three path updates of a row -- the only work on the
+//                                      row-to-row dependency chain -- and the sum S, parked in the stage ring; they run
+//                                      in lock step with one 32*TW-thread barrier per row.
+//   WTA warps  (twmax .. 2*twmax-1)  : one per column; resolve kWB parked rows at a time (winner-take-all, uniqueness,
+//                                      sub-pixel, disp2 scatter).  They trail the path warps by up to kStage rows and fill
+//                                      the issue slots the path warps leave idle while they wait on each other.
+// Ring hand-over: named barriers full[q] (path warps arrive, WTA warps sync) and empty[q] (the reverse).
 // FULL      : Dp == D == 64*N (no padded cells, every lane active)
-// CLAMP_EACH: saturate after every addition of the sum (needed when kMaxCost + 3*(Cmax+P2) could exceed 65535)
+// CLAMP_EACH: saturate after every addition of the sum (needed when the 16-bit sum of the terms could wrap)
 template <int N, bool UP, bool DO_WTA, bool FULL, bool CLAMP_EACH>
-__global__ void __launch_bounds__(512, 2) k_vert(const uint16_t* __restrict__ Cvol, uint16_t* __restrict__ Svol, VertGeom g,
-                                                 int16_t* __restrict__ disp, uint32_t* __restrict__ disp2key,
-                                                 uint2* __restrict__ xbuf, int* __restrict__ err)
+__global__ void __launch_bounds__(1024, 1) k_vert(const uint16_t* __restrict__ Cvol, uint16_t* __restrict__ Svol, VertGeom g,
+                                                  int16_t* __restrict__ disp, uint32_t* __restrict__ disp2key,
+                                                  uint2* __restrict__ xbuf, int* __restrict__ err)
 {
     extern __shared__ __align__(16) uint16_t smem_v[];
-    const int W1 = g.w.W1, H = g.w.H, Dp = g.w.Dp;
-    const int lane = threadIdx.x & 31, j = threadIdx.x >> 5;
+    const int W1 = g.w.W1, H = g.w.H, Dp = FULL ? 64 * N : g.w.Dp;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int b = blockIdx.x, n = g.nstrips;
     const int x0 = int((long long)b * W1 / n), x1e = int((long long)(b + 1) * W1 / n);
     const int TW = x1e - x0;
@@ -415,19 +434,71 @@ __global__ void __launch_bounds__(512, 2) k_vert(const uint16_t* __restrict__ Cv
     uint16_t* Ld = smem_v;
     uint16_t* ringbase = Ld + size_t(4) * slots * Dp;
     uint16_t* sringbase = ringbase + size_t(kVRing) * g.twmax * Dp;
-    uint16_t* scratchbase = sringbase + size_t(kSRing) * g.twmax * Dp;
+    uint16_t* stagebase = sringbase + size_t(kSRing) * g.twmax * Dp;
     {
         uint32_t* z = reinterpret_cast<uint32_t*>(smem_v);
         const int nz = 2 * slots * Dp;
         for (int i = threadIdx.x; i < nz; i += blockDim.x) z[i] = 0;
     }
     __syncthreads();
-    if (j >= TW) return;                 // the row barrier below only counts the column warps
-    const int nbar = 32 * TW;
+    const bool wta_role = DO_WTA && w >= g.twmax;
+    const int j = wta_role ? w - g.twmax : w;
+    if (j >= TW) return;                 // the barriers below only count the TW column warps of each role
+    const int nrow = 32 * TW, nboth = 64 * TW;
+    constexpr int BAR_ROW = 1, BAR_FULL = 2, BAR_EMPTY = 2 + kStage;
     const LaneCtx lc = make_lane_ctx<N>(lane, Dp, g.P1, g.P2);
     const bool active = FULL || lc.active;
     const int x = x0 + j;
     const int lo = lane * 2 * N;
+    const int ringSlot = g.twmax * Dp;                 // slot stride of the stage ring [slot][warp][Dp]
+    const ptrdiff_t rowStride = (UP ? -1 : 1) * ptrdiff_t(W1) * Dp;
+    const int ystart = UP ? H - 1 : 0;
+    uint16_t* stage = stagebase + size_t(j) * Dp;      // + slot * ringSlot
+    const bool wta_on = !(g.debug_flags & 2);
+
+    if (wta_role) {
+        // ================================ WTA warps ================================
+        int16_t* dptr = disp + size_t(ystart) * g.w.W + x + g.w.minX1;
+        uint32_t* kptr = disp2key + size_t(ystart) * g.w.W;
+        const ptrdiff_t dStride = (UP ? -1 : 1) * ptrdiff_t(g.w.W);
+        WtaCtx wc;
+        wc.Dh = Dp >> 1;
+        wc.kk0 = uint32_t(lane * N) | (uint32_t(lane * N + wc.Dh) << 16);
+        wc.f = 100 - g.w.uniq;
+        wc.umagic = wc.f > 0 ? uint32_t((1ull << 32) / uint32_t(wc.f)) + 1u : 0u;
+        WtaAcc acc{0xFFFFFFFFu, 0u, 0, 0};
+        int pending = 0;                    // rows parked in acc
+        for (int r = 0; r < H; r += kWB) {
+            const int cnt = min(kWB, H - r);
+            const int q0 = r & (kStage - 1);
+            for (int q = 0; q < cnt; q++) named_bar_sync(BAR_FULL + q0 + q, nboth);
+            uint16_t* sc = stage + q0 * ringSlot;
+            if (wta_on) {
+                if (wc.f > 0) {
+                    wta_vec<N>(sc, ringSlot, r, g.w, wc, lane, active, acc);   // a row past the end lands in a lane >= cnt of the flush
+                    pending += cnt;
+                    if (((r + kWB) & 31) == 0 || r + kWB >= H) {
+                        wta_flush32(acc, pending, g.w, wc, x, lane, dptr, kptr, dStride);
+                        dptr += pending * dStride; kptr += pending * dStride;
+                        pending = 0;
+                    }
+                } else {
+                    __syncwarp();
+                    for (int q = 0; q < cnt; q++) {
+                        const int d = wta_slow<N>(sc + q * ringSlot, g.w, wc, x, lane, active, kptr + q * dStride);
+                        if (lane == 0) dptr[q * dStride] = int16_t(d);
+                    }
+                    __syncwarp();
+                    dptr += cnt * dStride; kptr += cnt * dStride;
+                }
+            }
+            for (int q = 0; q < cnt; q++)
+                if (r + q + kStage < H) named_bar_arrive(BAR_EMPTY + q0 + q, nboth);
+        }
+        return;
+    }
+
+    // ================================ path warps ================================
     // direction 0: predecessor column x-1 (slot j); direction 1: predecessor column x+1 (slot j+2).
     // The left-edge warp runs direction 1 first (it publishes it), every other warp direction 0 first.
     const int dirA = j == 0 ? 1 : 0, dirB = 1 - dirA;
@@ -448,132 +519,124 @@ __global__ void __launch_bounds__(512, 2) k_vert(const uint16_t* __restrict__ Cv
     const uint2* con_base = xrec(xbuf, n, Dp, dirB, edge ? nb : b, 0) + lane * N;
     const int gen_stride = Dp / 2;
 
-    const ptrdiff_t rowStride = (UP ? -1 : 1) * ptrdiff_t(W1) * Dp;
-    const int ystart = UP ? H - 1 : 0;
     const uint16_t* gC = Cvol + (size_t(ystart) * W1 + x) * Dp + lo;      // next row to fetch
     const uint16_t* gSin = Svol + (size_t(ystart) * W1 + x) * Dp + lo;
     uint16_t* gSout = Svol + (size_t(ystart) * W1 + x) * Dp + lo;          // row being computed (first pass of MODE_HH)
-    int16_t* dptr = disp + size_t(ystart) * g.w.W + x + g.w.minX1;         // first row of the pending WTA batch
-    uint32_t* kptr = disp2key + size_t(ystart) * g.w.W;
-    const ptrdiff_t dStride = (UP ? -1 : 1) * ptrdiff_t(g.w.W);
-    WtaCtx wc;
-    wc.Dh = Dp >> 1;
-    wc.kk0 = uint32_t(lane * N) | (uint32_t(lane * N + wc.Dh) << 16);
-    wc.f = 100 - g.w.uniq;
-    wc.umagic = wc.f > 0 ? uint32_t((1ull << 32) / uint32_t(wc.f)) + 1u : 0u;
-    uint16_t* scratch = scratchbase + size_t(j) * kWB * Dp;
-    // cp.async rings: [slot][warp][Dp].  Group G_r (committed at the top of row r) carries C of row r+kVRing-1 and
-    // S_h of row r+1; the prologue commits C rows 0..kVRing-2 and S_h row 0.
-    uint16_t* ring = ringbase + size_t(j) * Dp + lo;
-    uint16_t* sring = sringbase + size_t(j) * Dp + lo;
-    const int ringSlot = g.twmax * Dp;
-    int issue_row = 0;   // row of the next C fetch
-    auto issue_c = [&](int slot) {
-        if (issue_row < H && active) cp_async_lane<N>(ring + slot * ringSlot, gC);
+    const int Dh = Dp >> 1;
+    // cp.async rings: [warp][slot][Dp], slot = row & (ring - 1).  Group G_r (committed at the top of row r) carries C
+    // of row r+kVRing-1 and S_h of row r+kSRing-1; the prologue commits C rows 0..kVRing-2 and S_h rows 0..kSRing-2.
+    uint16_t* ring = ringbase + size_t(j) * kVRing * Dp + lo;
+    uint16_t* sring = sringbase + size_t(j) * kSRing * Dp + lo;
+    auto issue_c = [&](int row_) {
+        if (row_ < H && active) cp_async_lane<N>(ring + (row_ & (kVRing - 1)) * Dp, gC);
         gC += rowStride;
-        issue_row++;
     };
-    auto issue_s = [&](int row_, int slot) {
-        if (row_ < H && active) cp_async_lane<N>(sring + slot * ringSlot, gSin);
+    auto issue_s = [&](int row_) {
+        if (row_ < H && active) cp_async_lane<N>(sring + (row_ & (kSRing - 1)) * Dp, gSin);
         gSin += rowStride;
     };
-    issue_s(0, 0);
+#pragma unroll
+    for (int i = 0; i < kSRing - 1; i++) issue_s(i);
 #pragma unroll
     for (int i = 0; i < kVRing - 1; i++) { issue_c(i); cp_async_commit(); }
 
     uint32_t LtV[N];
+    uint2 pre[N];        // edge warps: the neighbour's record of the previous row, requested one row early
 #pragma unroll
-    for (int q = 0; q < N; q++) LtV[q] = 0;
+    for (int q = 0; q < N; q++) { LtV[q] = 0; pre[q] = make_uint2(0u, 0u); }
     bool dead = false;
-    const bool wta_on = DO_WTA && !(g.debug_flags & 2);
 
-    auto flush_wta = [&](int cnt) {
-        if (wc.f > 0) {
-            wta_batch<N>(scratch, cnt, g.w, wc, x, lane, active, dptr, kptr, dStride);
-        } else {
-            __syncwarp();
-            for (int q = 0; q < cnt; q++) {
-                const int d = wta_slow<N>(scratch + q * Dp, g.w, wc, x, lane, active, kptr + q * dStride);
-                if (lane == 0) dptr[q * dStride] = int16_t(d);
-            }
-            __syncwarp();
-        }
-        dptr += cnt * dStride; kptr += cnt * dStride;
-    };
-
-    // one row; Q = r mod 4 (ring slot, record generation, staging slot; parity = Q & 1)
-    auto row = [&](auto q_tag, int r) {
+    // one row; Q = r mod 4 (ring slot, record generation, stage slot; parity = Q & 1); EDGE = this warp exchanges
+    auto row = [&](auto q_tag, auto edge_tag, int r) {
         constexpr int Q = decltype(q_tag)::value;
+        constexpr bool EDGE = decltype(edge_tag)::value;
         constexpr int PAR = Q & 1;
-        issue_c((Q + kVRing - 1) & (kVRing - 1)); issue_s(r + 1, (Q + 1) & (kSRing - 1)); cp_async_commit();
-        // incoming diagonal of the previous row: fire the loads now, look at the tags later
-        uint2 pre[N];
-        if (edge && r > 0 && active) {
-            const uint2* rec = con_base + ((Q + kXbufGen - 1) & (kXbufGen - 1)) * gen_stride;
-#pragma unroll
-            for (int q = 0; q < N; q++) pre[q] = ld_volatile_v2(rec + q);
-        }
-        cp_async_wait<kVRing - 1>();     // this thread's copies of row r have landed (each lane reads only its own bytes)
+        issue_c(r + kVRing - 1); issue_s(r + kSRing - 1); cp_async_commit();
         uint32_t Cc[N], Sc[N], LtA[N], LtB[N], LnA[N], LnV[N], LnB[N];
-        if (active) { ld_regs<N>(ring + Q * ringSlot, Cc); ld_regs<N>(rdA[PAR ^ 1], LtA); }
-        else {
+        // incoming diagonal of the previous row: its loads were fired at the end of the previous row (`pre`), the
+        // tags are inspected right before step B
+        const bool consume = EDGE && r > 0;
+        cp_async_wait<kVRing - 1>();     // this thread's copies of row r have landed (each lane reads only its own bytes)
+        if (active) {
+            ld_regs<N>(ring + (r & (kVRing - 1)) * Dp, Cc); ld_regs<N>(rdA[PAR ^ 1], LtA);
+            if (!EDGE) ld_regs<N>(rdB[PAR ^ 1], LtB);
+        } else {
 #pragma unroll
-            for (int q = 0; q < N; q++) { Cc[q] = kMaxCostX2; LtA[q] = 0; }
+            for (int q = 0; q < N; q++) { Cc[q] = kMaxCostX2; LtA[q] = 0; LtB[q] = 0; }
         }
         // ---- step A (the direction this warp publishes)
         path_step<N>(Cc, LtA, LnA, lc);
         if (active) st_regs<N>(wrA[PAR], LtA);
-        if (edge && active) {
-            uint2* rec = pub_base + Q * gen_stride;
+        if (EDGE) {
+            if (active) {
+                uint2* rec = pub_base + Q * gen_stride;
 #pragma unroll
-            for (int q = 0; q < N; q++) st_volatile_v2(rec + q, LtA[q], uint32_t(r + 1));
+                for (int q = 0; q < N; q++) st_volatile_v2(rec + q, LtA[q], uint32_t(r + 1));
+            }
+        }
+        if (EDGE) {
+            if (consume) {      // second chance for a record that was not there yet when it was requested a row ago
+                bool ok = true;
+                if (active) {
+#pragma unroll
+                    for (int q = 0; q < N; q++) ok = ok && pre[q].y == uint32_t(r);
+                }
+                if (!__all_sync(kFullMask, ok) && active) {
+                    const uint2* rec = con_base + ((Q + kXbufGen - 1) & (kXbufGen - 1)) * gen_stride;
+#pragma unroll
+                    for (int q = 0; q < N; q++) pre[q] = ld_volatile_v2(rec + q);
+                }
+            }
         }
         // ---- vertical path: registers only
         path_step<N>(Cc, LtV, LnV, lc);
         // ---- step B
-        if (edge && r > 0) {
-            bool ok = true;
-#pragma unroll
-            for (int q = 0; q < N; q++) LtB[q] = 0;
-            if (active) {
-#pragma unroll
-                for (int q = 0; q < N; q++) { LtB[q] = pre[q].x; ok = ok && pre[q].y == uint32_t(r); }
-            }
-            if (!__all_sync(kFullMask, ok)) {       // the neighbour is late: poll
-                const uint2* rec = con_base + ((Q + kXbufGen - 1) & (kXbufGen - 1)) * gen_stride;
-                if (active && !dead) {
-                    const long long t0 = clock64();
-                    int spins = 0;
-                    while (true) {
-                        ok = true;
-#pragma unroll
-                        for (int q = 0; q < N; q++) {
-                            uint2 v = ld_volatile_v2(rec + q);
-                            LtB[q] = v.x;
-                            ok = ok && v.y == uint32_t(r);
-                        }
-                        if (ok) break;
-                        if ((++spins & 255) == 0 && (clock64() - t0 > g.spin_limit || *reinterpret_cast<volatile int*>(err))) {
-                            atomicExch(err, 1);
-                            dead = true;
-                            break;
-                        }
-                    }
-                }
-                dead = __any_sync(kFullMask, dead);
-            }
-        } else {
-            if (active) ld_regs<N>(rdB[PAR ^ 1], LtB);
-            else {
+        if (EDGE) {
+            if (consume) {
+                bool ok = true;
 #pragma unroll
                 for (int q = 0; q < N; q++) LtB[q] = 0;
+                if (active) {
+#pragma unroll
+                    for (int q = 0; q < N; q++) { LtB[q] = pre[q].x; ok = ok && pre[q].y == uint32_t(r); }
+                }
+                if (!__all_sync(kFullMask, ok)) {       // the neighbour is late: poll
+                    if ((g.debug_flags & 4) && lane == 0) atomicAdd(err + 1, 1);
+                    const uint2* rec = con_base + ((Q + kXbufGen - 1) & (kXbufGen - 1)) * gen_stride;
+                    if (active && !dead) {
+                        const long long t0 = clock64();
+                        int spins = 0;
+                        while (true) {
+                            ok = true;
+#pragma unroll
+                            for (int q = 0; q < N; q++) {
+                                uint2 v = ld_volatile_v2(rec + q);
+                                LtB[q] = v.x;
+                                ok = ok && v.y == uint32_t(r);
+                            }
+                            if (ok) break;
+                            if ((++spins & 255) == 0 && (clock64() - t0 > g.spin_limit || *reinterpret_cast<volatile int*>(err))) {
+                                atomicExch(err, 1);
+                                dead = true;
+                                break;
+                            }
+                        }
+                    }
+                    dead = __any_sync(kFullMask, dead);
+                }
+            } else {
+                if (active) ld_regs<N>(rdB[PAR ^ 1], LtB);
+                else {
+#pragma unroll
+                    for (int q = 0; q < N; q++) LtB[q] = 0;
+                }
             }
         }
         path_step<N>(Cc, LtB, LnB, lc);
         if (active) st_regs<N>(wrB[PAR], LtB);
         // ---- S = sat(S_h + L_v + L_A + L_B)
-        cp_async_wait<1>();              // S_h of this row travelled in the previous row's group
-        if (active) ld_regs<N>(sring + (Q & (kSRing - 1)) * ringSlot, Sc);
+        cp_async_wait<kSRing - 1>();     // S_h of this row travelled in the group of row r - (kSRing - 1)
+        if (active) ld_regs<N>(sring + (Q & (kSRing - 1)) * Dp, Sc);
         else {
 #pragma unroll
             for (int q = 0; q < N; q++) Sc[q] = 0;
@@ -595,30 +658,41 @@ __global__ void __launch_bounds__(512, 2) k_vert(const uint16_t* __restrict__ Cv
                 for (int q = 0; q < N; q++) {   // cells beyond D never win and never veto
                     const int k = lane * N + q;
                     if (k >= g.w.D) S[q] = 0xFFFFFFFFu;
-                    else if (k + wc.Dh >= g.w.D) S[q] |= 0xFFFF0000u;
+                    else if (k + Dh >= g.w.D) S[q] |= 0xFFFF0000u;
                 }
             }
-            if (active) st_regs<N>(scratch + (Q & (kWB - 1)) * Dp + lo, S);
+            if (r >= kStage) named_bar_sync(BAR_EMPTY + Q, nboth);    // the WTA warps have taken row r - kStage
+            if (active) st_regs<N>(stage + Q * ringSlot + lo, S);
+            named_bar_arrive(BAR_FULL + Q, nboth);
         } else {
             if (active) st_regs<N>(gSout, S);
             gSout += rowStride;
         }
-        if ((Q & (kWB - 1)) == kWB - 1 && wta_on) flush_wta(kWB);
-        asm volatile("bar.sync 1, %0;" ::"r"(nbar) : "memory");
+        if (EDGE) {
+            if (active) {       // request the neighbour's record of THIS row: it is consumed late in the next row
+                const uint2* rec = con_base + Q * gen_stride;
+#pragma unroll
+                for (int q = 0; q < N; q++) pre[q] = ld_volatile_v2(rec + q);
+            }
+        }
+        named_bar_sync(BAR_ROW, nrow);
     };
 
-    int r = 0;
-    for (; r + 3 < H; r += 4) {
-        row(std::integral_constant<int, 0>{}, r);
-        row(std::integral_constant<int, 1>{}, r + 1);
-        row(std::integral_constant<int, 2>{}, r + 2);
-        row(std::integral_constant<int, 3>{}, r + 3);
-    }
-    const int rem = H - r;
-    if (rem > 0) row(std::integral_constant<int, 0>{}, r);
-    if (rem > 1) row(std::integral_constant<int, 1>{}, r + 1);
-    if (rem > 2) row(std::integral_constant<int, 2>{}, r + 2);
-    if ((rem & (kWB - 1)) != 0 && wta_on) flush_wta(rem & (kWB - 1));
+    auto sweep = [&](auto edge_tag) {
+        int r = 0;
+        for (; r + 3 < H; r += 4) {
+            row(std::integral_constant<int, 0>{}, edge_tag, r);
+            row(std::integral_constant<int, 1>{}, edge_tag, r + 1);
+            row(std::integral_constant<int, 2>{}, edge_tag, r + 2);
+            row(std::integral_constant<int, 3>{}, edge_tag, r + 3);
+        }
+        const int rem = H - r;
+        if (rem > 0) row(std::integral_constant<int, 0>{}, edge_tag, r);
+        if (rem > 1) row(std::integral_constant<int, 1>{}, edge_tag, r + 1);
+        if (rem > 2) row(std::integral_constant<int, 2>{}, edge_tag, r + 2);
+    };
+    if (edge) sweep(std::true_type{});
+    else sweep(std::false_type{});
     cp_async_wait<0>();
 }
 
