@@ -357,10 +357,8 @@ int run_pipeline(b200sgm_engine* h, Lane& ln, const Eff& e, const uint8_t* dL, s
     }
     prof_mark(h, ln, 0, st);
     {
-        dim3 block(256), grid((W + 255) / 256, H);
-        k_prefilter<<<grid, block, 0, st>>>(dL, lp, W, H, e.ftzero, ln.feat_l);
-        LAUNCH_CHECK(h);
-        k_prefilter<<<grid, block, 0, st>>>(dR, rp, W, H, e.ftzero, ln.feat_r);
+        dim3 block(256), grid((W + 255) / 256, H, 2);
+        k_prefilter<<<grid, block, 0, st>>>(dL, lp, dR, rp, W, H, e.ftzero, ln.feat_l, ln.feat_r);
         LAUNCH_CHECK(h);
     }
     CUDA_TRY(h, cudaMemsetAsync(ln.disp2key, 0xFF, size_t(npix) * 4, st));
@@ -370,10 +368,15 @@ int run_pipeline(b200sgm_engine* h, Lane& ln, const Eff& e, const uint8_t* dL, s
     if (e.W1 > 0) {
         if (e.SW2 <= 10 && h->path != 1) {
             CostFastGeom fg{W, H, e.W1, e.minX1, e.minD, e.D, e.Dp, e.SW2, 128};
-            const size_t smem = cost_fast_smem(e.SW2);
+            const bool ring8 = 2 * e.ftzero + 63 <= 255;
+            const bool nopad = e.Dp == e.D && (e.Dp / 2) % kCfDCP == 0;
+            const size_t smem = cost_fast_smem(e.SW2, ring8);
             const int TX = kCfTXH - 2 * e.SW2;
             dim3 grid((e.W1 + TX - 1) / TX, (e.Dp / 2 + kCfDCP - 1) / kCfDCP, (H + fg.RS - 1) / fg.RS);
-            auto kern = e.SW2 == 4 ? k_cost_fast<4> : (e.SW2 == 2 ? k_cost_fast<2> : k_cost_fast<0>);
+            void (*kern)(const Feat*, const Feat*, uint16_t*, CostFastGeom);
+            if (e.SW2 == 4) kern = ring8 ? (nopad ? k_cost_fast<4, true, true> : k_cost_fast<4, true, false>) : k_cost_fast<4, false, false>;
+            else if (e.SW2 == 2) kern = ring8 ? (nopad ? k_cost_fast<2, true, true> : k_cost_fast<2, true, false>) : k_cost_fast<2, false, false>;
+            else kern = ring8 ? k_cost_fast<0, true, false> : k_cost_fast<0, false, false>;
             CUDA_TRY(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
             kern<<<grid, 256, smem, st>>>(ln.feat_l, ln.feat_r, ln.C, fg);
             LAUNCH_CHECK(h);

@@ -2,6 +2,7 @@
 // Replaces the first stages of cv::StereoSGBM::compute as called at
 // /root/reference/src/stereoMatcher/matcherOpenCVSGBM.cpp:21 (algorithm: SURVEY.md Appendix A).
 #pragma once
+#include <type_traits>
 #include "sgm_types.h"
 
 namespace b200sgm {
@@ -19,12 +20,18 @@ __device__ __forceinline__ int sobel_at(const uint8_t* __restrict__ r, const uin
     return min(max(g, -ftzero), ftzero) + ftzero;
 }
 
-__global__ void k_prefilter(const uint8_t* __restrict__ img, size_t pitch, int W, int H, int ftzero,
-                            Feat* __restrict__ feat)
+__device__ __forceinline__ uint32_t pk16(int a, int b) { return (uint32_t(a) & 0xFFFFu) | (uint32_t(b) << 16); }
+
+// grid.z = 2: z = 0 left image, z = 1 right image
+__global__ void k_prefilter(const uint8_t* __restrict__ imgL, size_t pitchL, const uint8_t* __restrict__ imgR, size_t pitchR,
+                            int W, int H, int ftzero, Feat* __restrict__ featL, Feat* __restrict__ featR)
 {
     int x = blockIdx.x * blockDim.x + threadIdx.x;
     int y = blockIdx.y;
     if (x >= W || y >= H) return;
+    const uint8_t* img = blockIdx.z ? imgR : imgL;
+    const size_t pitch = blockIdx.z ? pitchR : pitchL;
+    Feat* feat = blockIdx.z ? featR : featL;
     const uint8_t* r = img + size_t(y) * pitch;
     const uint8_t* rn = img + size_t(y > 0 ? y - 1 : y) * pitch;
     const uint8_t* rs = img + size_t(y < H - 1 ? y + 1 : y) * pitch;
@@ -39,20 +46,19 @@ __global__ void k_prefilter(const uint8_t* __restrict__ img, size_t pitch, int W
     int ra = x > 0 ? (r0 + rl) >> 1 : r0, rb = x < W - 1 ? (r0 + rr) >> 1 : r0;
     int slo = min(s0, min(sa, sb)), shi = max(s0, max(sa, sb));
     int rlo = min(r0, min(ra, rb)), rhi = max(r0, max(ra, rb));
-    Feat f;
-    f.x = uint32_t(s0) | (uint32_t(slo) << 8) | (uint32_t(shi) << 16) | (uint32_t(r0) << 24);
-    f.y = uint32_t(rlo) | (uint32_t(rhi) << 8);
-    feat[size_t(y) * W + x] = f;
+    feat[size_t(y) * W + x] = make_uint4(pk16(s0, slo), pk16(-shi, -s0), pk16(r0 * 64, rlo * 64), pk16(-rhi * 64, -r0 * 64));
 }
 
 // A.3 for one (left pixel, right pixel) pair.
 __device__ __forceinline__ int bt_pixel_cost(Feat a, Feat b)
 {
-    int u = a.x & 0xFF, ulo = (a.x >> 8) & 0xFF, uhi = (a.x >> 16) & 0xFF;
-    int v = b.x & 0xFF, vlo = (b.x >> 8) & 0xFF, vhi = (b.x >> 16) & 0xFF;
+    auto lo16 = [](uint32_t w) { return int(int16_t(w & 0xFFFFu)); };
+    auto hi16 = [](uint32_t w) { return int(int16_t(w >> 16)); };
+    int u = lo16(a.x), ulo = hi16(a.x), uhi = -lo16(a.y);
+    int v = lo16(b.x), vlo = hi16(b.x), vhi = -lo16(b.y);
     int cs = min(max(0, max(u - vhi, vlo - u)), max(0, max(v - uhi, ulo - v)));
-    u = a.x >> 24; ulo = a.y & 0xFF; uhi = (a.y >> 8) & 0xFF;
-    v = b.x >> 24; vlo = b.y & 0xFF; vhi = (b.y >> 8) & 0xFF;
+    u = lo16(a.z) >> 6; ulo = hi16(a.z) >> 6; uhi = (-lo16(a.w)) >> 6;
+    v = lo16(b.z) >> 6; vlo = hi16(b.z) >> 6; vhi = (-lo16(b.w)) >> 6;
     int cr = min(max(0, max(u - vhi, vlo - u)), max(0, max(v - uhi, ulo - v)));
     return cs + (cr >> 2);
 }
@@ -161,18 +167,19 @@ constexpr int kCfDCP = 32;    // disparity pairs per CTA
 constexpr int kCfNRP = 128;   // right-image pair records per row (>= TXH + DCP - 1)
 constexpr int kCfPPT = 8;     // disparity pairs per thread in phase 1
 
-inline size_t cost_fast_smem(int SW2)
+inline size_t cost_fast_smem(int SW2, bool ring8)
 {
     const int bs = 2 * SW2 + 1;
     return size_t(2) * (2 * kCfNRP + 2 * kCfTXH) * sizeof(uint4) + size_t(kCfDCP) * (kCfTXH + 1) * 4 +
-           size_t(bs) * kCfDCP * kCfTXH * 4;
+           size_t(bs) * kCfDCP * kCfTXH * (ring8 ? 2 : 4);
 }
 
-__device__ __forceinline__ uint32_t pk16(int a, int b) { return (uint32_t(a) & 0xFFFFu) | (uint32_t(b) << 16); }
-
 // SW2T > 0: blockSize/2 known at compile time (loops unrolled); SW2T == 0: taken from the geometry.
-template <int SW2T>
-__global__ void __launch_bounds__(256, 2) k_cost_fast(const Feat* __restrict__ fl, const Feat* __restrict__ fr,
+// RING8  : pixel costs fit a byte (2*ftzero + 63 <= 255): the ring of the last `bs` rows holds a disparity pair in 16
+//          bits, which halves the dominant shared-memory array (3 CTAs per SM instead of 2)
+// NOPAD  : Dp == D and every lane owns a word: no padded cells to force to kMaxCost
+template <int SW2T, bool RING8, bool NOPAD>
+__global__ void __launch_bounds__(256, RING8 ? 3 : 2) k_cost_fast(const Feat* __restrict__ fl, const Feat* __restrict__ fr,
                                                       uint16_t* __restrict__ Cvol, CostFastGeom g)
 {
     extern __shared__ uint4 cf_smem[];
@@ -184,7 +191,8 @@ __global__ void __launch_bounds__(256, 2) k_cost_fast(const Feat* __restrict__ f
     uint4* Ls = Rr + 2 * kCfNRP;               // [2][TXH]  sobel: (u, -u, lo, -hi) replicated
     uint4* Lr = Ls + 2 * kCfTXH;               // [2][TXH]  raw x64
     uint32_t* vs = reinterpret_cast<uint32_t*>(Lr + 2 * kCfTXH);   // [DCP][TXH+1]
-    uint32_t* ring = vs + kCfDCP * (kCfTXH + 1);                    // [bs][DCP][TXH]
+    using ring_t = typename std::conditional<RING8, uint16_t, uint32_t>::type;
+    ring_t* ring = reinterpret_cast<ring_t*>(vs + kCfDCP * (kCfTXH + 1));   // [bs][DCP][TXH]
 
     const int t = threadIdx.x, lane = t & 31, w = t >> 5;
     const int tx0 = blockIdx.x * TX;
@@ -209,19 +217,19 @@ __global__ void __launch_bounds__(256, 2) k_cost_fast(const Feat* __restrict__ f
             const int xr = xr_min + t;
             const Feat a = __ldg(fr + size_t(e) * g.W + min(max(xr, 0), g.W - 1));
             const Feat b = __ldg(fr + size_t(e) * g.W + min(max(xr - Dh, 0), g.W - 1));
-            int va = a.x & 0xFF, la = (a.x >> 8) & 0xFF, ha = (a.x >> 16) & 0xFF;
-            int vb = b.x & 0xFF, lb = (b.x >> 8) & 0xFF, hb = (b.x >> 16) & 0xFF;
-            Rs[buf * kCfNRP + t] = make_uint4(pk16(va, vb), pk16(la, lb), pk16(-ha, -hb), pk16(-va, -vb));
-            va = (a.x >> 24) * 64; la = (a.y & 0xFF) * 64; ha = ((a.y >> 8) & 0xFF) * 64;
-            vb = (b.x >> 24) * 64; lb = (b.y & 0xFF) * 64; hb = ((b.y >> 8) & 0xFF) * 64;
-            Rr[buf * kCfNRP + t] = make_uint4(pk16(va, vb), pk16(la, lb), pk16(-ha, -hb), pk16(-va, -vb));
+            // (v, lo, -hi, -v) of the pixel pair (xr, xr - Dh), low half = xr
+            Rs[buf * kCfNRP + t] = make_uint4(__byte_perm(a.x, b.x, 0x5410), __byte_perm(a.x, b.x, 0x7632),
+                                              __byte_perm(a.y, b.y, 0x5410), __byte_perm(a.y, b.y, 0x7632));
+            Rr[buf * kCfNRP + t] = make_uint4(__byte_perm(a.z, b.z, 0x5410), __byte_perm(a.z, b.z, 0x7632),
+                                              __byte_perm(a.w, b.w, 0x5410), __byte_perm(a.w, b.w, 0x7632));
         } else if (t >= 128 && t < 128 + kCfTXH) {
             const int c = t - 128;
             const Feat a = __ldg(fl + size_t(e) * g.W + col_x(c));
-            int u = a.x & 0xFF, lo = (a.x >> 8) & 0xFF, hi = (a.x >> 16) & 0xFF;
-            Ls[buf * kCfTXH + c] = make_uint4(pk16(u, u), pk16(-u, -u), pk16(lo, lo), pk16(-hi, -hi));
-            u = (a.x >> 24) * 64; lo = (a.y & 0xFF) * 64; hi = ((a.y >> 8) & 0xFF) * 64;
-            Lr[buf * kCfTXH + c] = make_uint4(pk16(u, u), pk16(-u, -u), pk16(lo, lo), pk16(-hi, -hi));
+            // (u, -u, lo, -hi), each replicated in both halves
+            Ls[buf * kCfTXH + c] = make_uint4(__byte_perm(a.x, a.x, 0x1010), __byte_perm(a.y, a.y, 0x3232),
+                                              __byte_perm(a.x, a.x, 0x3232), __byte_perm(a.y, a.y, 0x1010));
+            Lr[buf * kCfTXH + c] = make_uint4(__byte_perm(a.z, a.z, 0x1010), __byte_perm(a.w, a.w, 0x3232),
+                                              __byte_perm(a.z, a.z, 0x3232), __byte_perm(a.w, a.w, 0x1010));
         }
     };
 
@@ -244,7 +252,7 @@ __global__ void __launch_bounds__(256, 2) k_cost_fast(const Feat* __restrict__ f
         // ---- phase 1
         {
             const uint4 ls = Ls[buf * kCfTXH + col], lr = Lr[buf * kCfTXH + col];
-            uint32_t* rrow = ring + size_t(slot) * kCfDCP * kCfTXH + col;
+            ring_t* rrow = ring + size_t(slot) * kCfDCP * kCfTXH + col;
             slot = slot + 1 == bs ? 0 : slot + 1;
             const uint4* rs_p = Rs + buf * kCfNRP + rbase;
             const uint4* rr_p = Rr + buf * kCfNRP + rbase;
@@ -263,8 +271,14 @@ __global__ void __launch_bounds__(256, 2) k_cost_fast(const Feat* __restrict__ f
                 c1 = __viaddmax_s16x2_relu(rr.x, lr.w, Y);
                 const uint32_t cr = __vmins2(c0, c1);
                 const uint32_t pd = cs + __byte_perm(cr, 0, 0x4341);   // + (cost_raw >> 2)
-                const uint32_t old = rrow[p * kCfTXH];
-                rrow[p * kCfTXH] = pd;
+                uint32_t old;
+                if (RING8) {
+                    old = __byte_perm(uint32_t(rrow[p * kCfTXH]), 0, 0x4140);
+                    rrow[p * kCfTXH] = ring_t(__byte_perm(pd, 0, 0x4420));
+                } else {
+                    old = rrow[p * kCfTXH];
+                    rrow[p * kCfTXH] = ring_t(pd);
+                }
                 V[i] = V[i] + pd - old;
                 vs[p * (kCfTXH + 1) + col] = V[i];
             }
@@ -287,13 +301,13 @@ __global__ void __launch_bounds__(256, 2) k_cost_fast(const Feat* __restrict__ f
 #pragma unroll
                 for (int c = 0; c < CPW; c++) {
                     if (c > 0) hs = hs + v[c + BS - 1] - v[c - 1];
-                    if (c < ncol) *reinterpret_cast<uint32_t*>(out + c * colBytes) = (hs & pad_and) | pad_or;
+                    if (c < ncol) *reinterpret_cast<uint32_t*>(out + c * colBytes) = NOPAD ? hs : ((hs & pad_and) | pad_or);
                 }
             } else {
                 for (int jj = 0; jj < bs; jj++) hs += vrow[jj];
                 for (int c = 0; c < ncol; c++) {
                     if (c > 0) hs = hs + vrow[c + bs - 1] - vrow[c - 1];
-                    *reinterpret_cast<uint32_t*>(out + c * colBytes) = (hs & pad_and) | pad_or;
+                    *reinterpret_cast<uint32_t*>(out + c * colBytes) = NOPAD ? hs : ((hs & pad_and) | pad_or);
                 }
             }
         }

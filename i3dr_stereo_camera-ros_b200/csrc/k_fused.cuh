@@ -380,7 +380,8 @@ struct VertGeom {
 // the data, so in the common case (the neighbour is not late) the L2 round trip is off the critical path.
 constexpr int kXbufGen = 4;
 constexpr int kVRing = 8;     // rows of C in flight per column (cp.async ring in shared memory): DRAM latency x row rate
-constexpr int kSRing = 4;     // rows of S_h in flight (S_h is consumed at the END of a row)
+constexpr int kSRing = 8;     // rows of S_h in flight: same depth as C -- cp.async groups retire in order, so a shallower
+                              // S_h ring would make its wait drain the younger C requests as well
 constexpr int kRowUnroll = 4; // the row loop is unrolled by this: record generation, stage slot, parity are immediates
 __device__ __forceinline__ uint2* xrec(uint2* xbuf, int nstrips, int Dp, int side, int strip, int row)
 {
@@ -635,8 +636,8 @@ __global__ void __launch_bounds__(1024, 1) k_vert(const uint16_t* __restrict__ C
         path_step<N>(Cc, LtB, LnB, lc);
         if (active) st_regs<N>(wrB[PAR], LtB);
         // ---- S = sat(S_h + L_v + L_A + L_B)
-        cp_async_wait<kSRing - 1>();     // S_h of this row travelled in the group of row r - (kSRing - 1)
-        if (active) ld_regs<N>(sring + (Q & (kSRing - 1)) * Dp, Sc);
+        static_assert(kSRing == kVRing, "S_h of row r travels in the same group as C of row r");
+        if (active) ld_regs<N>(sring + (r & (kSRing - 1)) * Dp, Sc);
         else {
 #pragma unroll
             for (int q = 0; q < N; q++) Sc[q] = 0;

@@ -26,8 +26,11 @@ struct Eff {
     int minX1, W1;   // first valid column, number of valid columns
 };
 
-// One prefiltered pixel (A.2): Sobel-x value and its half-pixel interval, raw value and its interval.
-// Packed as uint2: x = sob | sob_lo<<8 | sob_hi<<16 | raw<<24 ; y = raw_lo | raw_hi<<8.
-typedef uint2 Feat;
+// One prefiltered pixel (A.2): Sobel-x value with its half-pixel interval and the raw value (x64, so that the
+// ">> 2" of the raw cost is a byte extraction) with its interval, as signed 16-bit fields already in the form the
+// packed Birchfield-Tomasi arithmetic consumes them:
+//   x = sob | sob_lo << 16        y = (-sob_hi) | (-sob) << 16
+//   z = raw64 | raw64_lo << 16    w = (-raw64_hi) | (-raw64) << 16
+typedef uint4 Feat;
 
 }  // namespace b200sgm
