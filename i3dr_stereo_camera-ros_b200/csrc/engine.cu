@@ -213,6 +213,10 @@ int launch_vert_t(b200sgm_engine* h, Lane& ln, const Eff& e, const VertPlan& vp,
     g.P1 = e.P1; g.P2 = e.P2;
     g.spin_limit = (long long)h->clock_khz * 500;   // ~0.5 s of SM clock ticks
     { static const int dbg = [] { const char* v = getenv("B200SGM_DEBUG_VERT"); return v ? atoi(v) : 0; }(); g.debug_flags = dbg; }
+    // two agent warps per CTA when they fit next to the column warps (1024 threads per CTA)
+    int nthreads = (DO_WTA ? 64 : 32) * vp.twmax;
+    { static const bool no_agents = getenv("B200SGM_NO_AGENTS") != nullptr; g.agents = (!no_agents && nthreads + 64 <= 1024) ? 1 : 0; }
+    if (g.agents) nthreads += 64;
     auto kern = k_vert<N, UP, DO_WTA, FULL, CLAMP_EACH>;
     CUDA_TRY(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(vp.smem)));
     CUDA_TRY(h, cudaMemsetAsync(ln.xbuf, 0, size_t(2) * vp.nstrips * kXbufGen * (e.Dp / 2) * sizeof(uint2), st));
@@ -222,7 +226,7 @@ int launch_vert_t(b200sgm_engine* h, Lane& ln, const Eff& e, const VertPlan& vp,
     {
         std::lock_guard<std::mutex> lk(h->mu);
         if (h->coop_prev[0]) CUDA_TRY(h, cudaStreamWaitEvent(st, h->coop_prev[0], 0));
-        CUDA_TRY(h, cudaLaunchCooperativeKernel((void*)kern, dim3(vp.nstrips), dim3((DO_WTA ? 64 : 32) * vp.twmax), args, vp.smem, st));
+        CUDA_TRY(h, cudaLaunchCooperativeKernel((void*)kern, dim3(vp.nstrips), dim3(nthreads), args, vp.smem, st));
         h->launches++;
         cudaEvent_t ev = ln.coop_ev[ln.coop_idx];
         ln.coop_idx ^= 1;

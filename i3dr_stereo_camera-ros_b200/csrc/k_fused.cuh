@@ -369,6 +369,7 @@ struct VertGeom {
     int P1, P2;
     long long spin_limit; // clock64 ticks before a record wait gives up
     int debug_flags;      // timing experiments only (results are wrong): 1 = no inter-strip exchange, 2 = no WTA
+    int agents;           // 1: two extra warps per CTA poll the neighbours' records on behalf of the edge warps
 };
 
 // Inter-strip exchange, "low latency" protocol: a record is Dp/2 entries of {two packed costs, tag}; each
@@ -403,10 +404,11 @@ static_assert(kStage == kRowUnroll && kXbufGen == kRowUnroll && kStage % kWB == 
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
 __device__ __forceinline__ void named_bar_arrive(int id, int nthreads) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
 
-// dynamic smem: Ld[2 parity][2 dir][twmax+2][Dp] | Cring[kVRing][twmax][Dp] | Sring[kSRing][twmax][Dp] | stage[kStage][twmax][Dp]   (uint16)
+// dynamic smem: Ld[2 parity][2 dir][twmax+2][Dp] | Cring[kVRing][twmax][Dp] | Sring[kSRing][twmax][Dp] | stage[kStage][twmax][Dp]
+//               | xring[2 sides][kXbufGen][Dp]   (uint16)
 inline size_t vert_smem_bytes(int twmax, int Dp)
 {
-    return (size_t(4) * (twmax + 2) + size_t(kVRing + kSRing + kStage) * twmax) * Dp * sizeof(uint16_t);   // 155 KB at c3
+    return (size_t(4) * (twmax + 2) + size_t(kVRing + kSRing + kStage) * twmax + 2 * kXbufGen) * Dp * sizeof(uint16_t);   // 190 KB at c3
 }
 
 // Warp-specialised vertical sweep.  Launch: 32 * twmax threads when !DO_WTA, else 64 * twmax:
@@ -416,7 +418,11 @@ inline size_t vert_smem_bytes(int twmax, int Dp)
 //   WTA warps  (twmax .. 2*twmax-1)  : one per column; resolve kWB parked rows at a time (winner-take-all, uniqueness,
 //                                      sub-pixel, disp2 scatter).  They trail the path warps by up to kStage rows and fill
 //                                      the issue slots the path warps leave idle while they wait on each other.
-// Ring hand-over: named barriers full[q] (path warps arrive, WTA warps sync) and empty[q] (the reverse).
+//   agent warps (last two, optional) : one per neighbouring strip; poll the neighbour's exchange record of each row
+//                                      with back-to-back loads and drop it into shared memory, so the L2 round trips
+//                                      of the inter-strip exchange never sit on an edge path warp's critical path.
+// Ring hand-over: named barriers full[q] (path warps arrive, WTA warps sync) and empty[q] (the reverse); halo[side]
+// pairs an agent with its edge warp once per row.
 // FULL      : Dp == D == 64*N (no padded cells, every lane active)
 // CLAMP_EACH: saturate after every addition of the sum (needed when the 16-bit sum of the terms could wrap)
 template <int N, bool UP, bool DO_WTA, bool FULL, bool CLAMP_EACH>
@@ -436,19 +442,60 @@ __global__ void __launch_bounds__(1024, 1) k_vert(const uint16_t* __restrict__ C
     uint16_t* ringbase = Ld + size_t(4) * slots * Dp;
     uint16_t* sringbase = ringbase + size_t(kVRing) * g.twmax * Dp;
     uint16_t* stagebase = sringbase + size_t(kSRing) * g.twmax * Dp;
+    uint16_t* xringbase = stagebase + size_t(kStage) * g.twmax * Dp;
     {
         uint32_t* z = reinterpret_cast<uint32_t*>(smem_v);
         const int nz = 2 * slots * Dp;
         for (int i = threadIdx.x; i < nz; i += blockDim.x) z[i] = 0;
     }
     __syncthreads();
+    const int agent_base = DO_WTA ? 2 * g.twmax : g.twmax;
+    const bool exchange_on = !(g.debug_flags & 1);
+    const LaneCtx lc = make_lane_ctx<N>(lane, Dp, g.P1, g.P2);
+    const bool active = FULL || lc.active;
+    constexpr int BAR_ROW = 1, BAR_FULL = 2, BAR_EMPTY = 2 + kStage, BAR_HALO = 2 + 2 * kStage;
+    if (w >= agent_base) {
+        // ================================ agent warps ================================
+        const int side = w - agent_base;                     // 0: left neighbour (feeds warp 0), 1: right neighbour (feeds warp TW-1)
+        if (!g.agents || !exchange_on || (side == 0 ? b == 0 : b == n - 1)) return;
+        const uint2* rec0 = xrec(xbuf, n, Dp, side, side == 0 ? b - 1 : b + 1, 0) + lane * N;
+        uint16_t* dst = xringbase + size_t(side) * kXbufGen * Dp + lane * 2 * N;
+        const int gen_stride = Dp / 2;
+        bool dead = false;
+        for (int i = 0; i + 1 < H; i++) {                    // record of row i: consumed by the edge warp in its row i + 1
+            const uint2* rec = rec0 + (i & (kXbufGen - 1)) * gen_stride;
+            uint32_t d[N];
+#pragma unroll
+            for (int q = 0; q < N; q++) d[q] = 0;
+            if (active && !dead) {
+                const long long t0 = clock64();
+                int spins = 0;
+                while (true) {
+                    bool ok = true;
+#pragma unroll
+                    for (int q = 0; q < N; q++) {
+                        uint2 v = ld_volatile_v2(rec + q);
+                        d[q] = v.x;
+                        ok = ok && v.y == uint32_t(i + 1);
+                    }
+                    if (ok) break;
+                    if ((++spins & 255) == 0 && (clock64() - t0 > g.spin_limit || *reinterpret_cast<volatile int*>(err))) {
+                        atomicExch(err, 1);
+                        dead = true;
+                        break;
+                    }
+                }
+            }
+            dead = __any_sync(kFullMask, dead);
+            if (active) st_regs<N>(dst + (i & (kXbufGen - 1)) * Dp, d);
+            named_bar_sync(BAR_HALO + side, 64);
+        }
+        return;
+    }
     const bool wta_role = DO_WTA && w >= g.twmax;
     const int j = wta_role ? w - g.twmax : w;
     if (j >= TW) return;                 // the barriers below only count the TW column warps of each role
     const int nrow = 32 * TW, nboth = 64 * TW;
-    constexpr int BAR_ROW = 1, BAR_FULL = 2, BAR_EMPTY = 2 + kStage;
-    const LaneCtx lc = make_lane_ctx<N>(lane, Dp, g.P1, g.P2);
-    const bool active = FULL || lc.active;
     const int x = x0 + j;
     const int lo = lane * 2 * N;
     const int ringSlot = g.twmax * Dp;                 // slot stride of the stage ring [slot][warp][Dp]
@@ -469,11 +516,12 @@ __global__ void __launch_bounds__(1024, 1) k_vert(const uint16_t* __restrict__ C
         wc.umagic = wc.f > 0 ? uint32_t((1ull << 32) / uint32_t(wc.f)) + 1u : 0u;
         WtaAcc acc{0xFFFFFFFFu, 0u, 0, 0};
         int pending = 0;                    // rows parked in acc
-        for (int r = 0; r < H; r += kWB) {
-            const int cnt = min(kWB, H - r);
-            const int q0 = r & (kStage - 1);
-            for (int q = 0; q < cnt; q++) named_bar_sync(BAR_FULL + q0 + q, nboth);
-            uint16_t* sc = stage + q0 * ringSlot;
+        // one batch of kWB (= 2) parked rows starting at row r; Q0 = r & 3 is an immediate so that the barrier ids are
+        auto batch = [&](auto q0_tag, int r, int cnt) {
+            constexpr int Q0 = decltype(q0_tag)::value;
+            named_bar_sync(BAR_FULL + Q0, nboth);
+            if (cnt > 1) named_bar_sync(BAR_FULL + Q0 + 1, nboth);
+            uint16_t* sc = stage + Q0 * ringSlot;
             if (wta_on) {
                 if (wc.f > 0) {
                     wta_vec<N>(sc, ringSlot, r, g.w, wc, lane, active, acc);   // a row past the end lands in a lane >= cnt of the flush
@@ -493,9 +541,17 @@ __global__ void __launch_bounds__(1024, 1) k_vert(const uint16_t* __restrict__ C
                     dptr += cnt * dStride; kptr += cnt * dStride;
                 }
             }
-            for (int q = 0; q < cnt; q++)
-                if (r + q + kStage < H) named_bar_arrive(BAR_EMPTY + q0 + q, nboth);
+            if (r + kStage < H) named_bar_arrive(BAR_EMPTY + Q0, nboth);
+            if (cnt > 1 && r + 1 + kStage < H) named_bar_arrive(BAR_EMPTY + Q0 + 1, nboth);
+        };
+        static_assert(kWB == 2 && kStage == 4, "two batches per stage-ring revolution");
+        int r = 0;
+        for (; r + 3 < H; r += 4) {
+            batch(std::integral_constant<int, 0>{}, r, 2);
+            batch(std::integral_constant<int, 2>{}, r + 2, 2);
         }
+        if (r < H) batch(std::integral_constant<int, 0>{}, r, min(2, H - r));
+        if (r + 2 < H) batch(std::integral_constant<int, 2>{}, r + 2, 1);
         return;
     }
 
@@ -504,7 +560,10 @@ __global__ void __launch_bounds__(1024, 1) k_vert(const uint16_t* __restrict__ C
     // The left-edge warp runs direction 1 first (it publishes it), every other warp direction 0 first.
     const int dirA = j == 0 ? 1 : 0, dirB = 1 - dirA;
     const int slotA = dirA == 0 ? j : j + 2, slotB = dirB == 0 ? j : j + 2;
-    const bool edge = !(g.debug_flags & 1) && ((j == 0 && b > 0) || (j == TW - 1 && j != 0 && b < n - 1));   // publishes dirA, consumes dirB
+    const bool edge = exchange_on && ((j == 0 && b > 0) || (j == TW - 1 && j != 0 && b < n - 1));   // publishes dirA, consumes dirB
+    const bool use_agent = g.agents != 0;
+    const int halo_bar = BAR_HALO + (j == 0 ? 0 : 1);
+    const uint16_t* xin = xringbase + size_t(j == 0 ? 0 : 1) * kXbufGen * Dp + lo;   // what my agent received
     const int dirStride = slots * Dp, parStride = 2 * slots * Dp;
     const uint16_t* rdA[2]; uint16_t* wrA[2]; const uint16_t* rdB[2]; uint16_t* wrB[2];
 #pragma unroll
@@ -554,9 +613,15 @@ __global__ void __launch_bounds__(1024, 1) k_vert(const uint16_t* __restrict__ C
         constexpr int PAR = Q & 1;
         issue_c(r + kVRing - 1); issue_s(r + kSRing - 1); cp_async_commit();
         uint32_t Cc[N], Sc[N], LtA[N], LtB[N], LnA[N], LnV[N], LnB[N];
-        // incoming diagonal of the previous row: its loads were fired at the end of the previous row (`pre`), the
-        // tags are inspected right before step B
+        // incoming diagonal of the previous row: fire the loads now, inspect the tags right before step B
         const bool consume = EDGE && r > 0;
+        if (EDGE) {
+            if (consume && active && !use_agent) {
+                const uint2* rec = con_base + ((Q + kXbufGen - 1) & (kXbufGen - 1)) * gen_stride;
+#pragma unroll
+                for (int q = 0; q < N; q++) pre[q] = ld_volatile_v2(rec + q);
+            }
+        }
         cp_async_wait<kVRing - 1>();     // this thread's copies of row r have landed (each lane reads only its own bytes)
         if (active) {
             ld_regs<N>(ring + (r & (kVRing - 1)) * Dp, Cc); ld_regs<N>(rdA[PAR ^ 1], LtA);
@@ -575,25 +640,18 @@ __global__ void __launch_bounds__(1024, 1) k_vert(const uint16_t* __restrict__ C
                 for (int q = 0; q < N; q++) st_volatile_v2(rec + q, LtA[q], uint32_t(r + 1));
             }
         }
-        if (EDGE) {
-            if (consume) {      // second chance for a record that was not there yet when it was requested a row ago
-                bool ok = true;
-                if (active) {
-#pragma unroll
-                    for (int q = 0; q < N; q++) ok = ok && pre[q].y == uint32_t(r);
-                }
-                if (!__all_sync(kFullMask, ok) && active) {
-                    const uint2* rec = con_base + ((Q + kXbufGen - 1) & (kXbufGen - 1)) * gen_stride;
-#pragma unroll
-                    for (int q = 0; q < N; q++) pre[q] = ld_volatile_v2(rec + q);
-                }
-            }
-        }
         // ---- vertical path: registers only
         path_step<N>(Cc, LtV, LnV, lc);
         // ---- step B
         if (EDGE) {
-            if (consume) {
+            if (consume && use_agent) {
+                named_bar_sync(halo_bar, 64);          // my agent has dropped the record of row r-1 into shared memory
+                if (active) ld_regs<N>(xin + ((Q + kXbufGen - 1) & (kXbufGen - 1)) * Dp, LtB);
+                else {
+#pragma unroll
+                    for (int q = 0; q < N; q++) LtB[q] = 0;
+                }
+            } else if (consume) {
                 bool ok = true;
 #pragma unroll
                 for (int q = 0; q < N; q++) LtB[q] = 0;
@@ -668,13 +726,6 @@ __global__ void __launch_bounds__(1024, 1) k_vert(const uint16_t* __restrict__ C
         } else {
             if (active) st_regs<N>(gSout, S);
             gSout += rowStride;
-        }
-        if (EDGE) {
-            if (active) {       // request the neighbour's record of THIS row: it is consumed late in the next row
-                const uint2* rec = con_base + Q * gen_stride;
-#pragma unroll
-                for (int q = 0; q < N; q++) pre[q] = ld_volatile_v2(rec + q);
-            }
         }
         named_bar_sync(BAR_ROW, nrow);
     };
