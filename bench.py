@@ -43,7 +43,7 @@ def parse():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--config", default="c3", choices=sorted(CONFIGS))
     ap.add_argument("--frames", type=int, default=16, help="distinct frames per step per GPU")
-    ap.add_argument("--lanes", type=int, default=2, help="frames in flight per GPU")
+    ap.add_argument("--lanes", type=int, default=4, help="frames in flight per GPU")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--cpu-frames", type=int, default=0, help="frames in the CPU sample (default: one per core)")

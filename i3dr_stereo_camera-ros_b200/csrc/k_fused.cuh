@@ -462,6 +462,58 @@ __global__ void __launch_bounds__(1024, 1) k_vert(const uint16_t* __restrict__ C
         uint16_t* dst = xringbase + size_t(side) * kXbufGen * Dp + lane * 2 * N;
         const int gen_stride = Dp / 2;
         bool dead = false;
+        if (DO_WTA) {
+            // The agent OWNS the edge column's incoming-diagonal path (the one step of the row that depends on the
+            // neighbour strip): record of row r-1 -> path update with C(r) from the column's cp.async ring -> new state for
+            // the inner neighbour column (Ld) and L for the sum (stageB, added by the column's WTA warp).  The edge path
+            // warp is left with two independent steps, so the exchange latency is off every column warp's critical path.
+            const int nag = (b > 0 ? 1 : 0) + (b < n - 1 ? 1 : 0);
+            const int nrow_a = 32 * (TW + nag), nfe_a = 64 * TW + 32 * nag;
+            const int je = side == 0 ? 0 : TW - 1;
+            uint16_t* wr = Ld + side * (slots * Dp) + (je + 1) * Dp + lane * 2 * N;          // + parity * 2*slots*Dp
+            const uint16_t* cring = ringbase + size_t(je) * kVRing * Dp + lane * 2 * N;
+            uint16_t* sB = dst;                                                              // stageB[side][kStage][Dp] aliases the xring
+            asm volatile("bar.sync 1, %0;" ::"r"(nrow_a) : "memory");                          // C(0) is visible
+            for (int r = 0; r < H; r++) {
+                uint32_t Cc[N], Lt[N], Ln[N];
+#pragma unroll
+                for (int q = 0; q < N; q++) Lt[q] = 0;
+                if (r > 0 && active && !dead) {
+                    const uint2* rec = rec0 + ((r - 1) & (kXbufGen - 1)) * gen_stride;
+                    const long long t0 = clock64();
+                    int spins = 0;
+                    while (true) {
+                        bool ok = true;
+#pragma unroll
+                        for (int q = 0; q < N; q++) {
+                            uint2 v = ld_volatile_v2(rec + q);
+                            Lt[q] = v.x;
+                            ok = ok && v.y == uint32_t(r);
+                        }
+                        if (ok || (g.debug_flags & 8)) break;     // 8: timing experiment, take whatever is there
+                        if ((++spins & 255) == 0 && (clock64() - t0 > g.spin_limit || *reinterpret_cast<volatile int*>(err))) {
+                            atomicExch(err, 1);
+                            dead = true;
+                            break;
+                        }
+                    }
+                }
+                dead = __any_sync(kFullMask, dead);
+                if (active) ld_regs<N>(cring + (r & (kVRing - 1)) * Dp, Cc);
+                else {
+#pragma unroll
+                    for (int q = 0; q < N; q++) Cc[q] = kMaxCostX2;
+                }
+                path_step<N>(Cc, Lt, Ln, lc);
+                if (active) st_regs<N>(wr + (r & 1) * (2 * slots * Dp), Lt);
+                const int q4 = r & (kStage - 1);
+                if (r >= kStage) named_bar_sync(BAR_EMPTY + q4, nfe_a);
+                if (active) st_regs<N>(sB + q4 * Dp, Ln);
+                named_bar_arrive(BAR_FULL + q4, nfe_a);
+                asm volatile("bar.sync 1, %0;" ::"r"(nrow_a) : "memory");                      // BAR_ROW of row r
+            }
+            return;
+        }
         for (int i = 0; i + 1 < H; i++) {                    // record of row i: consumed by the edge warp in its row i + 1
             const uint2* rec = rec0 + (i & (kXbufGen - 1)) * gen_stride;
             uint32_t d[N];
@@ -495,7 +547,9 @@ __global__ void __launch_bounds__(1024, 1) k_vert(const uint16_t* __restrict__ C
     const bool wta_role = DO_WTA && w >= g.twmax;
     const int j = wta_role ? w - g.twmax : w;
     if (j >= TW) return;                 // the barriers below only count the TW column warps of each role
-    const int nrow = 32 * TW, nboth = 64 * TW;
+    // agents of a WTA sweep take part in the row barrier and in the stage-ring hand-over
+    const int nag3 = (DO_WTA && g.agents && exchange_on) ? (b > 0 ? 1 : 0) + (b < n - 1 ? 1 : 0) : 0;
+    const int nrow = 32 * (TW + nag3), nboth = 64 * TW + 32 * nag3;
     const int x = x0 + j;
     const int lo = lane * 2 * N;
     const int ringSlot = g.twmax * Dp;                 // slot stride of the stage ring [slot][warp][Dp]
@@ -516,12 +570,35 @@ __global__ void __launch_bounds__(1024, 1) k_vert(const uint16_t* __restrict__ C
         wc.umagic = wc.f > 0 ? uint32_t((1ull << 32) / uint32_t(wc.f)) + 1u : 0u;
         WtaAcc acc{0xFFFFFFFFu, 0u, 0, 0};
         int pending = 0;                    // rows parked in acc
+        const int edge_side = nag3 == 0 ? -1 : ((j == 0 && b > 0) ? 0 : ((j == TW - 1 && j != 0 && b < n - 1) ? 1 : -1));
         // one batch of kWB (= 2) parked rows starting at row r; Q0 = r & 3 is an immediate so that the barrier ids are
         auto batch = [&](auto q0_tag, int r, int cnt) {
             constexpr int Q0 = decltype(q0_tag)::value;
             named_bar_sync(BAR_FULL + Q0, nboth);
             if (cnt > 1) named_bar_sync(BAR_FULL + Q0 + 1, nboth);
             uint16_t* sc = stage + Q0 * ringSlot;
+            if (edge_side >= 0) {
+                // edge column: the agent computed the incoming-diagonal path; add its L to the parked partial sum
+                const uint16_t* sB = xringbase + size_t(edge_side) * kStage * Dp + lane * 2 * N;
+#pragma unroll
+                for (int q = 0; q < kWB; q++) {
+                    if (q < cnt && active) {
+                        uint32_t P[N], B[N];
+                        ld_regs<N>(sc + q * ringSlot + lane * 2 * N, P);
+                        ld_regs<N>(sB + (Q0 + q) * Dp, B);
+#pragma unroll
+                        for (int i = 0; i < N; i++) {
+                            P[i] = __vminu2(P[i] + B[i], kMaxCostX2);
+                            if (!FULL) {
+                                const int k = lane * N + i;
+                                if (k >= g.w.D) P[i] = 0xFFFFFFFFu;
+                                else if (k + wc.Dh >= g.w.D) P[i] |= 0xFFFF0000u;
+                            }
+                        }
+                        st_regs<N>(sc + q * ringSlot + lane * 2 * N, P);
+                    }
+                }
+            }
             if (wta_on) {
                 if (wc.f > 0) {
                     wta_vec<N>(sc, ringSlot, r, g.w, wc, lane, active, acc);   // a row past the end lands in a lane >= cnt of the flush
@@ -562,6 +639,9 @@ __global__ void __launch_bounds__(1024, 1) k_vert(const uint16_t* __restrict__ C
     const int slotA = dirA == 0 ? j : j + 2, slotB = dirB == 0 ? j : j + 2;
     const bool edge = exchange_on && ((j == 0 && b > 0) || (j == TW - 1 && j != 0 && b < n - 1));   // publishes dirA, consumes dirB
     const bool use_agent = g.agents != 0;
+    // edge mode: 1 = poll the neighbour's record in this warp, 2 = an agent delivers it (halo barrier), 3 = an agent
+    // computes the incoming-diagonal step itself (WTA sweeps)
+    const int edge_mode = !edge ? 0 : (!use_agent ? 1 : (DO_WTA ? 3 : 2));
     const int halo_bar = BAR_HALO + (j == 0 ? 0 : 1);
     const uint16_t* xin = xringbase + size_t(j == 0 ? 0 : 1) * kXbufGen * Dp + lo;   // what my agent received
     const int dirStride = slots * Dp, parStride = 2 * slots * Dp;
@@ -599,6 +679,10 @@ __global__ void __launch_bounds__(1024, 1) k_vert(const uint16_t* __restrict__ C
     for (int i = 0; i < kSRing - 1; i++) issue_s(i);
 #pragma unroll
     for (int i = 0; i < kVRing - 1; i++) { issue_c(i); cp_async_commit(); }
+    if (nag3) {            // agents read this column's C ring: make row 0 visible to them
+        cp_async_wait<kVRing - 2>();
+        named_bar_sync(BAR_ROW, nrow);
+    }
 
     uint32_t LtV[N];
     uint2 pre[N];        // edge warps: the neighbour's record of the previous row, requested one row early
@@ -609,14 +693,16 @@ __global__ void __launch_bounds__(1024, 1) k_vert(const uint16_t* __restrict__ C
     // one row; Q = r mod 4 (ring slot, record generation, stage slot; parity = Q & 1); EDGE = this warp exchanges
     auto row = [&](auto q_tag, auto edge_tag, int r) {
         constexpr int Q = decltype(q_tag)::value;
-        constexpr bool EDGE = decltype(edge_tag)::value;
+        constexpr int EMODE = decltype(edge_tag)::value;
+        constexpr bool EDGE = EMODE != 0;
+        constexpr bool NO_B = EMODE == 3;      // the agent owns the incoming-diagonal step
         constexpr int PAR = Q & 1;
         issue_c(r + kVRing - 1); issue_s(r + kSRing - 1); cp_async_commit();
         uint32_t Cc[N], Sc[N], LtA[N], LtB[N], LnA[N], LnV[N], LnB[N];
         // incoming diagonal of the previous row: fire the loads now, inspect the tags right before step B
         const bool consume = EDGE && r > 0;
-        if (EDGE) {
-            if (consume && active && !use_agent) {
+        if (EMODE == 1) {
+            if (consume && active) {
                 const uint2* rec = con_base + ((Q + kXbufGen - 1) & (kXbufGen - 1)) * gen_stride;
 #pragma unroll
                 for (int q = 0; q < N; q++) pre[q] = ld_volatile_v2(rec + q);
@@ -643,8 +729,8 @@ __global__ void __launch_bounds__(1024, 1) k_vert(const uint16_t* __restrict__ C
         // ---- vertical path: registers only
         path_step<N>(Cc, LtV, LnV, lc);
         // ---- step B
-        if (EDGE) {
-            if (consume && use_agent) {
+        if (EDGE && !NO_B) {
+            if (consume && EMODE == 2) {
                 named_bar_sync(halo_bar, 64);          // my agent has dropped the record of row r-1 into shared memory
                 if (active) ld_regs<N>(xin + ((Q + kXbufGen - 1) & (kXbufGen - 1)) * Dp, LtB);
                 else {
@@ -691,8 +777,13 @@ __global__ void __launch_bounds__(1024, 1) k_vert(const uint16_t* __restrict__ C
                 }
             }
         }
-        path_step<N>(Cc, LtB, LnB, lc);
-        if (active) st_regs<N>(wrB[PAR], LtB);
+        if (!NO_B) {
+            path_step<N>(Cc, LtB, LnB, lc);
+            if (active) st_regs<N>(wrB[PAR], LtB);
+        } else {
+#pragma unroll
+            for (int q = 0; q < N; q++) LnB[q] = 0;
+        }
         // ---- S = sat(S_h + L_v + L_A + L_B)
         static_assert(kSRing == kVRing, "S_h of row r travels in the same group as C of row r");
         if (active) ld_regs<N>(sring + (r & (kSRing - 1)) * Dp, Sc);
@@ -727,6 +818,7 @@ __global__ void __launch_bounds__(1024, 1) k_vert(const uint16_t* __restrict__ C
             if (active) st_regs<N>(gSout, S);
             gSout += rowStride;
         }
+        if (DO_WTA) cp_async_wait<kVRing - 2>();   // C of the NEXT row is complete before the barrier: the agents read it
         named_bar_sync(BAR_ROW, nrow);
     };
 
@@ -743,8 +835,10 @@ __global__ void __launch_bounds__(1024, 1) k_vert(const uint16_t* __restrict__ C
         if (rem > 1) row(std::integral_constant<int, 1>{}, edge_tag, r + 1);
         if (rem > 2) row(std::integral_constant<int, 2>{}, edge_tag, r + 2);
     };
-    if (edge) sweep(std::true_type{});
-    else sweep(std::false_type{});
+    if (edge_mode == 0) sweep(std::integral_constant<int, 0>{});
+    else if (edge_mode == 1) sweep(std::integral_constant<int, 1>{});
+    else if (DO_WTA) sweep(std::integral_constant<int, DO_WTA ? 3 : 1>{});
+    else sweep(std::integral_constant<int, DO_WTA ? 1 : 2>{});
     cp_async_wait<0>();
 }
 
