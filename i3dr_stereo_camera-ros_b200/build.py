@@ -24,20 +24,37 @@ def sources():
     return [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC)) if f.endswith(".cu")]
 
 
-def needs_build() -> bool:
-    if not os.path.exists(LIB):
+OBJ = os.path.join(CSRC, "_obj")
+
+
+def _stale(target: str, deps) -> bool:
+    if not os.path.exists(target):
         return True
-    t = os.path.getmtime(LIB)
-    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(HERE, "..", "include", "b200sgm.h")]
+    t = os.path.getmtime(target)
     return any(os.path.getmtime(d) > t for d in deps)
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
-    if not force and not needs_build():
-        return LIB
-    cmd = [NVCC] + FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + sources()
-    print("[b200sgm] " + " ".join(cmd), file=sys.stderr)
-    subprocess.check_call(cmd)
+    """Compiles every csrc/*.cu to its own object (in parallel, only the stale ones) and links libb200sgm.so."""
+    os.makedirs(OBJ, exist_ok=True)
+    headers = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".h", ".cuh"))]
+    headers.append(os.path.join(HERE, "..", "include", "b200sgm.h"))
+    cflags = [f for f in FLAGS if f != "-shared"]
+    procs, objs = [], []
+    for src in sources():
+        obj = os.path.join(OBJ, os.path.basename(src)[:-3] + ".o")
+        objs.append(obj)
+        if force or _stale(obj, [src] + headers):
+            cmd = [NVCC] + cflags + (["-Xptxas", "-v"] if verbose else []) + ["-c", "-o", obj, src]
+            print("[b200sgm] " + " ".join(cmd), file=sys.stderr)
+            procs.append((cmd, subprocess.Popen(cmd)))
+    for cmd, p in procs:
+        if p.wait() != 0:
+            raise subprocess.CalledProcessError(p.returncode, cmd)
+    if procs or force or _stale(LIB, objs):
+        cmd = [NVCC, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", LIB] + objs
+        print("[b200sgm] " + " ".join(cmd), file=sys.stderr)
+        subprocess.check_call(cmd)
     return LIB
 
 

@@ -13,7 +13,7 @@
 
 #include "../../include/b200sgm.h"
 #include "sgm_types.h"
-#include "k_cost.cuh"
+#include "stages.h"
 #include "k_path.cuh"
 #include "k_wta.cuh"
 #include "k_fused.cuh"
@@ -153,12 +153,6 @@ int make_eff(b200sgm_engine* h, int W, int H, Eff& e)
     if (maxD * 16 >= 32768 || e.INVALID < -32768) return fail(h, B200SGM_EINVAL, "disparity range does not fit CV_16S x16");
     if (e.SW2 > 127) return fail(h, B200SGM_EINVAL, "blockSize > 255 unsupported");
     return B200SGM_OK;
-}
-
-size_t cost_smem_bytes(int TX, int DCP, int SW2)
-{
-    const int bs = 2 * SW2 + 1;
-    return size_t((TX + 2 * SW2) + bs * TX + TX) * DCP * 4;
 }
 
 template <int N>
@@ -361,8 +355,7 @@ int run_pipeline(b200sgm_engine* h, Lane& ln, const Eff& e, const uint8_t* dL, s
     }
     prof_mark(h, ln, 0, st);
     {
-        dim3 block(256), grid((W + 255) / 256, H, 2);
-        k_prefilter<<<grid, block, 0, st>>>(dL, lp, dR, rp, W, H, e.ftzero, ln.feat_l, ln.feat_r);
+        launch_prefilter(dL, lp, dR, rp, W, H, e.ftzero, ln.feat_l, ln.feat_r, st);
         LAUNCH_CHECK(h);
     }
     CUDA_TRY(h, cudaMemsetAsync(ln.disp2key, 0xFF, size_t(npix) * 4, st));
@@ -370,37 +363,12 @@ int run_pipeline(b200sgm_engine* h, Lane& ln, const Eff& e, const uint8_t* dL, s
     LAUNCH_CHECK(h);
     prof_mark(h, ln, 1, st);
     if (e.W1 > 0) {
-        if (e.SW2 <= 10 && h->path != 1) {
-            CostFastGeom fg{W, H, e.W1, e.minX1, e.minD, e.D, e.Dp, e.SW2, 128};
-            const bool ring8 = 2 * e.ftzero + 63 <= 255;
-            const bool nopad = e.Dp == e.D && (e.Dp / 2) % kCfDCP == 0;
-            const size_t smem = cost_fast_smem(e.SW2, ring8);
-            const int TX = kCfTXH - 2 * e.SW2;
-            dim3 grid((e.W1 + TX - 1) / TX, (e.Dp / 2 + kCfDCP - 1) / kCfDCP, (H + fg.RS - 1) / fg.RS);
-            void (*kern)(const Feat*, const Feat*, uint16_t*, CostFastGeom);
-            if (e.SW2 == 4) kern = ring8 ? (nopad ? k_cost_fast<4, true, true> : k_cost_fast<4, true, false>) : k_cost_fast<4, false, false>;
-            else if (e.SW2 == 2) kern = ring8 ? (nopad ? k_cost_fast<2, true, true> : k_cost_fast<2, true, false>) : k_cost_fast<2, false, false>;
-            else kern = ring8 ? k_cost_fast<0, true, false> : k_cost_fast<0, false, false>;
-            CUDA_TRY(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
-            kern<<<grid, 256, smem, st>>>(ln.feat_l, ln.feat_r, ln.C, fg);
-            LAUNCH_CHECK(h);
-        } else {
-            CostGeom cg;
-            cg.W = W; cg.H = H; cg.W1 = e.W1; cg.minX1 = e.minX1; cg.minD = e.minD; cg.D = e.D; cg.Dp = e.Dp; cg.SW2 = e.SW2;
-            int TX = 32, DCP = 32;
-            while (DCP * 2 > e.Dp && DCP > 1) DCP /= 2;
-            const size_t limit = 200 * 1024;
-            while (cost_smem_bytes(TX, DCP, e.SW2) > limit && TX > 4) TX /= 2;
-            while (cost_smem_bytes(TX, DCP, e.SW2) > limit && DCP > 4) DCP /= 2;
-            while (cost_smem_bytes(TX, DCP, e.SW2) > limit && TX > 1) TX /= 2;
-            if (cost_smem_bytes(TX, DCP, e.SW2) > limit) return fail(h, B200SGM_EINVAL, "blockSize too large for the cost kernel");
-            cg.TX = TX; cg.DCP = DCP; cg.RS = 64;
-            const size_t smem = cost_smem_bytes(TX, DCP, e.SW2);
-            CUDA_TRY(h, cudaFuncSetAttribute(k_cost_generic, cudaFuncAttributeMaxDynamicSharedMemorySize, int(limit)));
-            dim3 grid((e.W1 + TX - 1) / TX, (e.Dp / 2 + DCP - 1) / DCP, (H + cg.RS - 1) / cg.RS);
-            k_cost_generic<<<grid, 256, smem, st>>>(ln.feat_l, ln.feat_r, ln.C, cg);
-            LAUNCH_CHECK(h);
-        }
+        const char* msg = nullptr;
+        int nl = 0;
+        const cudaError_t ce = launch_cost(ln.feat_l, ln.feat_r, ln.C, e, h->path == 1, h->num_sms, st, &nl, &msg);
+        h->launches += nl;
+        if (msg) return fail(h, B200SGM_EINVAL, msg);
+        if (ce != cudaSuccess) return fail(h, B200SGM_ECUDA, std::string("cost kernel launch: ") + cudaGetErrorString(ce));
     }
     prof_mark(h, ln, 2, st);
     if (e.W1 > 0) {

@@ -316,4 +316,178 @@ __global__ void __launch_bounds__(256, RING8 ? 3 : 2) k_cost_fast(const Feat* __
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// A.3 + A.4, register-tiled version (blockSize <= 21, pixel costs that fit a byte).  One CTA (256 threads) owns a
+// tile of 128 x1-columns (128 - 2*SW2 output columns + halo) x 32 disparity pairs and slides down a segment of rows.
+// Phase 1: a thread owns TWO adjacent columns x EIGHT consecutive disparity pairs.  The right-image record of
+// (column c, pair p) is record c + 31 - p of the row, so the 16 pixel costs of a thread need only 9 right records
+// (a rolling pair of registers) + 2 left records: 22 LDS.128 instead of 36 for the same work -- the shared-memory
+// pipe is what bounds this kernel.  Records are stored de-interleaved by parity so that the stride-2 column
+// ownership stays bank-conflict free; the ring of the last `bs` rows holds the byte costs of both columns of a
+// disparity pair in one 32-bit word; the vertical sums go to vs[pair][f(column)], f(c) = (c & 1) * 64 + (c >> 1).
+// Tile columns are VIRTUAL (x1 = tx0 - SW2 + c, unclamped): the x1-domain replicate clamp of A.4 is applied by
+// phase 2 when it picks the columns of a window, so border tiles need no special record indexing.
+// Phase 2: lanes <-> disparity pairs, a warp owns a run of 16 output columns (sliding horizontal window held in
+// registers), coalesced 128-byte stores of C[y][x1][k0 .. k0+64).
+// ------------------------------------------------------------------------------------------------
+constexpr int kC2TXH = 128;   // tile columns incl. halo
+constexpr int kC2NRH = 80;    // right-image records per parity (records 0 .. 158)
+constexpr int kC2VS = 129;    // row stride of vs (odd: phase 2 reads one column of 32 pairs conflict-free)
+constexpr int kC2CPW = 16;    // output columns per warp in phase 2 (even, so f() of a window column is an immediate)
+
+inline size_t cost_tile2_smem(int SW2)
+{
+    const int bs = 2 * SW2 + 1;
+    return size_t(2) * 2 * 2 * kC2NRH * sizeof(uint4) + size_t(2) * 2 * kC2TXH * sizeof(uint4) + size_t(kCfDCP) * kC2VS * 4 +
+           size_t(bs) * kCfDCP * (kC2TXH / 2) * 4;
+}
+
+template <int SW2T, bool NOPAD>
+__global__ void __launch_bounds__(256, 2) k_cost_tile2(const Feat* __restrict__ fl, const Feat* __restrict__ fr,
+                                                       uint16_t* __restrict__ Cvol, CostFastGeom g)
+{
+    extern __shared__ uint4 c2_smem[];
+    const int SW2 = SW2T > 0 ? SW2T : g.SW2;
+    const int bs = 2 * SW2 + 1;
+    const int TX = kC2TXH - 2 * SW2;
+    uint4* Rrec = c2_smem;                                  // [2 buf][2 chan][2 parity][kC2NRH]
+    uint4* Lrec = Rrec + 2 * 2 * 2 * kC2NRH;                // [2 buf][2 chan][2 parity][64]
+    uint32_t* vs = reinterpret_cast<uint32_t*>(Lrec + 2 * 2 * kC2TXH);   // [32][kC2VS]
+    uint32_t* ring = vs + kCfDCP * kC2VS;                   // [bs][32][64]
+
+    const int t = threadIdx.x, lane = t & 31, w = t >> 5;
+    const int tx0 = blockIdx.x * TX;
+    const int k0 = blockIdx.y * kCfDCP;
+    const int Dh = g.Dp >> 1;
+    const int ya = blockIdx.z * g.RS, yb = min(ya + g.RS, g.H);
+    const int xv0 = tx0 - SW2 + g.minX1;                    // image x of (virtual) tile column 0
+    const int xr_min = xv0 - g.minD - k0 - (kCfDCP - 1);    // right-image x of record 0
+
+    // phase-1 role: columns 2m, 2m+1; pairs p0 .. p0+7
+    const int m = (w >> 2) * 32 + lane, p0 = (w & 3) * 8;
+    uint32_t VA[8], VB[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) { VA[i] = 0; VB[i] = 0; }
+    for (int i = t; i < bs * kCfDCP * (kC2TXH / 2); i += 256) ring[i] = 0;
+
+    auto stage = [&](int s, int buf) {
+        const int e = min(max(ya - SW2 + s, 0), g.H - 1);
+        if (t < 2 * kC2NRH) {
+            const int xr = xr_min + t;
+            const Feat a = __ldg(fr + size_t(e) * g.W + min(max(xr, 0), g.W - 1));
+            const Feat b = __ldg(fr + size_t(e) * g.W + min(max(xr - Dh, 0), g.W - 1));
+            uint4* d = Rrec + ((buf * 2 + 0) * 2 + (t & 1)) * kC2NRH + (t >> 1);
+            // (v, lo, -hi, -v) of the pixel pair (xr, xr - Dh), low half = xr
+            d[0] = make_uint4(__byte_perm(a.x, b.x, 0x5410), __byte_perm(a.x, b.x, 0x7632),
+                              __byte_perm(a.y, b.y, 0x5410), __byte_perm(a.y, b.y, 0x7632));
+            d[2 * kC2NRH] = make_uint4(__byte_perm(a.z, b.z, 0x5410), __byte_perm(a.z, b.z, 0x7632),
+                                       __byte_perm(a.w, b.w, 0x5410), __byte_perm(a.w, b.w, 0x7632));
+        }
+        if (t >= 128) {
+            const int c = t - 128;
+            const Feat a = __ldg(fl + size_t(e) * g.W + min(max(xv0 + c, 0), g.W - 1));
+            uint4* d = Lrec + ((buf * 2 + 0) * 2 + (c & 1)) * 64 + (c >> 1);
+            // (u, -u, lo, -hi), each replicated in both halves
+            d[0] = make_uint4(__byte_perm(a.x, a.x, 0x1010), __byte_perm(a.y, a.y, 0x3232),
+                              __byte_perm(a.x, a.x, 0x3232), __byte_perm(a.y, a.y, 0x1010));
+            d[2 * 64] = make_uint4(__byte_perm(a.z, a.z, 0x1010), __byte_perm(a.w, a.w, 0x3232),
+                                   __byte_perm(a.z, a.z, 0x3232), __byte_perm(a.w, a.w, 0x1010));
+        }
+    };
+    // Birchfield-Tomasi cost of one (left pixel, right pixel pair): sobel + (raw >> 2), 16x2
+    auto bt = [](const uint4& ls, const uint4& lr, const uint4& rs, const uint4& rr) {
+        uint32_t X = __vadd2(rs.y, ls.y);
+        uint32_t c0 = __viaddmax_s16x2_relu(ls.x, rs.z, X);
+        uint32_t Y = __vadd2(ls.z, rs.w);
+        uint32_t c1 = __viaddmax_s16x2_relu(rs.x, ls.w, Y);
+        const uint32_t cs = __vmins2(c0, c1);
+        X = __vadd2(rr.y, lr.y);
+        c0 = __viaddmax_s16x2_relu(lr.x, rr.z, X);
+        Y = __vadd2(lr.z, rr.w);
+        c1 = __viaddmax_s16x2_relu(rr.x, lr.w, Y);
+        const uint32_t cr = __vmins2(c0, c1);
+        return cs + __byte_perm(cr, 0, 0x4341);   // + (cost_raw >> 2)
+    };
+
+    stage(0, 0);
+    __syncthreads();
+    const int nsteps = (yb - ya) + bs - 1;
+    // phase-2 role
+    const int c_lo = w * kC2CPW, c_hi = min(c_lo + kC2CPW, TX);
+    const int kk = k0 + lane;
+    const uint32_t pad_or = kk >= g.D ? kMaxCostX2 : (kk + Dh >= g.D ? (uint32_t(kMaxCost) << 16) : 0u);
+    const uint32_t pad_and = kk >= g.D ? 0u : (kk + Dh >= g.D ? 0x0000FFFFu : 0xFFFFFFFFu);
+    const bool lane_ok = kk < Dh;
+    const size_t colBytes = size_t(g.Dp) * 2;
+    const int ncol = min(c_hi, g.W1 - tx0) - c_lo;           // output columns of this run that exist in the image
+    // tile columns that exist in the x1 domain: windows clamp to [cmin, cmax]
+    const int cmin = max(0, SW2 - tx0), cmax = min(kC2TXH - 1, g.W1 - 1 - tx0 + SW2);
+    const bool interior = cmin == 0 && cmax == kC2TXH - 1;
+    auto vsf = [](int c) { return (c & 1) * 64 + (c >> 1); };
+    int slot = 0;
+    for (int s = 0; s < nsteps; s++) {
+        const int buf = s & 1;
+        // ---- phase 1
+        {
+            const uint4* Lb = Lrec + buf * 4 * 64 + m;
+            const uint4 lsA = Lb[0], lsB = Lb[64], lrA = Lb[128], lrB = Lb[192];
+            uint32_t* rrow = ring + size_t(slot) * kCfDCP * 64 + p0 * 64 + m;
+            slot = slot + 1 == bs ? 0 : slot + 1;
+            // record of (column 2m, pair p): 2m + 31 - p; p even -> odd record m + 15 - p/2, p odd -> even record m + (31-p)/2
+            const uint4* Rb = Rrec + buf * 4 * kC2NRH + m - (p0 >> 1);
+            uint4 rsB = Rb[16], rrB = Rb[2 * kC2NRH + 16];          // record 2m + 32 - p0 (even)
+            uint32_t* vrowA = vs + p0 * kC2VS + m;
+#pragma unroll
+            for (int i = 0; i < 8; i++) {
+                const int off = (i & 1) ? (31 - i) / 2 : kC2NRH + 15 - i / 2;
+                const uint4 rsA = Rb[off], rrA = Rb[2 * kC2NRH + off];
+                const uint32_t pdA = bt(lsA, lrA, rsA, rrA);
+                const uint32_t pdB = bt(lsB, lrB, rsB, rrB);
+                const uint32_t rw = rrow[i * 64];
+                rrow[i * 64] = __byte_perm(pdA, pdB, 0x6420);
+                VA[i] = VA[i] + pdA - __byte_perm(rw, 0, 0x4140);
+                VB[i] = VB[i] + pdB - __byte_perm(rw, 0, 0x4342);
+                vrowA[i * kC2VS] = VA[i];
+                vrowA[i * kC2VS + 64] = VB[i];
+                rsB = rsA; rrB = rrA;
+            }
+        }
+        __syncthreads();
+        // ---- phase 2 (once the vertical window is full) + staging of the next row
+        if (s >= bs - 1 && ncol > 0 && lane_ok) {
+            const int y = ya + s - (bs - 1);
+            const uint32_t* vrow = vs + lane * kC2VS;
+            char* out = reinterpret_cast<char*>(Cvol + (size_t(y) * g.W1 + tx0 + c_lo) * g.Dp + 2 * kk);
+            uint32_t hs = 0;
+            if (SW2T > 0) {
+                constexpr int BS = 2 * SW2T + 1;
+                uint32_t v[kC2CPW + BS - 1];
+                if (interior) {
+                    const uint32_t* vb = vrow + (c_lo >> 1);
+#pragma unroll
+                    for (int jj = 0; jj < kC2CPW + BS - 1; jj++) v[jj] = vb[(jj & 1) * 64 + (jj >> 1)];   // may run past the tile: harmless
+                } else {
+#pragma unroll
+                    for (int jj = 0; jj < kC2CPW + BS - 1; jj++) v[jj] = vrow[vsf(min(max(c_lo + jj, cmin), cmax))];
+                }
+#pragma unroll
+                for (int jj = 0; jj < BS; jj++) hs += v[jj];
+#pragma unroll
+                for (int c = 0; c < kC2CPW; c++) {
+                    if (c > 0) hs = hs + v[c + BS - 1] - v[c - 1];
+                    if (c < ncol) *reinterpret_cast<uint32_t*>(out + c * colBytes) = NOPAD ? hs : ((hs & pad_and) | pad_or);
+                }
+            } else {
+                for (int jj = 0; jj < bs; jj++) hs += vrow[vsf(min(max(c_lo + jj, cmin), cmax))];
+                for (int c = 0; c < ncol; c++) {
+                    if (c > 0) hs = hs + vrow[vsf(min(max(c_lo + c + bs - 1, cmin), cmax))] - vrow[vsf(min(max(c_lo + c - 1, cmin), cmax))];
+                    *reinterpret_cast<uint32_t*>(out + c * colBytes) = NOPAD ? hs : ((hs & pad_and) | pad_or);
+                }
+            }
+        }
+        if (s + 1 < nsteps) stage(s + 1, buf ^ 1);
+        __syncthreads();
+    }
+}
+
 }  // namespace b200sgm

@@ -1,0 +1,16 @@
+// Stage launchers that live in their own translation units (so that a kernel change recompiles one file).
+#pragma once
+#include "sgm_types.h"
+
+namespace b200sgm {
+
+// A.2: Sobel-x + raw prefilter of both images (one launch).  stage_cost.cu
+void launch_prefilter(const uint8_t* dL, size_t lp, const uint8_t* dR, size_t rp, int W, int H, int ftzero, Feat* featL, Feat* featR,
+                      cudaStream_t st);
+
+// A.3 + A.4: Birchfield-Tomasi cost + block sum into the paired-layout volume C[H][W1][Dp].  `generic_only` forces the
+// validation kernel.  *launches is incremented per kernel launched; *errmsg is set for unsupported geometry.  stage_cost.cu
+cudaError_t launch_cost(const Feat* fl, const Feat* fr, uint16_t* C, const Eff& e, bool generic_only, int num_sms, cudaStream_t st,
+                        int* launches, const char** errmsg);
+
+}  // namespace b200sgm
