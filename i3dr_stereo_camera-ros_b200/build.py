@@ -34,17 +34,28 @@ def _stale(target: str, deps) -> bool:
     return any(os.path.getmtime(d) > t for d in deps)
 
 
+def _deps(src: str, seen=None):
+    """src plus every header it includes (quoted includes, resolved relative to the including file), transitively."""
+    import re
+    seen = set() if seen is None else seen
+    src = os.path.normpath(src)
+    if src in seen or not os.path.exists(src):
+        return seen
+    seen.add(src)
+    for inc in re.findall(r'^\s*#include\s+"([^"]+)"', open(src).read(), flags=re.M):
+        _deps(os.path.join(os.path.dirname(src), inc), seen)
+    return seen
+
+
 def build(force: bool = False, verbose: bool = False) -> str:
     """Compiles every csrc/*.cu to its own object (in parallel, only the stale ones) and links libb200sgm.so."""
     os.makedirs(OBJ, exist_ok=True)
-    headers = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".h", ".cuh"))]
-    headers.append(os.path.join(HERE, "..", "include", "b200sgm.h"))
     cflags = [f for f in FLAGS if f != "-shared"]
     procs, objs = [], []
     for src in sources():
         obj = os.path.join(OBJ, os.path.basename(src)[:-3] + ".o")
         objs.append(obj)
-        if force or _stale(obj, [src] + headers):
+        if force or _stale(obj, _deps(src)):
             cmd = [NVCC] + cflags + (["-Xptxas", "-v"] if verbose else []) + ["-c", "-o", obj, src]
             print("[b200sgm] " + " ".join(cmd), file=sys.stderr)
             procs.append((cmd, subprocess.Popen(cmd)))

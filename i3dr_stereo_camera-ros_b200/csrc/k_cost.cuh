@@ -331,14 +331,15 @@ __global__ void __launch_bounds__(256, RING8 ? 3 : 2) k_cost_fast(const Feat* __
 // registers), coalesced 128-byte stores of C[y][x1][k0 .. k0+64).
 // ------------------------------------------------------------------------------------------------
 constexpr int kC2TXH = 128;   // tile columns incl. halo
-constexpr int kC2NRH = 80;    // right-image records per parity (records 0 .. 158)
+constexpr int kC2NRH = 84;    // right-image records per parity (records 0 .. 158), padded so that the parity arrays are 16 banks apart
+constexpr int kC2LH = 68;     // left-image records per parity (64), same padding
 constexpr int kC2VS = 129;    // row stride of vs (odd: phase 2 reads one column of 32 pairs conflict-free)
 constexpr int kC2CPW = 16;    // output columns per warp in phase 2 (even, so f() of a window column is an immediate)
 
 inline size_t cost_tile2_smem(int SW2)
 {
     const int bs = 2 * SW2 + 1;
-    return size_t(2) * 2 * 2 * kC2NRH * sizeof(uint4) + size_t(2) * 2 * kC2TXH * sizeof(uint4) + size_t(kCfDCP) * kC2VS * 4 +
+    return size_t(2) * 2 * 2 * kC2NRH * sizeof(uint4) + size_t(2) * 2 * 2 * kC2LH * sizeof(uint4) + size_t(kCfDCP) * kC2VS * 4 +
            size_t(bs) * kCfDCP * (kC2TXH / 2) * 4;
 }
 
@@ -351,8 +352,8 @@ __global__ void __launch_bounds__(256, 2) k_cost_tile2(const Feat* __restrict__ 
     const int bs = 2 * SW2 + 1;
     const int TX = kC2TXH - 2 * SW2;
     uint4* Rrec = c2_smem;                                  // [2 buf][2 chan][2 parity][kC2NRH]
-    uint4* Lrec = Rrec + 2 * 2 * 2 * kC2NRH;                // [2 buf][2 chan][2 parity][64]
-    uint32_t* vs = reinterpret_cast<uint32_t*>(Lrec + 2 * 2 * kC2TXH);   // [32][kC2VS]
+    uint4* Lrec = Rrec + 2 * 2 * 2 * kC2NRH;                // [2 buf][2 chan][2 parity][kC2LH]
+    uint32_t* vs = reinterpret_cast<uint32_t*>(Lrec + 2 * 2 * 2 * kC2LH);   // [32][kC2VS]
     uint32_t* ring = vs + kCfDCP * kC2VS;                   // [bs][32][64]
 
     const int t = threadIdx.x, lane = t & 31, w = t >> 5;
@@ -370,28 +371,35 @@ __global__ void __launch_bounds__(256, 2) k_cost_tile2(const Feat* __restrict__ 
     for (int i = 0; i < 8; i++) { VA[i] = 0; VB[i] = 0; }
     for (int i = t; i < bs * kCfDCP * (kC2TXH / 2); i += 256) ring[i] = 0;
 
-    auto stage = [&](int s, int buf) {
+    // Staging of a row is split: the global loads are issued before phase 1 of the previous row and land in registers
+    // while it runs; the repacked records are written to the other buffer after phase 2.
+    Feat sa, sb, sl;
+    auto stage_load = [&](int s) {
         const int e = min(max(ya - SW2 + s, 0), g.H - 1);
-        if (t < 2 * kC2NRH) {
+        if (t < 160) {
             const int xr = xr_min + t;
-            const Feat a = __ldg(fr + size_t(e) * g.W + min(max(xr, 0), g.W - 1));
-            const Feat b = __ldg(fr + size_t(e) * g.W + min(max(xr - Dh, 0), g.W - 1));
+            sa = __ldg(fr + size_t(e) * g.W + min(max(xr, 0), g.W - 1));
+            sb = __ldg(fr + size_t(e) * g.W + min(max(xr - Dh, 0), g.W - 1));
+        }
+        if (t >= 128) sl = __ldg(fl + size_t(e) * g.W + min(max(xv0 + t - 128, 0), g.W - 1));
+    };
+    auto stage_store = [&](int buf) {
+        if (t < 160) {
             uint4* d = Rrec + ((buf * 2 + 0) * 2 + (t & 1)) * kC2NRH + (t >> 1);
             // (v, lo, -hi, -v) of the pixel pair (xr, xr - Dh), low half = xr
-            d[0] = make_uint4(__byte_perm(a.x, b.x, 0x5410), __byte_perm(a.x, b.x, 0x7632),
-                              __byte_perm(a.y, b.y, 0x5410), __byte_perm(a.y, b.y, 0x7632));
-            d[2 * kC2NRH] = make_uint4(__byte_perm(a.z, b.z, 0x5410), __byte_perm(a.z, b.z, 0x7632),
-                                       __byte_perm(a.w, b.w, 0x5410), __byte_perm(a.w, b.w, 0x7632));
+            d[0] = make_uint4(__byte_perm(sa.x, sb.x, 0x5410), __byte_perm(sa.x, sb.x, 0x7632),
+                              __byte_perm(sa.y, sb.y, 0x5410), __byte_perm(sa.y, sb.y, 0x7632));
+            d[2 * kC2NRH] = make_uint4(__byte_perm(sa.z, sb.z, 0x5410), __byte_perm(sa.z, sb.z, 0x7632),
+                                       __byte_perm(sa.w, sb.w, 0x5410), __byte_perm(sa.w, sb.w, 0x7632));
         }
         if (t >= 128) {
             const int c = t - 128;
-            const Feat a = __ldg(fl + size_t(e) * g.W + min(max(xv0 + c, 0), g.W - 1));
-            uint4* d = Lrec + ((buf * 2 + 0) * 2 + (c & 1)) * 64 + (c >> 1);
+            uint4* d = Lrec + ((buf * 2 + 0) * 2 + (c & 1)) * kC2LH + (c >> 1);
             // (u, -u, lo, -hi), each replicated in both halves
-            d[0] = make_uint4(__byte_perm(a.x, a.x, 0x1010), __byte_perm(a.y, a.y, 0x3232),
-                              __byte_perm(a.x, a.x, 0x3232), __byte_perm(a.y, a.y, 0x1010));
-            d[2 * 64] = make_uint4(__byte_perm(a.z, a.z, 0x1010), __byte_perm(a.w, a.w, 0x3232),
-                                   __byte_perm(a.z, a.z, 0x3232), __byte_perm(a.w, a.w, 0x1010));
+            d[0] = make_uint4(__byte_perm(sl.x, sl.x, 0x1010), __byte_perm(sl.y, sl.y, 0x3232),
+                              __byte_perm(sl.x, sl.x, 0x3232), __byte_perm(sl.y, sl.y, 0x1010));
+            d[2 * kC2LH] = make_uint4(__byte_perm(sl.z, sl.z, 0x1010), __byte_perm(sl.w, sl.w, 0x3232),
+                                      __byte_perm(sl.z, sl.z, 0x3232), __byte_perm(sl.w, sl.w, 0x1010));
         }
     };
     // Birchfield-Tomasi cost of one (left pixel, right pixel pair): sobel + (raw >> 2), 16x2
@@ -409,7 +417,9 @@ __global__ void __launch_bounds__(256, 2) k_cost_tile2(const Feat* __restrict__ 
         return cs + __byte_perm(cr, 0, 0x4341);   // + (cost_raw >> 2)
     };
 
-    stage(0, 0);
+    sa = sb = sl = make_uint4(0, 0, 0, 0);
+    stage_load(0);
+    stage_store(0);
     __syncthreads();
     const int nsteps = (yb - ya) + bs - 1;
     // phase-2 role
@@ -427,10 +437,11 @@ __global__ void __launch_bounds__(256, 2) k_cost_tile2(const Feat* __restrict__ 
     int slot = 0;
     for (int s = 0; s < nsteps; s++) {
         const int buf = s & 1;
+        if (s + 1 < nsteps) stage_load(s + 1);
         // ---- phase 1
         {
-            const uint4* Lb = Lrec + buf * 4 * 64 + m;
-            const uint4 lsA = Lb[0], lsB = Lb[64], lrA = Lb[128], lrB = Lb[192];
+            const uint4* Lb = Lrec + buf * 4 * kC2LH + m;
+            const uint4 lsA = Lb[0], lsB = Lb[kC2LH], lrA = Lb[2 * kC2LH], lrB = Lb[3 * kC2LH];
             uint32_t* rrow = ring + size_t(slot) * kCfDCP * 64 + p0 * 64 + m;
             slot = slot + 1 == bs ? 0 : slot + 1;
             // record of (column 2m, pair p): 2m + 31 - p; p even -> odd record m + 15 - p/2, p odd -> even record m + (31-p)/2
@@ -485,7 +496,7 @@ __global__ void __launch_bounds__(256, 2) k_cost_tile2(const Feat* __restrict__ 
                 }
             }
         }
-        if (s + 1 < nsteps) stage(s + 1, buf ^ 1);
+        if (s + 1 < nsteps) stage_store(buf ^ 1);
         __syncthreads();
     }
 }
