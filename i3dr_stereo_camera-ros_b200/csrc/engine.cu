@@ -379,30 +379,19 @@ int run_pipeline(b200sgm_engine* h, Lane& ln, const Eff& e, const uint8_t* dL, s
     }
     prof_mark(h, ln, 4, st);
     if (e.W1 > 0) {
-        WtaGeom wg{e.W, e.H, e.W1, e.minX1, e.minD, e.D, e.Dp, e.uniq, e.d12, e.INVALID};
-        dim3 block(256), grid2((e.W1 + 255) / 256, H);
-        k_lrcheck<<<grid2, block, 0, st>>>(ln.disp_wta, ln.disp2key, wg);
+        launch_lrcheck(ln.disp_wta, ln.disp2key, e, st);
         LAUNCH_CHECK(h);
     }
     prof_mark(h, ln, 5, st);
-    {
-        dim3 block(256), grid((W + 255) / 256, H);
-        k_median3<<<grid, block, 0, st>>>(ln.disp_wta, ln.disp_med, W, H);
-        LAUNCH_CHECK(h);
-    }
+    launch_median3(ln.disp_wta, ln.disp_med, W, H, st);
+    LAUNCH_CHECK(h);
     prof_mark(h, ln, 6, st);
     CUDA_TRY(h, cudaMemcpyAsync(ln.disp_out, ln.disp_med, size_t(npix) * 2, cudaMemcpyDeviceToDevice, st));
     if (e.speckleWin > 0) {
-        const int maxDiff = 16 * e.speckleRange;
-        k_speckle_runs<<<H, 256, 0, st>>>(ln.disp_out, ln.label, ln.parent, ln.runlen, ln.csize, W, e.INVALID, maxDiff);
-        LAUNCH_CHECK(h);
-        dim3 block(256), grid((W + 255) / 256, H);
-        k_speckle_vmerge<<<grid, block, 0, st>>>(ln.disp_out, ln.label, ln.parent, W, H, e.INVALID, maxDiff);
-        LAUNCH_CHECK(h);
-        k_speckle_size<<<(npix + 255) / 256, 256, 0, st>>>(ln.label, ln.parent, ln.runlen, ln.csize, npix);
-        LAUNCH_CHECK(h);
-        k_speckle_apply<<<(npix + 255) / 256, 256, 0, st>>>(ln.disp_out, ln.label, ln.parent, ln.csize, npix, e.INVALID, e.speckleWin);
-        LAUNCH_CHECK(h);
+        int nl = 0;
+        const cudaError_t ce = launch_speckle(ln.disp_out, ln.label, ln.parent, ln.runlen, ln.csize, e, st, &nl);
+        h->launches += nl;
+        if (ce != cudaSuccess) return fail(h, B200SGM_ECUDA, std::string("speckle filter launch: ") + cudaGetErrorString(ce));
     }
     prof_mark(h, ln, 7, st);
     if (h->profile && !ln.prof_events.empty()) { ln.prof_head = (ln.prof_head + 1) % kProfRing; ln.prof_count++; }

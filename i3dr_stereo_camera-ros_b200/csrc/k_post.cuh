@@ -6,7 +6,7 @@
 
 namespace b200sgm {
 
-__global__ void k_fill16(int16_t* __restrict__ p, int n, int16_t v)
+static __global__ void k_fill16(int16_t* __restrict__ p, int n, int16_t v)
 {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) p[i] = v;
@@ -15,7 +15,7 @@ __global__ void k_fill16(int16_t* __restrict__ p, int n, int16_t v)
 __device__ __forceinline__ void cswap(int& a, int& b) { int lo = min(a, b), hi = max(a, b); a = lo; b = hi; }
 
 // cv::medianBlur(disp, 3) on CV_16S (replicate border) -- always applied by StereoSGBM::compute.
-__global__ void k_median3(const int16_t* __restrict__ src, int16_t* __restrict__ dst, int W, int H)
+static __global__ void k_median3(const int16_t* __restrict__ src, int16_t* __restrict__ dst, int W, int H)
 {
     int x = blockIdx.x * blockDim.x + threadIdx.x;
     int y = blockIdx.y;
@@ -36,10 +36,16 @@ __global__ void k_median3(const int16_t* __restrict__ src, int16_t* __restrict__
 // ---- speckle filter: cv::filterSpeckles(disp, INVALID, maxSize, 16*range) --------------------------
 // Components are 4-connected sets of pixels != newVal where neighbours join iff |a-b| <= maxDiff;
 // components of size <= maxSize are overwritten with newVal (order independent).
-__device__ __forceinline__ int uf_find(const int* L, int i)
+__device__ __forceinline__ int uf_find(int* L, int i)
 {
     int p = __ldcg(L + i);  // L2 loads: other SMs re-parent nodes concurrently with atomics
-    while (p != i) { i = p; p = __ldcg(L + i); }
+    while (p != i) {
+        // path halving: a non-root never becomes a root again and its parent only ever moves to an ancestor of the
+        // same set (smaller index), so this plain store cannot disconnect anything it races with
+        const int gp = __ldcg(L + p);
+        if (gp != p) __stcg(L + i, gp);
+        i = p; p = gp;
+    }
     return i;
 }
 
@@ -63,7 +69,7 @@ __device__ __forceinline__ void uf_union(int* L, int a, int b)
 //   label[p]  : pixel index of the run start of p (or -1 for invalid pixels)
 //   parent[p] : union-find parent, meaningful at run starts only
 //   runlen[p] : run length, at run starts only;  csize[p]: component size, at roots only
-__global__ void __launch_bounds__(256) k_speckle_runs(const int16_t* __restrict__ img, int* __restrict__ label,
+static __global__ void __launch_bounds__(256) k_speckle_runs(const int16_t* __restrict__ img, int* __restrict__ label,
                                                       int* __restrict__ parent, int* __restrict__ runlen,
                                                       int* __restrict__ csize, int W, int newVal, int maxDiff)
 {
@@ -102,10 +108,9 @@ __global__ void __launch_bounds__(256) k_speckle_runs(const int16_t* __restrict_
         const bool start = valid && !(pv != newVal && abs(v - pv) <= maxDiff);
         if (start) cur = x;
         const int p = base + x;
-        csize[p] = 0;
         if (valid) {
             label[p] = base + cur;
-            if (start) parent[p] = p;
+            if (start) { parent[p] = p; csize[p] = 0; }   // component sizes are accumulated at roots, and roots are run starts
             const int nv = x + 1 < W ? int(row[x + 1]) : newVal;
             const bool ends = !(nv != newVal && abs(nv - v) <= maxDiff);
             if (ends) runlen[base + cur] = x - cur + 1;
@@ -116,7 +121,7 @@ __global__ void __launch_bounds__(256) k_speckle_runs(const int16_t* __restrict_
     }
 }
 
-__global__ void k_speckle_vmerge(const int16_t* __restrict__ img, const int* __restrict__ label, int* __restrict__ parent,
+static __global__ void k_speckle_vmerge(const int16_t* __restrict__ img, const int* __restrict__ label, int* __restrict__ parent,
                                  int W, int H, int newVal, int maxDiff)
 {
     const int x = blockIdx.x * blockDim.x + threadIdx.x;
@@ -132,27 +137,34 @@ __global__ void k_speckle_vmerge(const int16_t* __restrict__ img, const int* __r
     uf_union(parent, label[p], label[p + W]);
 }
 
-__global__ void k_speckle_size(const int* __restrict__ label, int* __restrict__ parent, const int* __restrict__ runlen,
-                               int* __restrict__ csize, int n)
+// csize only has to answer "size <= maxSize": once a root's count is past the threshold further runs skip the atomic,
+// which keeps the thousands of runs of a large surface from serialising on one address.
+static __global__ void k_speckle_size(const int* __restrict__ label, int* __restrict__ parent, const int* __restrict__ runlen,
+                               int* __restrict__ csize, int n, int maxSize)
 {
     const int p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= n || label[p] != p) return;   // run starts only
     const int r = uf_find(parent, p);
     parent[p] = r;                          // flatten (roots keep parent[r] == r)
-    atomicAdd(&csize[r], runlen[p]);
+    if (__ldcg(csize + r) <= maxSize) atomicAdd(&csize[r], runlen[p]);
 }
 
-__global__ void k_speckle_apply(int16_t* __restrict__ img, const int* __restrict__ label, const int* __restrict__ parent,
+static __global__ void k_speckle_apply(int16_t* __restrict__ img, const int* __restrict__ label, const int* __restrict__ parent,
                                 const int* __restrict__ csize, int n, int newVal, int maxSize)
 {
     const int p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= n) return;
     const int s = label[p];
-    if (s >= 0 && csize[parent[s]] <= maxSize) img[p] = int16_t(newVal);
+    if (s < 0) return;
+    // k_speckle_size left every run start one or two hops from its root (its own flattening store can be overtaken by a
+    // concurrent path-halving store, which still points at an ancestor)
+    int r = parent[s], q = parent[r];
+    while (q != r) { r = q; q = parent[r]; }
+    if (csize[r] <= maxSize) img[p] = int16_t(newVal);
 }
 
 // ---- a10: CV_16S -> CV_32F, value unchanged (matcherOpenCVSGBM.cpp:34, abstractStereoMatcher.cpp:49)
-__global__ void k_to_f32(const int16_t* __restrict__ src, float* __restrict__ dst, int n)
+static __global__ void k_to_f32(const int16_t* __restrict__ src, float* __restrict__ dst, int n)
 {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) dst[i] = float(src[i]);
@@ -181,7 +193,7 @@ __device__ __forceinline__ bool reproject_pixel(const ReprojGeom& g, int i, int 
 }
 
 // pass 1: dmat + depth + per-block kept count
-__global__ void __launch_bounds__(256) k_reproject_count(const int16_t* __restrict__ disp, ReprojGeom g,
+static __global__ void __launch_bounds__(256) k_reproject_count(const int16_t* __restrict__ disp, ReprojGeom g,
                                                          float* __restrict__ dmat, float* __restrict__ depth,
                                                          uint32_t* __restrict__ block_count)
 {
@@ -200,7 +212,7 @@ __global__ void __launch_bounds__(256) k_reproject_count(const int16_t* __restri
 }
 
 // pass 2: exclusive scan of the block counts (single CTA, sequential chunks of 1024)
-__global__ void __launch_bounds__(1024) k_scan_blocks(uint32_t* __restrict__ block_count, int nblocks, uint32_t* __restrict__ total)
+static __global__ void __launch_bounds__(1024) k_scan_blocks(uint32_t* __restrict__ block_count, int nblocks, uint32_t* __restrict__ total)
 {
     __shared__ uint32_t warp_sum[32];
     __shared__ uint32_t carry;
@@ -232,7 +244,7 @@ __global__ void __launch_bounds__(1024) k_scan_blocks(uint32_t* __restrict__ blo
 }
 
 // pass 3: write the kept points at block offset + rank within the block
-__global__ void __launch_bounds__(256) k_reproject_write(const int16_t* __restrict__ disp, const uint8_t* __restrict__ gray,
+static __global__ void __launch_bounds__(256) k_reproject_write(const int16_t* __restrict__ disp, const uint8_t* __restrict__ gray,
                                                          size_t gray_pitch, ReprojGeom g,
                                                          const uint32_t* __restrict__ block_offset, float4* __restrict__ pts)
 {

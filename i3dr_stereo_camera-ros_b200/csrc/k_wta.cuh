@@ -65,7 +65,7 @@ __device__ __forceinline__ int wta_pixel(const uint32_t (&S)[N], const uint16_t*
 
 // Stand-alone WTA over a materialised S volume: one warp per valid pixel.
 template <int N>
-__global__ void __launch_bounds__(256) k_wta(const uint16_t* __restrict__ Svol, WtaGeom g,
+static __global__ void __launch_bounds__(256) k_wta(const uint16_t* __restrict__ Svol, WtaGeom g,
                                              int16_t* __restrict__ disp, uint32_t* __restrict__ disp2key)
 {
     const int lane = threadIdx.x & 31;
@@ -84,7 +84,7 @@ __global__ void __launch_bounds__(256) k_wta(const uint16_t* __restrict__ Svol, 
 // A.7: a pixel survives unless BOTH the floor and the ceil candidate disagree with disp2 by more than
 // d12.  disp2 is reconstructed from the atomicMin key; an unassigned entry holds the SCALED invalid
 // value (minD-1)*16, which counts as a (failing) candidate when it is >= minD (OpenCV quirk, kept).
-__global__ void k_lrcheck(int16_t* __restrict__ disp, const uint32_t* __restrict__ disp2key, WtaGeom g)
+static __global__ void k_lrcheck(int16_t* __restrict__ disp, const uint32_t* __restrict__ disp2key, WtaGeom g)
 {
     int x = blockIdx.x * blockDim.x + threadIdx.x;
     int y = blockIdx.y;

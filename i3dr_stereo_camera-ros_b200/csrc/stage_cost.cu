@@ -11,7 +11,7 @@ namespace b200sgm {
 void launch_prefilter(const uint8_t* dL, size_t lp, const uint8_t* dR, size_t rp, int W, int H, int ftzero, Feat* featL, Feat* featR,
                       cudaStream_t st)
 {
-    dim3 block(256), grid((W + 255) / 256, H, 2);
+    dim3 block(128), grid((W + 128 * kPfPPT - 1) / (128 * kPfPPT), H, 2);
     k_prefilter<<<grid, block, 0, st>>>(dL, lp, dR, rp, W, H, ftzero, featL, featR);
 }
 

@@ -13,4 +13,9 @@ void launch_prefilter(const uint8_t* dL, size_t lp, const uint8_t* dR, size_t rp
 cudaError_t launch_cost(const Feat* fl, const Feat* fr, uint16_t* C, const Eff& e, bool generic_only, int num_sms, cudaStream_t st,
                         int* launches, const char** errmsg);
 
+// A.7 left-right check (in place on disp), A.8 3x3 median, A.8 speckle filter (in place on img).  stage_post.cu
+void launch_lrcheck(int16_t* disp, const uint32_t* disp2key, const Eff& e, cudaStream_t st);
+void launch_median3(const int16_t* src, int16_t* dst, int W, int H, cudaStream_t st);
+cudaError_t launch_speckle(int16_t* img, int* label, int* parent, int* runlen, int* csize, const Eff& e, cudaStream_t st, int* launches);
+
 }  // namespace b200sgm
