@@ -55,6 +55,9 @@ def build(force: bool = False, verbose: bool = False) -> str:
     for src in sources():
         obj = os.path.join(OBJ, os.path.basename(src)[:-3] + ".o")
         objs.append(obj)
+        only = os.environ.get("B200SGM_ONLY")   # development aid: rebuild just these translation units (comma separated)
+        if only and os.path.exists(obj) and os.path.basename(src)[:-3] not in only.split(","):
+            continue
         if force or _stale(obj, _deps(src)):
             cmd = [NVCC] + cflags + (["-Xptxas", "-v"] if verbose else []) + ["-c", "-o", obj, src]
             print("[b200sgm] " + " ".join(cmd), file=sys.stderr)

@@ -1,0 +1,159 @@
+// Host launchers of the aggregation stages (k_horiz + cooperative k_vert, or the generic per-direction kernels),
+// templated on N; instantiated once per N in agg_n*.cu so that the instantiations compile in parallel.
+#pragma once
+#include "engine_internal.h"
+#include "k_path.cuh"
+#include "k_wta.cuh"
+#include "k_fused.cuh"
+
+template <int N>
+int launch_paths_generic(b200sgm_engine* h, Lane& ln, const Eff& e, cudaStream_t st)
+{
+    static const int dirs_sgbm[5][2] = {{1, 0}, {1, 1}, {0, 1}, {-1, 1}, {-1, 0}};
+    static const int dirs_hh[8][2] = {{1, 0}, {1, 1}, {0, 1}, {-1, 1}, {-1, 0}, {-1, -1}, {0, -1}, {1, -1}};
+    const int nd = e.mode == B200SGM_MODE_HH ? 8 : 5;
+    for (int r = 0; r < nd; r++) {
+        PathGeom g;
+        g.W1 = e.W1; g.H = e.H; g.Dp = e.Dp;
+        g.dx = e.mode == B200SGM_MODE_HH ? dirs_hh[r][0] : dirs_sgbm[r][0];
+        g.dy = e.mode == B200SGM_MODE_HH ? dirs_hh[r][1] : dirs_sgbm[r][1];
+        g.nchains = chain_count(e.W1, e.H, g.dx, g.dy);
+        g.P1 = e.P1; g.P2 = e.P2;
+        const int wpb = 4;
+        dim3 grid((g.nchains + wpb - 1) / wpb), block(32 * wpb);
+        if (r == 0) k_path_generic<N, true><<<grid, block, 0, st>>>(ln.C, ln.S, g);
+        else k_path_generic<N, false><<<grid, block, 0, st>>>(ln.C, ln.S, g);
+        LAUNCH_CHECK(h);
+    }
+    WtaGeom wg{e.W, e.H, e.W1, e.minX1, e.minD, e.D, e.Dp, e.uniq, e.d12, e.INVALID};
+    const long long npix = (long long)e.W1 * e.H;
+    k_wta<N><<<unsigned((npix + 7) / 8), 256, 0, st>>>(ln.S, wg, ln.disp_wta, ln.disp2key);
+    LAUNCH_CHECK(h);
+    return B200SGM_OK;
+}
+
+// ---- fused path: k_horiz + cooperative k_vert ---------------------------------------------------------
+struct VertPlan { bool ok; int nstrips, twmax; size_t smem; };
+
+inline VertPlan plan_vert(const b200sgm_engine* h, const Eff& e)
+{
+    VertPlan p{false, 0, 0, 0};
+    if (e.W1 < 2) return p;
+    int n = std::min(h->num_sms, e.W1 / 2);
+    n = std::min(n, kMaxStrips);
+    int tw = (e.W1 + n - 1) / n;
+    if (tw > kVertMaxWarps) return p;      // wider than one co-resident wave of strips: use the hybrid path
+    p.nstrips = n; p.twmax = tw;
+    p.smem = vert_smem_bytes(tw, e.Dp);
+    p.ok = p.smem <= 200 * 1024;
+    return p;
+}
+
+template <int N, bool UP, bool DO_WTA, bool FULL, bool CLAMP_EACH>
+int launch_vert_t(b200sgm_engine* h, Lane& ln, const Eff& e, const VertPlan& vp, cudaStream_t st)
+{
+    VertGeom g;
+    g.w = WtaGeom{e.W, e.H, e.W1, e.minX1, e.minD, e.D, e.Dp, e.uniq, e.d12, e.INVALID};
+    g.nstrips = vp.nstrips; g.twmax = vp.twmax;
+    g.P1 = e.P1; g.P2 = e.P2;
+    g.spin_limit = (long long)h->clock_khz * 500;   // ~0.5 s of SM clock ticks
+    { static const int dbg = [] { const char* v = getenv("B200SGM_DEBUG_VERT"); return v ? atoi(v) : 0; }(); g.debug_flags = dbg; }
+    // two agent warps per CTA when they fit next to the column warps (1024 threads per CTA)
+    int nthreads = (DO_WTA ? 64 : 32) * vp.twmax;
+    { static const bool no_agents = getenv("B200SGM_NO_AGENTS") != nullptr; g.agents = (!no_agents && nthreads + 64 <= 1024) ? 1 : 0; }
+    if (g.agents) nthreads += 64;
+    auto kern = k_vert<N, UP, DO_WTA, FULL, CLAMP_EACH>;
+    CUDA_TRY(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(vp.smem)));
+    CUDA_TRY(h, cudaMemsetAsync(ln.xbuf, 0, size_t(2) * vp.nstrips * kXbufGen * (e.Dp / 2) * sizeof(uint2), st));
+    const uint16_t* Cp = ln.C; uint16_t* Sp = ln.S; int16_t* dp = ln.disp_wta; uint32_t* kp = ln.disp2key;
+    uint2* xb = ln.xbuf; int* er = ln.d_err;
+    void* args[] = {(void*)&Cp, (void*)&Sp, (void*)&g, (void*)&dp, (void*)&kp, (void*)&xb, (void*)&er};
+    {
+        std::lock_guard<std::mutex> lk(h->mu);
+        if (h->coop_prev[0]) CUDA_TRY(h, cudaStreamWaitEvent(st, h->coop_prev[0], 0));
+        CUDA_TRY(h, cudaLaunchCooperativeKernel((void*)kern, dim3(vp.nstrips), dim3(nthreads), args, vp.smem, st));
+        h->launches++;
+        cudaEvent_t ev = ln.coop_ev[ln.coop_idx];
+        ln.coop_idx ^= 1;
+        CUDA_TRY(h, cudaEventRecord(ev, st));
+        h->coop_prev[1] = h->coop_prev[0];
+        h->coop_prev[0] = ev;
+    }
+    return B200SGM_OK;
+}
+
+template <int N, bool UP, bool DO_WTA>
+int launch_vert(b200sgm_engine* h, Lane& ln, const Eff& e, const VertPlan& vp, cudaStream_t st)
+{
+    const bool full = e.Dp == e.D && e.D == 64 * N;
+    // worst-case cost of a cell: bs^2 * (2*ftzero + 63) (A.5 value bounds); one final clamp is enough when
+    // kMaxCost + 3 * (Cmax + P2) cannot wrap 16 bits
+    const long long bs = 2 * e.SW2 + 1;
+    const long long cmax = bs * bs * (2 * e.ftzero + 63) + e.P2;
+    // S_h arrives unclamped (<= 2*cmax) in MODE_SGBM / first sweep, clamped (<= kMaxCost) in the second sweep of MODE_HH
+    const bool clamp_each = kMaxCost + 3 * cmax > 65535 || 5 * cmax > 65535;
+    if (full) {
+        if (clamp_each) return launch_vert_t<N, UP, DO_WTA, true, true>(h, ln, e, vp, st);
+        return launch_vert_t<N, UP, DO_WTA, true, false>(h, ln, e, vp, st);
+    }
+    return launch_vert_t<N, UP, DO_WTA, false, true>(h, ln, e, vp, st);
+}
+
+template <int N>
+int launch_fused(b200sgm_engine* h, Lane& ln, const Eff& e, cudaStream_t st, bool hybrid)
+{
+    int wpb = 2;
+    while (wpb > 1 && size_t(wpb) * horiz_smem_per_warp(e.Dp) > 200 * 1024) wpb /= 2;
+    const size_t hsmem = size_t(wpb) * horiz_smem_per_warp(e.Dp);
+    if (hsmem > 200 * 1024) return fail(h, B200SGM_EINVAL, "numDisparities too large for the horizontal kernel");
+    {
+        const bool full = e.Dp == 64 * N;
+        const long long bs = 2 * e.SW2 + 1;
+        const bool clamp = !full || 2 * (bs * bs * (2 * e.ftzero + 63) + e.P2) > 65535;
+        auto kern = !full ? k_horiz<N, false, true> : (clamp ? k_horiz<N, true, true> : k_horiz<N, true, false>);
+        CUDA_TRY(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(hsmem)));
+        kern<<<(e.H + wpb - 1) / wpb, 32 * wpb, hsmem, st>>>(ln.C, ln.S, ln.ckpt, e.W1, e.H, e.Dp, e.P1, e.P2);
+        LAUNCH_CHECK(h);
+    }
+    prof_mark(h, ln, 3, st);
+    VertPlan vp = plan_vert(h, e);
+    if (hybrid || !vp.ok) {
+        static const int dirs_sgbm[3][2] = {{1, 1}, {0, 1}, {-1, 1}};
+        static const int dirs_hh[6][2] = {{1, 1}, {0, 1}, {-1, 1}, {-1, -1}, {0, -1}, {1, -1}};
+        const int nd = e.mode == B200SGM_MODE_HH ? 6 : 3;
+        for (int r = 0; r < nd; r++) {
+            PathGeom g;
+            g.W1 = e.W1; g.H = e.H; g.Dp = e.Dp;
+            g.dx = e.mode == B200SGM_MODE_HH ? dirs_hh[r][0] : dirs_sgbm[r][0];
+            g.dy = e.mode == B200SGM_MODE_HH ? dirs_hh[r][1] : dirs_sgbm[r][1];
+            g.nchains = chain_count(e.W1, e.H, g.dx, g.dy);
+            g.P1 = e.P1; g.P2 = e.P2;
+            k_path_generic<N, false><<<(g.nchains + 3) / 4, 128, 0, st>>>(ln.C, ln.S, g);
+            LAUNCH_CHECK(h);
+        }
+        WtaGeom wg{e.W, e.H, e.W1, e.minX1, e.minD, e.D, e.Dp, e.uniq, e.d12, e.INVALID};
+        const long long npix = (long long)e.W1 * e.H;
+        k_wta<N><<<unsigned((npix + 7) / 8), 256, 0, st>>>(ln.S, wg, ln.disp_wta, ln.disp2key);
+        LAUNCH_CHECK(h);
+        return B200SGM_OK;
+    }
+    int rc;
+    if (e.mode == B200SGM_MODE_HH) {
+        rc = launch_vert<N, false, false>(h, ln, e, vp, st);
+        if (rc) return rc;
+        rc = launch_vert<N, true, true>(h, ln, e, vp, st);
+    } else {
+        rc = launch_vert<N, false, true>(h, ln, e, vp, st);
+    }
+    if (rc) return rc;
+    CUDA_TRY(h, cudaMemcpyAsync(ln.h_err, ln.d_err, sizeof(int), cudaMemcpyDeviceToHost, st));
+    return B200SGM_OK;
+}
+
+template <int N>
+int launch_agg_n(b200sgm_engine* h, Lane& ln, const Eff& e, cudaStream_t st)
+{
+    if (h->path == 1) { prof_mark(h, ln, 3, st); return launch_paths_generic<N>(h, ln, e, st); }
+    return launch_fused<N>(h, ln, e, st, h->path == 2);
+}
+

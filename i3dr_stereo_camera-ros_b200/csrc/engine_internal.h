@@ -1,0 +1,109 @@
+// Internal host-side types of the engine shared by engine.cu and the per-N aggregation translation units.
+#pragma once
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <cmath>
+#include <string>
+#include <vector>
+#include <mutex>
+#include <atomic>
+
+#include "../../include/b200sgm.h"
+#include "sgm_types.h"
+#include "stages.h"
+
+
+using namespace b200sgm;
+
+struct Lane {
+    cudaStream_t stream = nullptr;
+    cudaEvent_t done = nullptr;
+    bool busy = false;
+    // device buffers
+    uint8_t *left = nullptr, *right = nullptr;      // W x H, pitch = W
+    Feat *feat_l = nullptr, *feat_r = nullptr;      // W x H
+    uint16_t *C = nullptr, *S = nullptr;            // [H][W1][Dp], paired layout (k_path.cuh)
+    uint16_t *ckpt = nullptr;                       // k_horiz checkpoints [H][ceil(W1/kHT)][Dp]
+    uint32_t* disp2key = nullptr;                   // W x H
+    int16_t *disp_wta = nullptr, *disp_med = nullptr, *disp_out = nullptr;  // W x H
+    int *label = nullptr, *csize = nullptr, *parent = nullptr, *runlen = nullptr;   // W x H (speckle filter)
+    float *f32a = nullptr, *f32b = nullptr;         // W x H (dmat / depth / CV_32F disparity)
+    float4* points = nullptr;                       // W x H
+    uint32_t *block_count = nullptr, *total = nullptr;
+    uint32_t* h_total = nullptr;                    // pinned
+    uint2* xbuf = nullptr;                          // k_vert exchange records (LL protocol)
+    int* d_err = nullptr;                           // device error word of the fused kernels
+    int* h_err = nullptr;                           // pinned copy
+    cudaEvent_t coop_ev[2] = {nullptr, nullptr};   // alternating: MODE_HH launches two sweeps per frame
+    int coop_idx = 0;
+    // stage profiling (b200sgm_profile): ring of event sets, harvested by b200sgm_stage_times
+    std::vector<cudaEvent_t> prof_events;           // kProfRing * (kStages + 1)
+    int prof_head = 0, prof_count = 0;
+    double stage_ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // >= kStages
+    std::vector<float> timeline;                    // (kStages+1) timestamps per harvested frame, ms since prof_ref
+    uint64_t stage_frames = 0;
+};
+
+constexpr int kStages = 7;    // prefilter, cost, horizontal, vertical+wta, lrcheck, median, speckle
+constexpr int kProfRing = 256;
+constexpr int kMaxStrips = 1024;
+constexpr int kVertMaxWarps = 16;
+
+
+struct b200sgm_engine {
+    int device = 0;
+    int maxW = 0, maxH = 0, maxD = 0;
+    std::vector<Lane> lanes;
+    b200sgm_params raw{};
+    bool have_params = false;
+    std::string err;
+    std::atomic<uint64_t> launches{0};
+    int path = 0;
+    bool profile = false;
+    cudaEvent_t prof_ref = nullptr;   // time origin of the stage timeline
+    int num_sms = 148;
+    // cooperative (k_vert) launches of all lanes: one sweep fills the register file of every SM (1024 threads x 64
+    // registers), and two partially resident sweeps would spin on CTAs that can never be scheduled -> serialise them
+    cudaEvent_t coop_prev[2] = {nullptr, nullptr};
+    int clock_khz = 1965000;
+    std::mutex mu;
+};
+
+
+#define CUDA_TRY(h, expr)                                                                      \
+    do {                                                                                       \
+        cudaError_t e__ = (expr);                                                              \
+        if (e__ != cudaSuccess) {                                                              \
+            (h)->err = std::string(#expr) + ": " + cudaGetErrorString(e__);                    \
+            return B200SGM_ECUDA;                                                              \
+        }                                                                                      \
+    } while (0)
+
+#define LAUNCH_CHECK(h)                                                                        \
+    do {                                                                                       \
+        (h)->launches++;                                                                       \
+        cudaError_t e__ = cudaGetLastError();                                                  \
+        if (e__ != cudaSuccess) {                                                              \
+            (h)->err = std::string("kernel launch at line ") + std::to_string(__LINE__) + ": " + cudaGetErrorString(e__); \
+            return B200SGM_ECUDA;                                                              \
+        }                                                                                      \
+    } while (0)
+
+// Stage profiling: records event `idx` of the current frame's event set (no-op unless profiling is on).
+inline void prof_mark(b200sgm_engine* h, Lane& ln, int idx, cudaStream_t st)
+{
+    if (!h->profile || ln.prof_events.empty()) return;
+    cudaEventRecord(ln.prof_events[size_t(ln.prof_head) * (kStages + 1) + idx], st);
+}
+
+inline int fail(b200sgm_engine* h, int code, const std::string& msg)
+{
+    h->err = msg;
+    return code;
+}
+
+
+// Aggregation + WTA stages for N packed registers per lane (D <= 64 * N); one explicit instantiation per agg_n*.cu.
+template <int N>
+int launch_agg_n(b200sgm_engine* h, Lane& ln, const Eff& e, cudaStream_t st);
