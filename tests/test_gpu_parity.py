@@ -45,6 +45,32 @@ def test_stage_dumps_match_oracle():
         eng.close()
 
 
+def test_cost_volume_fast_path_tile_geometry():
+    """Cost stage (A.2-A.4) of the default path against the oracle's C volume at sizes chosen for the tiled kernels:
+    W1 on either side of the 120/124-column tile width, a single-column image, several row segments, padded and
+    unpadded disparity counts, block sizes with and without unrolled instantiations, and a preFilterCap whose pixel
+    costs no longer fit a byte (falls back to the 32-bit ring kernel)."""
+    cases = [  # (W1, H, D, minD, blockSize, preFilterCap)
+        (120, 70, 64, 0, 9, 31), (121, 70, 64, 0, 9, 31), (119, 33, 64, 0, 9, 31), (241, 300, 64, 0, 9, 31),
+        (1, 20, 16, 0, 9, 31), (5, 20, 16, 3, 5, 31), (124, 40, 48, -8, 5, 63), (250, 150, 256, 0, 9, 31),
+        (130, 60, 32, 9, 3, 15), (140, 50, 64, 0, 15, 31), (126, 45, 128, 0, 21, 7), (100, 40, 64, 0, 9, 127),
+        (100, 40, 32, 0, 25, 31),
+    ]
+    for W1, H, D, minD, bs, cap in cases:
+        W = W1 + max(minD + D, 0) - min(minD, 0)
+        p = SGBMParams(minDisparity=minD, numDisparities=D, blockSize=bs, preFilterCap=cap)
+        assert p.w1(W) == W1
+        L, R = synth.make_pair(W, H, D, minD, 21 + W1)
+        want, st = oracle.compute(L, R, p, dumps=True)
+        eng = Engine(0, W, H, D, 1, p)
+        got = eng.compute(L, R)
+        C = eng.debug_volume("C", W, H)
+        eng.close()
+        assert np.array_equal(C, st["C"].view(np.uint16)), "C differs in %d cells for case %s" % (
+            (C != st["C"].view(np.uint16)).sum(), (W1, H, D, minD, bs, cap))
+        assert np.array_equal(got, want)
+
+
 def test_random_parameter_sweep_vs_oracle():
     rng = np.random.default_rng(99)
     n = 0

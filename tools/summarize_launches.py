@@ -31,9 +31,9 @@ for r in rows:
     elif name == "sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active":
         k["pipe_alu_pct"] = v
 ks = list(by_id.values())
-# last frame = from the last k_prefilter pair onward
+# last frame = from the last k_prefilter launch onward (one launch filters both images)
 idx = [i for i, k in enumerate(ks) if k["kernel"].startswith("k_prefilter")]
-start = idx[-2] if len(idx) >= 2 else 0
+start = idx[-1] if idx else 0
 ks = ks[start:]
 tot_t = sum(k.get("time_us", 0) for k in ks)
 for k in ks:
