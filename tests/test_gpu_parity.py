@@ -238,3 +238,34 @@ def test_reprojection_c5_style():
     assert np.array_equal(depth, wdepth)
     assert np.array_equal(pts.view(np.uint32), wpts.view(np.uint32))
     eng.close()
+
+
+def test_config_c5_full_size_reprojection(golden_crc):
+    """c5: c3 + processDisparity + reprojection at full size (2448x2048x256, SURVEY 8d camera).  The disparity is pinned by
+    the golden CRC; dmat, depth and the compacted XYZRGB list must equal the oracle's restatement of
+    generate_disparity.cpp:436-452 / disparity_to_depth.cpp:136-205 bit for bit (float32, tolerance 0)."""
+    import time
+    c = CONFIGS["c5"]
+    p = c.params
+    W, H = c.width, c.height
+    L, R = synth.make_pair(W, H, p.numDisparities, 0, 1000)
+    cam = b200sgm.C5_CAMERA
+    q = oracle.calc_q(cam["fx"], cam["cx"], cam["cx"], cam["cy"], cam["p14"])
+    fT = np.float32(0.3 * 2400.0)
+    depth_min, depth_max = cam["depth_min"], cam["depth_max"]
+    min_disp = float(fT / np.float32(depth_max))
+    max_disp = float("inf") if depth_min == 0 else float(fT / np.float32(depth_min))
+    eng = Engine(0, W, H, p.numDisparities, 1, p)
+    eng.compute_xyz(L, R, q, depth_min, depth_max, min_disp, max_disp)           # warm-up
+    t0 = time.perf_counter()
+    disp, dmat, depth, pts, n = eng.compute_xyz(L, R, q, depth_min, depth_max, min_disp, max_disp)
+    dt = time.perf_counter() - t0
+    eng.close()
+    assert synth.crc32(disp) == golden_crc["c3"]["disp"]
+    wdm = oracle.process_disparity(disp, min_disp, max_disp)
+    assert np.array_equal(dmat, wdm)
+    wdepth, wpts = oracle.reproject(wdm, L, q, depth_min, depth_max)
+    assert n == wpts.shape[0] and n > 100000
+    assert np.array_equal(depth, wdepth)
+    assert np.array_equal(pts.view(np.uint32), wpts.view(np.uint32))
+    print("c5 end to end (pageable host buffers, %d points): %.1f ms" % (n, dt * 1e3))
