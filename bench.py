@@ -369,6 +369,32 @@ def run_b200(args, cfg):
             "stage_ms_per_frame": stages, "single_lane_fps": 1.0 / frame_s,
         }
 
+    # ---- row N2: rectification of both images in front of the matcher, device-resident (rank 0)
+    rect = None
+    if rank == 0:
+        try:
+            for cam in (0, 1):
+                eng.set_camera(cam, *synth.sample_camera(W, H, 7 + 2 * cam, 1.0))
+            rL, rR = torch.empty_like(devL[0]), torch.empty_like(devR[0])
+            ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+            nrep = 20
+            for rep in range(nrep + 3):
+                if rep == 3:
+                    ev[0].record(streams[0])
+                i = rep % NF
+                eng.rectify_device(0, 0, devL[i].data_ptr(), W, W, H, rL.data_ptr(), W, stream=streams[0].cuda_stream)
+                eng.rectify_device(0, 1, devR[i].data_ptr(), W, W, H, rR.data_ptr(), W, stream=streams[0].cuda_stream)
+            ev[1].record(streams[0])
+            streams[0].synchronize()
+            ms_pair = ev[0].elapsed_time(ev[1]) / nrep
+            by = 2 * W * H * (1 + 1 + 8)          # source + rectified image + fixed-point map entry per pixel, both cameras
+            rect = {"kernel": "k_remap_cubic (x2)", "ms_per_pair": ms_pair, "algorithmic_bytes_per_pair": by,
+                    "gbs": by / (ms_pair * 1e-3) / 1e9, "frac_of_hbm_peak": by / (ms_pair * 1e-3) / 1e9 / hbm_peak,
+                    "note": "cv::initUndistortRectifyMap + cv::remap(INTER_CUBIC, BORDER_CONSTANT) of generate_disparity.cpp:370-386; "
+                            "maps built once per camera; not part of `value` (the matcher's metric)"}
+        except Exception as e:  # pragma: no cover
+            rect = {"error": str(e)}
+
     # ---- CPU baseline beside it (rank 0, N=1 only)
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -385,7 +411,7 @@ def run_b200(args, cfg):
             "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "u16", "data": "synthetic", "config": workload(cfg, NF, lanes),
             "gpix_disp_per_s": fps * cfg.gpix_disp, "parity_checked_vs_golden_crc": checked,
-            "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
+            "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu, "rectify": rect,
         }
         print(json.dumps(line), flush=True)
     eng.close()

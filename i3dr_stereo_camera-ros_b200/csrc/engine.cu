@@ -228,6 +228,8 @@ int b200sgm_destroy(b200sgm_handle h)
     if (!h) return B200SGM_EINVAL;
     cudaSetDevice(h->device);
     for (Lane& ln : h->lanes) { if (ln.stream) cudaStreamSynchronize(ln.stream); free_lane(ln); }
+    for (auto& r : h->rect) { cudaFree(r.ent); cudaFree(r.map1); cudaFree(r.map2); }
+    cudaFree(h->d_wtab); cudaFree(h->rect_src); cudaFree(h->rect_dst);
     delete h;
     return B200SGM_OK;
 }
@@ -384,6 +386,91 @@ int b200sgm_compute_xyz(b200sgm_handle h, const uint8_t* left, size_t left_strid
 }
 
 const char* b200sgm_last_error(b200sgm_handle h) { return h ? h->err.c_str() : "null handle"; }
+
+// ---- rectification (row N2): generate_disparity.cpp:370-386 ------------------------------------------------------------
+int b200sgm_set_camera(b200sgm_handle h, int cam, const double* K, const double* D, int nD, const double* R, const double* P)
+{
+    if (!h) return B200SGM_EINVAL;
+    if (cam < 0 || cam > 1 || !K || !P || nD < 0 || nD > 14 || (nD > 0 && !D)) return fail(h, B200SGM_EINVAL, "bad camera arguments");
+    RectifyCam c;
+    if (!make_rectify_cam(K, D, nD, R, P, c)) return fail(h, B200SGM_EINVAL, "singular P*R or tilted sensor model (tauX/tauY) unsupported");
+    h->rect[cam].cam = c; h->rect[cam].have = true; h->rect[cam].dirty = true;
+    return B200SGM_OK;
+}
+
+namespace {
+int ensure_maps(b200sgm_engine* h, int cam, int w, int hgt, bool want_float, cudaStream_t st)
+{
+    if (cam < 0 || cam > 1) return fail(h, B200SGM_EINVAL, "camera index must be 0 or 1");
+    auto& r = h->rect[cam];
+    if (!r.have) return fail(h, B200SGM_ESTATE, "b200sgm_set_camera has not been called for this camera");
+    if (w <= 0 || hgt <= 0) return fail(h, B200SGM_EINVAL, "empty image");
+    if (w > h->maxW || hgt > h->maxH) return fail(h, B200SGM_ESIZE, "image exceeds the engine's max size");
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    if (!h->d_wtab) {
+        std::vector<int16_t> tab(1024 * 16);
+        build_cubic_table(tab.data());
+        CUDA_TRY(h, cudaMalloc(&h->d_wtab, tab.size() * sizeof(int16_t)));
+        CUDA_TRY(h, cudaMemcpy(h->d_wtab, tab.data(), tab.size() * sizeof(int16_t), cudaMemcpyHostToDevice));
+    }
+    const size_t cap = size_t(h->maxW) * h->maxH;
+    if (!r.ent) CUDA_TRY(h, cudaMalloc(&r.ent, cap * sizeof(RemapEntry)));
+    if (want_float && !r.map1) {
+        CUDA_TRY(h, cudaMalloc(&r.map1, cap * sizeof(float)));
+        CUDA_TRY(h, cudaMalloc(&r.map2, cap * sizeof(float)));
+        r.dirty = true;
+    }
+    if (r.dirty || r.W != w || r.H != hgt) {
+        launch_rectify_maps(r.cam, w, hgt, r.ent, r.map1, r.map2, st);
+        LAUNCH_CHECK(h);
+        r.W = w; r.H = hgt; r.dirty = false;
+    }
+    return B200SGM_OK;
+}
+}  // namespace
+
+int b200sgm_rectify_device(b200sgm_handle h, int lane, int cam, const uint8_t* d_src, size_t src_stride, int width, int height,
+                           uint8_t* d_dst, size_t dst_stride, void* cuda_stream)
+{
+    if (!h) return B200SGM_EINVAL;
+    if (int rc = lane_check(h, lane)) return rc;
+    if (!d_src || !d_dst || src_stride < size_t(width) || dst_stride < size_t(width)) return fail(h, B200SGM_EINVAL, "bad image arguments");
+    cudaStream_t st = cuda_stream ? cudaStream_t(cuda_stream) : h->lanes[lane].stream;
+    if (int rc = ensure_maps(h, cam, width, height, false, st)) return rc;
+    launch_remap_cubic(d_src, src_stride, width, height, h->rect[cam].ent, h->d_wtab, d_dst, dst_stride, width, height, st);
+    LAUNCH_CHECK(h);
+    return B200SGM_OK;
+}
+
+int b200sgm_rectify(b200sgm_handle h, int cam, const uint8_t* src, size_t src_stride, int width, int height, uint8_t* dst,
+                    size_t dst_stride)
+{
+    if (!h) return B200SGM_EINVAL;
+    if (!src || !dst || src_stride < size_t(width) || dst_stride < size_t(width)) return fail(h, B200SGM_EINVAL, "bad image arguments");
+    if (width <= 0 || height <= 0) return fail(h, B200SGM_EINVAL, "empty image");
+    if (width > h->maxW || height > h->maxH) return fail(h, B200SGM_ESIZE, "image exceeds the engine's max size");
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    const size_t cap = size_t(h->maxW) * h->maxH;
+    if (!h->rect_src) { CUDA_TRY(h, cudaMalloc(&h->rect_src, cap)); CUDA_TRY(h, cudaMalloc(&h->rect_dst, cap)); }
+    cudaStream_t st = h->lanes[0].stream;
+    CUDA_TRY(h, cudaMemcpy2DAsync(h->rect_src, width, src, src_stride, width, height, cudaMemcpyHostToDevice, st));
+    if (int rc = b200sgm_rectify_device(h, 0, cam, h->rect_src, width, width, height, h->rect_dst, width, st)) return rc;
+    CUDA_TRY(h, cudaMemcpy2DAsync(dst, dst_stride, h->rect_dst, width, width, height, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(h, cudaStreamSynchronize(st));
+    return B200SGM_OK;
+}
+
+int b200sgm_rectify_maps(b200sgm_handle h, int cam, int width, int height, float* map1, float* map2)
+{
+    if (!h || !map1 || !map2) return B200SGM_EINVAL;
+    cudaStream_t st = h->lanes[0].stream;
+    if (int rc = ensure_maps(h, cam, width, height, true, st)) return rc;
+    const size_t bytes = size_t(width) * height * sizeof(float);
+    CUDA_TRY(h, cudaMemcpyAsync(map1, h->rect[cam].map1, bytes, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(h, cudaMemcpyAsync(map2, h->rect[cam].map2, bytes, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(h, cudaStreamSynchronize(st));
+    return B200SGM_OK;
+}
 
 int b200sgm_launch_count(b200sgm_handle h, uint64_t* count)
 {

@@ -68,6 +68,16 @@ struct b200sgm_engine {
     cudaEvent_t coop_prev[2] = {nullptr, nullptr};
     int clock_khz = 1965000;
     std::mutex mu;
+    // rectification (row N2): per camera (0 left, 1 right) the model and the cached fixed-point maps
+    struct Rect {
+        bool have = false, dirty = true;
+        RectifyCam cam;
+        int W = 0, H = 0;
+        RemapEntry* ent = nullptr;
+        float *map1 = nullptr, *map2 = nullptr;
+    } rect[2];
+    int16_t* d_wtab = nullptr;                    // cv::remap's bicubic weight table [1024][16]
+    uint8_t *rect_src = nullptr, *rect_dst = nullptr;   // staging for the host-pointer call (maxW x maxH)
 };
 
 

@@ -33,4 +33,19 @@ struct Eff {
 //   z = raw64 | raw64_lo << 16    w = (-raw64_hi) | (-raw64) << 16
 typedef uint4 Feat;
 
+// Inverse of (P[:, :3] * R) and the distortion model of cv::initUndistortRectifyMap (no tilt: tauX = tauY = 0).
+struct RectifyCam {
+    double ir[9];
+    double fx, fy, u0, v0;
+    double k1, k2, p1, p2, k3, k4, k5, k6, s1, s2, s3, s4;
+};
+
+// One map entry: source position in 1/32 pixel units split like cv::remap does: integer part (minus the one-pixel
+// offset of the 4x4 footprint, saturated to int16 first) and the index of the weight set.
+struct RemapEntry {
+    int16_t x, y;      // top-left tap of the 4x4 footprint
+    uint16_t frac;     // (fy << 5) | fx, index into the 1024 x 16 weight table
+    uint16_t pad;
+};
+
 }  // namespace b200sgm

@@ -18,4 +18,11 @@ void launch_lrcheck(int16_t* disp, const uint32_t* disp2key, const Eff& e, cudaS
 void launch_median3(const int16_t* src, int16_t* dst, int W, int H, cudaStream_t st);
 cudaError_t launch_speckle(int16_t* img, int* label, int* parent, int* runlen, int* csize, const Eff& e, cudaStream_t st, int* launches);
 
+// Rectification (row N2): cv::initUndistortRectifyMap + cv::remap(INTER_CUBIC, BORDER_CONSTANT).  rectify.cu
+void build_cubic_table(int16_t* tab /* [1024][16] */);
+bool make_rectify_cam(const double* K, const double* D, int nD, const double* R, const double* P, RectifyCam& c);
+void launch_rectify_maps(const RectifyCam& c, int W, int H, RemapEntry* ent, float* map1, float* map2, cudaStream_t st);
+void launch_remap_cubic(const uint8_t* src, size_t spitch, int SW, int SH, const RemapEntry* ent, const int16_t* wtab, uint8_t* dst,
+                        size_t dpitch, int W, int H, cudaStream_t st);
+
 }  // namespace b200sgm

@@ -21,6 +21,7 @@ SYMBOLS = (
     "b200sgm_compute_f32", "b200sgm_compute_device", "b200sgm_enqueue", "b200sgm_wait", "b200sgm_compute_xyz",
     "b200sgm_last_error", "b200sgm_version", "b200sgm_launch_count", "b200sgm_lane_stream", "b200sgm_debug_read",
     "b200sgm_debug_set_path", "b200sgm_profile", "b200sgm_stage_times", "b200sgm_alu_peak", "b200sgm_stage_timeline",
+    "b200sgm_set_camera", "b200sgm_rectify", "b200sgm_rectify_device", "b200sgm_rectify_maps",
 )
 
 STAGES = ("prefilter", "cost", "horizontal", "vertical_wta", "lrcheck", "median", "speckle")
@@ -140,6 +141,38 @@ class Engine:
             dmat.ctypes.data_as(ctypes.c_void_p), depth.ctypes.data_as(ctypes.c_void_p),
             pts.ctypes.data_as(ctypes.c_void_p) if pts is not None else None, ctypes.byref(cnt)))
         return disp, dmat, depth, (pts[:cnt.value] if pts is not None else None), cnt.value
+
+    # ---- rectification (row N2): cv::initUndistortRectifyMap + cv::remap(INTER_CUBIC, BORDER_CONSTANT) ----
+    def set_camera(self, cam, K, D, R, P):
+        K = np.ascontiguousarray(K, np.float64).reshape(9)
+        D = np.ascontiguousarray(D if D is not None else [], np.float64).ravel()
+        P = np.ascontiguousarray(P, np.float64).reshape(12)
+        Rp = None
+        if R is not None:
+            R = np.ascontiguousarray(R, np.float64).reshape(9)
+            Rp = R.ctypes.data_as(ctypes.c_void_p)
+        self._check(self.lib.b200sgm_set_camera(self.h, int(cam), K.ctypes.data_as(ctypes.c_void_p),
+                                                D.ctypes.data_as(ctypes.c_void_p) if D.size else None, int(D.size), Rp,
+                                                P.ctypes.data_as(ctypes.c_void_p)))
+
+    def rectify(self, cam, image) -> np.ndarray:
+        a = _u8(image)
+        H, W = a.shape
+        out = np.empty((H, W), np.uint8)
+        self._check(self.lib.b200sgm_rectify(self.h, int(cam), a.ctypes.data_as(ctypes.c_void_p), ctypes.c_size_t(a.strides[0]), W, H,
+                                             out.ctypes.data_as(ctypes.c_void_p), ctypes.c_size_t(W)))
+        return out
+
+    def rectify_device(self, lane, cam, sptr, sstride, W, H, dptr, dstride, stream=0):
+        self._check(self.lib.b200sgm_rectify_device(self.h, int(lane), int(cam), ctypes.c_void_p(sptr), ctypes.c_size_t(sstride), int(W),
+                                                    int(H), ctypes.c_void_p(dptr), ctypes.c_size_t(dstride), ctypes.c_void_p(stream)))
+
+    def rectify_maps(self, cam, W, H):
+        m1 = np.empty((H, W), np.float32)
+        m2 = np.empty((H, W), np.float32)
+        self._check(self.lib.b200sgm_rectify_maps(self.h, int(cam), int(W), int(H), m1.ctypes.data_as(ctypes.c_void_p),
+                                                  m2.ctypes.data_as(ctypes.c_void_p)))
+        return m1, m2
 
     # ---- streaming with host buffers (pinned for true overlap) ----
     def enqueue(self, lane, left, right, disp_out):

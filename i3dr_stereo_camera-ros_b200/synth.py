@@ -34,3 +34,20 @@ def make_pair(width: int, height: int, num_disp: int, min_disp: int = 0, seed: i
 
 def crc32(a: np.ndarray) -> str:
     return "%08x" % (zlib.crc32(np.ascontiguousarray(a).tobytes()) & 0xFFFFFFFF)
+
+
+def sample_camera(width: int, height: int, seed: int = 0, strength: float = 1.0):
+    """A plausible calibrated camera (K, D, R, P) for the rectification tests and bench: focal ~ width, mild plumb_bob distortion, small rotation."""
+    rng = np.random.default_rng(seed)
+    f = width * (0.9 + 0.2 * rng.random())
+    K = np.array([[f, 0, width / 2 + rng.uniform(-8, 8)], [0, f * (1 + rng.uniform(-0.002, 0.002)), height / 2 + rng.uniform(-8, 8)], [0, 0, 1]])
+    D = strength * np.array([rng.uniform(-0.25, 0.05), rng.uniform(-0.05, 0.15), rng.uniform(-1e-3, 1e-3), rng.uniform(-1e-3, 1e-3),
+                             rng.uniform(-0.05, 0.05)])
+    rv = strength * rng.uniform(-0.01, 0.01, 3)
+    th = float(np.linalg.norm(rv))
+    kx = rv / th if th > 0 else np.zeros(3)
+    Kx = np.array([[0, -kx[2], kx[1]], [kx[2], 0, -kx[0]], [-kx[1], kx[0], 0]])
+    R = np.eye(3) + np.sin(th) * Kx + (1 - np.cos(th)) * (Kx @ Kx)
+    fn = f * (1 + rng.uniform(-0.01, 0.01))
+    P = np.array([[fn, 0, width / 2, -fn * 0.3 * (seed & 1)], [0, fn, height / 2, 0], [0, 0, 1, 0]])
+    return K, D, R, P

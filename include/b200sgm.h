@@ -120,6 +120,27 @@ int b200sgm_compute_xyz(b200sgm_handle h, const uint8_t *left, size_t left_strid
                         int16_t *disp, size_t disp_stride, float *dmat, float *depth,
                         b200sgm_point *points, uint32_t *count);
 
+/* ---- the step before the path (row N2 of SURVEY.md section 8f): rectification ---------------------------------- */
+
+/* Replaces rectify() of generate_disparity.cpp:370-386 (and rectify.cpp:111-127):
+ *   cv::initUndistortRectifyMap(K, D, R, P, image.size(), CV_32FC1, map1, map2);
+ *   cv::remap(image, image_rect, map1, map2, cv::INTER_CUBIC, cv::BORDER_CONSTANT);
+ * The reference rebuilds the maps for every frame; here b200sgm_set_camera installs the CameraInfo of camera
+ * `cam` (0 = left, 1 = right) and the maps are built on the device once per (camera, image size).
+ * K, R: 3x3 row-major (R may be NULL = identity); D: nD <= 12 distortion coefficients in OpenCV order
+ * (k1 k2 p1 p2 k3 k4 k5 k6 s1 s2 s3 s4; a non-zero tilt tauX/tauY is rejected); P: 3x4 row-major. */
+int b200sgm_set_camera(b200sgm_handle h, int cam, const double *K, const double *D, int nD, const double *R,
+                       const double *P);
+/* CV_8UC1 host image in, rectified CV_8UC1 host image out (same size), synchronous.  Bit-exact with cv::remap. */
+int b200sgm_rectify(b200sgm_handle h, int cam, const uint8_t *src, size_t src_stride, int width, int height,
+                    uint8_t *dst, size_t dst_stride);
+/* Device-resident variant, enqueued on `cuda_stream` (or the stream of lane `lane` when NULL), not synchronised:
+ * rectify straight into the buffers handed to b200sgm_compute_device. */
+int b200sgm_rectify_device(b200sgm_handle h, int lane, int cam, const uint8_t *d_src, size_t src_stride, int width,
+                           int height, uint8_t *d_dst, size_t dst_stride, void *cuda_stream);
+/* The CV_32FC1 maps of cv::initUndistortRectifyMap for `cam` at this size, copied to the host (H x W, tight). */
+int b200sgm_rectify_maps(b200sgm_handle h, int cam, int width, int height, float *map1, float *map2);
+
 /* ---- diagnostics ------------------------------------------------------------------------------------------ */
 
 const char *b200sgm_last_error(b200sgm_handle h);
