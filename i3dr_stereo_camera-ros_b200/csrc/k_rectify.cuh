@@ -53,15 +53,10 @@ static __global__ void k_rectify_maps(RectifyCam c, int W, int H, RemapEntry* __
     ent[p] = e;
 }
 
-// cv::remap(..., INTER_CUBIC, BORDER_CONSTANT, 0) on CV_8UC1: 4x4 taps, int16 weights summing to 2^15, taps outside the
-// source contribute 0, result = saturate_u8((sum + 2^14) >> 15).  wtab: [1024][16] int16 (host-built, rectify.cu).
-static __global__ void __launch_bounds__(256) k_remap_cubic(const uint8_t* __restrict__ src, size_t spitch, int SW, int SH,
-                                                           const RemapEntry* __restrict__ ent, const int16_t* __restrict__ wtab,
-                                                           uint8_t* __restrict__ dst, size_t dpitch, int W, int H)
+// One output pixel (device helper): entry -> weights -> 16 taps.
+__device__ __forceinline__ uint8_t remap_cubic_pixel(const uint8_t* __restrict__ src, size_t spitch, int SW, int SH, RemapEntry e,
+                                                     const int16_t* __restrict__ wtab)
 {
-    const int j = blockIdx.x * blockDim.x + threadIdx.x, i = blockIdx.y;
-    if (j >= W || i >= H) return;
-    const RemapEntry e = ent[size_t(i) * W + j];
     const int sx = int(e.x) - 1, sy = int(e.y) - 1;
     const uint4* wp = reinterpret_cast<const uint4*>(wtab + size_t(e.frac) * 16);
     const uint4 w0 = __ldg(wp), w1 = __ldg(wp + 1);
@@ -79,16 +74,6 @@ static __global__ void __launch_bounds__(256) k_remap_cubic(const uint8_t* __res
             asm("dp2a.lo.s32.u32 %0, %1, %2, %0;" : "+r"(sum) : "r"(wv[a * 2]), "r"(px));
             asm("dp2a.hi.s32.u32 %0, %1, %2, %0;" : "+r"(sum) : "r"(wv[a * 2 + 1]), "r"(px));
         }
-    } else if (unsigned(sx) < unsigned(max(SW - 3, 0)) && unsigned(sy) < unsigned(max(SH - 3, 0))) {
-#pragma unroll
-        for (int a = 0; a < 4; a++) {
-            const uint8_t* s = src + size_t(sy + a) * spitch + sx;
-#pragma unroll
-            for (int b = 0; b < 4; b++) {
-                const int wt = int(int16_t((b & 1) ? (wv[a * 2 + b / 2] >> 16) : (wv[a * 2 + b / 2] & 0xFFFFu)));
-                sum += int(s[b]) * wt;
-            }
-        }
     } else {
 #pragma unroll
         for (int a = 0; a < 4; a++) {
@@ -104,7 +89,35 @@ static __global__ void __launch_bounds__(256) k_remap_cubic(const uint8_t* __res
         }
     }
     const int r = (sum + (1 << 14)) >> 15;
-    dst[size_t(i) * dpitch + j] = uint8_t(min(max(r, 0), 255));
+    return uint8_t(min(max(r, 0), 255));
+}
+
+// cv::remap(..., INTER_CUBIC, BORDER_CONSTANT, 0) on CV_8UC1: 4x4 taps, int16 weights summing to 2^15, taps outside the
+// source contribute 0, result = saturate_u8((sum + 2^14) >> 15).  wtab: [1024][16] int16 (host-built, rectify.cu).
+// A thread produces kRmPPT pixels 256 columns apart (coalesced entry loads and stores per instruction, kRmPPT independent
+// entry -> gather chains in flight).
+constexpr int kRmPPT = 4;
+static __global__ void __launch_bounds__(256) k_remap_cubic(const uint8_t* __restrict__ src, size_t spitch, int SW, int SH,
+                                                           const RemapEntry* __restrict__ ent, const int16_t* __restrict__ wtab,
+                                                           uint8_t* __restrict__ dst, size_t dpitch, int W, int H)
+{
+    const int j0 = blockIdx.x * (256 * kRmPPT) + threadIdx.x, i = blockIdx.y;
+    if (i >= H) return;
+    RemapEntry e[kRmPPT];
+#pragma unroll
+    for (int k = 0; k < kRmPPT; k++) {
+        const int j = j0 + 256 * k;
+        const uint2 raw = j < W ? __ldg(reinterpret_cast<const uint2*>(ent + size_t(i) * W + j)) : make_uint2(0u, 0u);
+        e[k].x = int16_t(raw.x & 0xFFFFu); e[k].y = int16_t(raw.x >> 16); e[k].frac = uint16_t(raw.y & 0xFFFFu); e[k].pad = 0;
+    }
+    uint8_t out[kRmPPT];
+#pragma unroll
+    for (int k = 0; k < kRmPPT; k++) out[k] = remap_cubic_pixel(src, spitch, SW, SH, e[k], wtab);
+#pragma unroll
+    for (int k = 0; k < kRmPPT; k++) {
+        const int j = j0 + 256 * k;
+        if (j < W) dst[size_t(i) * dpitch + j] = out[k];
+    }
 }
 
 }  // namespace b200sgm

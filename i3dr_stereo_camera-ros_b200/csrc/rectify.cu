@@ -83,7 +83,7 @@ void launch_rectify_maps(const RectifyCam& c, int W, int H, RemapEntry* ent, flo
 void launch_remap_cubic(const uint8_t* src, size_t spitch, int SW, int SH, const RemapEntry* ent, const int16_t* wtab, uint8_t* dst,
                         size_t dpitch, int W, int H, cudaStream_t st)
 {
-    dim3 block(256), grid((W + 255) / 256, H);
+    dim3 block(256), grid((W + 256 * kRmPPT - 1) / (256 * kRmPPT), H);
     k_remap_cubic<<<grid, block, 0, st>>>(src, spitch, SW, SH, ent, wtab, dst, dpitch, W, H);
 }
 
