@@ -295,7 +295,9 @@ __device__ __forceinline__ void wta_flush32(const WtaAcc& acc, int cnt, const Wt
     if (lane >= cnt) return;
     const int minS = int(acc.key >> 16), best = int(acc.key & 0xFFFFu);
     // uniqueness: S[k] * f < minS * 100  <=>  S[k] < ceil(minS*100 / f)
-    const uint32_t thr = min(__umulhi(uint32_t(minS * 100 + w.f - 1), w.umagic), 0xFFFFu);
+    // magic division by f = 100 - uniq (2 <= f <= 100); for f == 1 the magic constant does not fit 32 bits and the quotient is n itself
+    const uint32_t n100 = uint32_t(minS * 100 + w.f - 1);
+    const uint32_t thr = min(w.f == 1 ? n100 : __umulhi(n100, w.umagic), 0xFFFFu);
     const bool reject = (acc.mm & 0xFFFFu) < thr || minS >= kMaxCost;
     int dfix = best * 16;
     if (best > 0 && best < g.D - 1) {

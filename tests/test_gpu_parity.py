@@ -110,6 +110,24 @@ def test_edge_cases():
     assert np.array_equal(run_gpu(Lp[:, :150], R, q), oracle.compute(L, R, q))
 
 
+def test_uniqueness_ratio_extremes():
+    """uniquenessRatio 99 (f = 1: the magic-division constant of the threshold does not fit 32 bits), 100 and beyond
+    (f <= 0: exact per-cell comparison path), on textured, noisy and flat inputs."""
+    rng = np.random.default_rng(3)
+    for uniq in (99, 100, 150, 98, 1):
+        for kind in range(3):
+            W, H, D = 260, 70, 64
+            L, R = synth.make_pair(W, H, D, 0, 40 + kind)
+            if kind == 1:
+                L = rng.integers(0, 256, L.shape).astype(np.uint8); R = rng.integers(0, 256, R.shape).astype(np.uint8)
+            elif kind == 2:
+                L = (L // 32 * 32).astype(np.uint8); R = (R // 32 * 32).astype(np.uint8)
+            for mode in (0, 1):
+                p = SGBMParams(numDisparities=D, uniquenessRatio=uniq, mode=mode, speckleWindowSize=0)
+                got, want = run_gpu(L, R, p), oracle.compute(L, R, p)
+                assert np.array_equal(got, want), "uniq %d kind %d mode %d: %d px differ" % (uniq, kind, mode, (got != want).sum())
+
+
 def test_error_behaviour():
     eng = Engine(0, 64, 64, 32, 1)
     L = np.zeros((64, 64), np.uint8)
