@@ -1,5 +1,5 @@
 """One-off randomized parity sweep of the CUDA path against the CPU oracle (larger and more varied than the test-suite's
-60 cases; run on a GPU box: python tools/fuzz_parity.py [cases] [seed])."""
+60 cases; run on a GPU box: python tools/fuzz_parity.py [cases] [seed] [wide])."""
 import os
 import sys
 import time
@@ -17,7 +17,10 @@ rng = np.random.default_rng(int(sys.argv[2]) if len(sys.argv) > 2 else 2024)
 bad = done = 0
 t0 = time.time()
 while done < n_cases:
-    W = int(rng.integers(40, 900)); H = int(rng.integers(8, 320))
+    if len(sys.argv) > 3 and sys.argv[3] == "wide":     # full-width strips (14-16 columns per vertical-sweep CTA), few rows
+        W = int(rng.integers(1500, 2600)); H = int(rng.integers(3, 48))
+    else:
+        W = int(rng.integers(40, 900)); H = int(rng.integers(8, 320))
     D = int(rng.choice([16, 32, 48, 8, 24, 40, 64, 80, 96, 112, 128, 144, 160, 192, 256, 272])); minD = int(rng.choice([-64, -8, 0, 0, 0, 1, 2, 9, -20, 30, 147]))
     if W - (D + abs(minD)) < 4:
         continue
