@@ -1,5 +1,5 @@
 """One-off randomized parity sweep of the CUDA path against the CPU oracle (larger and more varied than the test-suite's
-60 cases; run on a GPU box: python tools/fuzz_parity.py [cases] [seed] [wide])."""
+60 cases; run on a GPU box: python tools/fuzz_parity.py [cases] [seed] [wide|tall|full])."""
 import os
 import sys
 import time
@@ -17,7 +17,11 @@ rng = np.random.default_rng(int(sys.argv[2]) if len(sys.argv) > 2 else 2024)
 bad = done = 0
 t0 = time.time()
 while done < n_cases:
-    if len(sys.argv) > 3 and sys.argv[3] == "wide":     # full-width strips (14-16 columns per vertical-sweep CTA), few rows
+    if len(sys.argv) > 3 and sys.argv[3] == "full":     # Phobos resolution
+        W, H = 2448, 2048
+    elif len(sys.argv) > 3 and sys.argv[3] == "tall":
+        W = int(rng.integers(60, 400)); H = int(rng.integers(600, 2100))
+    elif len(sys.argv) > 3 and sys.argv[3] == "wide":     # full-width strips (14-16 columns per vertical-sweep CTA), few rows
         W = int(rng.integers(1500, 2600)); H = int(rng.integers(3, 48))
     else:
         W = int(rng.integers(40, 900)); H = int(rng.integers(8, 320))
