@@ -104,7 +104,7 @@ int run_pipeline(b200sgm_engine* h, Lane& ln, const Eff& e, const uint8_t* dL, s
         LAUNCH_CHECK(h);
     }
     CUDA_TRY(h, cudaMemsetAsync(ln.disp2key, 0xFF, size_t(npix) * 4, st));
-    k_fill16<<<(npix + 255) / 256, 256, 0, st>>>(ln.disp_wta, npix, int16_t(e.INVALID));
+    launch_fill16(ln.disp_wta, npix, int16_t(e.INVALID), st);
     LAUNCH_CHECK(h);
     prof_mark(h, ln, 1, st);
     if (e.W1 > 0) {
@@ -134,7 +134,7 @@ int run_pipeline(b200sgm_engine* h, Lane& ln, const Eff& e, const uint8_t* dL, s
     CUDA_TRY(h, cudaMemcpyAsync(ln.disp_out, ln.disp_med, size_t(npix) * 2, cudaMemcpyDeviceToDevice, st));
     if (e.speckleWin > 0) {
         int nl = 0;
-        const cudaError_t ce = launch_speckle(ln.disp_out, ln.label, ln.parent, ln.runlen, ln.csize, e, st, &nl);
+        const cudaError_t ce = launch_speckle(ln.disp_out, ln.label, ln.parent, ln.runlen, ln.csize, W, H, e.INVALID, e.speckleWin, 16 * e.speckleRange, st, &nl);
         h->launches += nl;
         if (ce != cudaSuccess) return fail(h, B200SGM_ECUDA, std::string("speckle filter launch: ") + cudaGetErrorString(ce));
     }
@@ -468,6 +468,41 @@ int b200sgm_rectify_maps(b200sgm_handle h, int cam, int width, int height, float
     const size_t bytes = size_t(width) * height * sizeof(float);
     CUDA_TRY(h, cudaMemcpyAsync(map1, h->rect[cam].map1, bytes, cudaMemcpyDeviceToHost, st));
     CUDA_TRY(h, cudaMemcpyAsync(map2, h->rect[cam].map2, bytes, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(h, cudaStreamSynchronize(st));
+    return B200SGM_OK;
+}
+
+// ---- StereoBM (row N4): matcherOpenCVBlock.cpp:13-20 ---------------------------------------------------------------------
+int b200sgm_bm_compute(b200sgm_handle h, const b200sgm_bm_params* bp, const uint8_t* left, size_t left_stride, const uint8_t* right,
+                       size_t right_stride, int width, int height, int16_t* disp, size_t disp_stride)
+{
+    if (!h || !bp || !left || !right || !disp) return B200SGM_EINVAL;
+    // cv::StereoBM's own argument checks (CV_Error -> forwardMatch() == -1 in the reference)
+    if (bp->numDisparities <= 0 || bp->numDisparities % 16 != 0) return fail(h, B200SGM_EINVAL, "numDisparities must be positive and divisible by 16");
+    if (bp->numDisparities > h->maxD) return fail(h, B200SGM_ESIZE, "numDisparities exceeds the engine's max_disparities");
+    if (width <= 0 || height <= 0) return fail(h, B200SGM_EINVAL, "empty image");
+    if (width > h->maxW || height > h->maxH) return fail(h, B200SGM_ESIZE, "image exceeds the engine's max size");
+    if (bp->blockSize < 5 || bp->blockSize > 255 || bp->blockSize % 2 == 0 || bp->blockSize >= std::min(width, height))
+        return fail(h, B200SGM_EINVAL, "blockSize must be odd, within 5..255 and smaller than the image width and height");
+    if (bp->preFilterCap < 1 || bp->preFilterCap > 63) return fail(h, B200SGM_EINVAL, "preFilterCap must be within 1..63");
+    if (bp->textureThreshold < 0 || bp->uniquenessRatio < 0) return fail(h, B200SGM_EINVAL, "textureThreshold and uniquenessRatio must be non-negative");
+    if (bp->disp12MaxDiff >= 0) return fail(h, B200SGM_EINVAL, "disp12MaxDiff >= 0 is not supported by the block matcher (the reference never sets it)");
+    if ((bp->minDisparity + bp->numDisparities) * 16 >= 32768 || (bp->minDisparity - 1) * 16 < -32768) return fail(h, B200SGM_EINVAL, "disparity range does not fit CV_16S x16");
+    if (left_stride < size_t(width) || right_stride < size_t(width) || disp_stride < size_t(width) * 2) return fail(h, B200SGM_EINVAL, "stride smaller than a row");
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    Lane& ln = h->lanes[0];
+    if (ln.busy) return fail(h, B200SGM_ESTATE, "lane 0 is busy: call b200sgm_wait first");
+    cudaStream_t st = ln.stream;
+    CUDA_TRY(h, cudaMemcpy2DAsync(ln.left, width, left, left_stride, width, height, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(h, cudaMemcpy2DAsync(ln.right, width, right, right_stride, width, height, cudaMemcpyHostToDevice, st));
+    BmParams p{bp->minDisparity, bp->numDisparities, bp->blockSize, bp->preFilterCap, bp->textureThreshold, bp->uniquenessRatio,
+               bp->speckleWindowSize, bp->speckleRange};
+    int nl = 0;
+    const cudaError_t ce = launch_bm(ln.left, width, ln.right, width, width, height, p, reinterpret_cast<uint8_t*>(ln.disp_wta), ln.C, ln.csize,
+                                     ln.disp_out, ln.label, ln.parent, ln.runlen, ln.csize, h->num_sms, st, &nl);
+    h->launches += nl;
+    if (ce != cudaSuccess) return fail(h, B200SGM_ECUDA, std::string("block matcher launch: ") + cudaGetErrorString(ce));
+    CUDA_TRY(h, cudaMemcpy2DAsync(disp, disp_stride, ln.disp_out, size_t(width) * 2, size_t(width) * 2, height, cudaMemcpyDeviceToHost, st));
     CUDA_TRY(h, cudaStreamSynchronize(st));
     return B200SGM_OK;
 }

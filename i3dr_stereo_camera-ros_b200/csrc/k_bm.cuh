@@ -1,0 +1,156 @@
+// Row N4 of SURVEY.md section 8(f): cv::StereoBM::compute as called by the reference's MatcherOpenCVBlock
+// (/root/reference/src/stereoMatcher/matcherOpenCVBlock.cpp:13-20; the package's default algorithm,
+// launch/stereo_matcher.launch:20).  Algorithm as restated and pinned in oracle/bm_oracle.py: PREFILTER_XSOBEL, SAD over a
+// blockSize x blockSize window with replicate-clamped columns and rows, texture threshold, uniqueness, x16 sub-pixel,
+// valid-ROI mask, speckle filter.  First version: correct and measured, with the horizontal SAD volume materialised in the
+// lane's cost-volume buffer (the SGBM kernels' C), not yet fused.
+#pragma once
+#include "sgm_types.h"
+
+namespace b200sgm {
+
+struct BmGeom {
+    int W, H, ndisp, mindisp, wsz, cap, tex, uniq;
+    int lofs, rofs, width1, FILTERED;
+};
+
+// prefilterXSobel; grid.z = 2 (left, right)
+static __global__ void k_bm_prefilter(const uint8_t* __restrict__ imgL, size_t pitchL, const uint8_t* __restrict__ imgR, size_t pitchR,
+                                      int W, int H, int cap, uint8_t* __restrict__ outL, uint8_t* __restrict__ outR)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    if (x >= W) return;
+    const uint8_t* img = blockIdx.z ? imgR : imgL;
+    const size_t pitch = blockIdx.z ? pitchR : pitchL;
+    uint8_t* out = blockIdx.z ? outR : outL;
+    int v = cap;
+    const bool last_odd = (H & 1) && y == H - 1;          // rows are produced in pairs: the odd one out is all `cap`
+    if (x > 0 && x < W - 1 && !last_odd) {
+        const int up = y > 0 ? y - 1 : min(y + 1, H - 1), dn = y < H - 1 ? y + 1 : max(y - 1, 0);
+        const uint8_t *r0 = img + size_t(up) * pitch, *r1 = img + size_t(y) * pitch, *r2 = img + size_t(dn) * pitch;
+        const int g = (int(r0[x + 1]) - int(r0[x - 1])) + 2 * (int(r1[x + 1]) - int(r1[x - 1])) + (int(r2[x + 1]) - int(r2[x - 1]));
+        v = min(max(g, -cap), cap) + cap;
+    }
+    out[size_t(y) * W + x] = uint8_t(v);
+}
+
+__device__ __forceinline__ int bm_lc(const BmGeom& g, int xx) { return min(max(xx, -g.lofs), g.W - g.lofs - 1) + g.lofs; }
+__device__ __forceinline__ int bm_rc(const BmGeom& g, int xx) { return min(max(xx, -g.rofs), g.W - g.rofs - g.ndisp) + g.rofs; }
+
+// Horizontal window sums: HS[y][x][d] = sum_{dx} |PL[y][lc(x+dx)] - PR[y][rc(x+dx) + d]| (uint16: <= 255 * 2*cap), one thread per
+// (y, d) sliding along a segment of columns; grid = (ceil(ndisp / blockDim.x), H, segments).
+static __global__ void k_bm_hsad(const uint8_t* __restrict__ PL, const uint8_t* __restrict__ PR, BmGeom g, int seg_len,
+                                 uint16_t* __restrict__ HS)
+{
+    const int d = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    const int x0 = blockIdx.z * seg_len, x1 = min(x0 + seg_len, g.width1);
+    if (d >= g.ndisp || x0 >= x1) return;
+    const uint8_t* l = PL + size_t(y) * g.W;
+    const uint8_t* r = PR + size_t(y) * g.W + d;
+    const int w2 = g.wsz >> 1;
+    int hs = 0;
+    for (int dx = -w2; dx <= w2; dx++) hs += abs(int(l[bm_lc(g, x0 + dx)]) - int(r[bm_rc(g, x0 + dx)]));
+    uint16_t* o = HS + (size_t(y) * g.width1 + x0) * g.ndisp + d;
+    for (int x = x0; x < x1; x++, o += g.ndisp) {
+        *o = uint16_t(hs);
+        hs += abs(int(l[bm_lc(g, x + w2 + 1)]) - int(r[bm_rc(g, x + w2 + 1)])) - abs(int(l[bm_lc(g, x - w2)]) - int(r[bm_rc(g, x - w2)]));
+    }
+}
+
+// Horizontal texture sums HT[y][x] = sum_{dx} |PL[y][lc(x+dx)] - cap|
+static __global__ void k_bm_htext(const uint8_t* __restrict__ PL, BmGeom g, int* __restrict__ HT)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    if (x >= g.width1) return;
+    const uint8_t* l = PL + size_t(y) * g.W;
+    const int w2 = g.wsz >> 1;
+    int s = 0;
+    for (int dx = -w2; dx <= w2; dx++) s += abs(int(l[bm_lc(g, x + dx)]) - g.cap);
+    HT[size_t(y) * g.width1 + x] = s;
+}
+
+// Vertical window sums + winner-take-all.  One warp per (column x, row segment); lane l holds disparity indices l, l+32, ...
+// (NPL per lane).  d index -> disparity = ndisp - 1 - d + mindisp; the FIRST minimum over d wins (= the largest disparity).
+template <int NPL>
+static __global__ void __launch_bounds__(128) k_bm_match(const uint16_t* __restrict__ HS, const int* __restrict__ HT, BmGeom g,
+                                                         int seg_rows, int16_t* __restrict__ disp)
+{
+    const int lane = threadIdx.x & 31;
+    const int x = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (x >= g.width1) return;
+    const int ya = blockIdx.y * seg_rows, yb = min(ya + seg_rows, g.H);
+    if (ya >= yb) return;
+    const int w2 = g.wsz >> 1, nd = g.ndisp;
+    const size_t rstride = size_t(g.width1) * nd;
+    const uint16_t* hs = HS + size_t(x) * nd;
+    auto cy = [&](int yy) { return min(max(yy, 0), g.H - 1); };
+    int sad[NPL];
+#pragma unroll
+    for (int k = 0; k < NPL; k++) sad[k] = 0;
+    int tsum = 0;
+    for (int r = ya - w2; r <= ya + w2; r++) {
+        const uint16_t* p = hs + size_t(cy(r)) * rstride;
+#pragma unroll
+        for (int k = 0; k < NPL; k++) { const int d = lane + 32 * k; if (d < nd) sad[k] += p[d]; }
+        tsum += HT[size_t(cy(r)) * g.width1 + x];
+    }
+    const bool in_row = g.lofs + x < g.W;
+    for (int y = ya; y < yb; y++) {
+        // first minimum
+        unsigned best = 0xFFFFFFFFu;
+#pragma unroll
+        for (int k = 0; k < NPL; k++) { const int d = lane + 32 * k; if (d < nd) best = min(best, unsigned(sad[k])); }
+        const unsigned minsad = __reduce_min_sync(0xFFFFFFFFu, best);
+        unsigned dc = 0xFFFFFFFFu;
+#pragma unroll
+        for (int k = 0; k < NPL; k++) { const int d = lane + 32 * k; if (d < nd && unsigned(sad[k]) == minsad) dc = min(dc, unsigned(d)); }
+        const int mind = int(__reduce_min_sync(0xFFFFFFFFu, dc));
+        bool ok = tsum >= g.tex;
+        if (g.uniq > 0) {
+            const long long thresh = (long long)minsad + ((long long)minsad * g.uniq / 100);
+            bool viol = false;
+#pragma unroll
+            for (int k = 0; k < NPL; k++) {
+                const int d = lane + 32 * k;
+                if (d < nd && (d < mind - 1 || d > mind + 1) && (long long)sad[k] <= thresh) viol = true;
+            }
+            ok = ok && !__any_sync(0xFFFFFFFFu, viol);
+        }
+        // neighbours of the minimum (sad[-1] = sad[1], sad[ndisp] = sad[ndisp-2])
+        const int jm = mind == 0 ? 1 : mind - 1, jp = mind == nd - 1 ? nd - 2 : mind + 1;
+        unsigned vn = 0, vp = 0;
+#pragma unroll
+        for (int k = 0; k < NPL; k++) {
+            const int d = lane + 32 * k;
+            if (d == jm) vn = unsigned(sad[k]);
+            if (d == jp) vp = unsigned(sad[k]);
+        }
+        const int n = int(__reduce_max_sync(0xFFFFFFFFu, vn)), p = int(__reduce_max_sync(0xFFFFFFFFu, vp));
+        if (lane == 0 && in_row) {
+            int out = g.FILTERED;
+            if (ok) {
+                const int den = p + n - 2 * int(minsad) + abs(p - n);
+                const int q = den != 0 ? (p - n) * 256 / den : 0;            // C division: toward zero
+                out = ((nd - mind - 1 + g.mindisp) * 256 + q + 15) >> 4;
+            }
+            disp[size_t(y) * g.W + g.lofs + x] = int16_t(out);
+        }
+        if (y + 1 < yb) {
+            const uint16_t* pa = hs + size_t(cy(y + w2 + 1)) * rstride;
+            const uint16_t* pr = hs + size_t(cy(y - w2)) * rstride;
+#pragma unroll
+            for (int k = 0; k < NPL; k++) { const int d = lane + 32 * k; if (d < nd) sad[k] += int(pa[d]) - int(pr[d]); }
+            tsum += HT[size_t(cy(y + w2 + 1)) * g.width1 + x] - HT[size_t(cy(y - w2)) * g.width1 + x];
+        }
+    }
+}
+
+// getValidDisparityROI with full-image ROIs: everything outside [xmin, xmax) x [ymin, ymax) is FILTERED
+static __global__ void k_bm_mask(int16_t* __restrict__ disp, int W, int H, int xmin, int xmax, int ymin, int ymax, int FILTERED)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    if (x >= W) return;
+    if (x < xmin || x >= xmax || y < ymin || y >= ymax) disp[size_t(y) * W + x] = int16_t(FILTERED);
+}
+
+}  // namespace b200sgm

@@ -18,19 +18,21 @@ void launch_median3(const int16_t* src, int16_t* dst, int W, int H, cudaStream_t
     k_median3<<<grid, block, 0, st>>>(src, dst, W, H);
 }
 
-cudaError_t launch_speckle(int16_t* img, int* label, int* parent, int* runlen, int* csize, const Eff& e, cudaStream_t st, int* launches)
+void launch_fill16(int16_t* p, int n, int16_t v, cudaStream_t st) { k_fill16<<<(n + 255) / 256, 256, 0, st>>>(p, n, v); }
+
+cudaError_t launch_speckle(int16_t* img, int* label, int* parent, int* runlen, int* csize, int W, int H, int newVal, int maxSize, int maxDiff,
+                           cudaStream_t st, int* launches)
 {
-    const int W = e.W, H = e.H, npix = W * H;
-    const int maxDiff = 16 * e.speckleRange;
+    const int npix = W * H;
     cudaError_t ce;
-    k_speckle_runs<<<H, 256, 0, st>>>(img, label, parent, runlen, csize, W, e.INVALID, maxDiff);
+    k_speckle_runs<<<H, 256, 0, st>>>(img, label, parent, runlen, csize, W, newVal, maxDiff);
     ++*launches; if ((ce = cudaGetLastError()) != cudaSuccess) return ce;
     dim3 block(256), grid((W + 255) / 256, H);
-    k_speckle_vmerge<<<grid, block, 0, st>>>(img, label, parent, W, H, e.INVALID, maxDiff);
+    k_speckle_vmerge<<<grid, block, 0, st>>>(img, label, parent, W, H, newVal, maxDiff);
     ++*launches; if ((ce = cudaGetLastError()) != cudaSuccess) return ce;
-    k_speckle_size<<<(npix + 255) / 256, 256, 0, st>>>(label, parent, runlen, csize, npix, e.speckleWin);
+    k_speckle_size<<<(npix + 255) / 256, 256, 0, st>>>(label, parent, runlen, csize, npix, maxSize);
     ++*launches; if ((ce = cudaGetLastError()) != cudaSuccess) return ce;
-    k_speckle_apply<<<(npix + 255) / 256, 256, 0, st>>>(img, label, parent, csize, npix, e.INVALID, e.speckleWin);
+    k_speckle_apply<<<(npix + 255) / 256, 256, 0, st>>>(img, label, parent, csize, npix, newVal, maxSize);
     ++*launches; return cudaGetLastError();
 }
 

@@ -21,7 +21,7 @@ SYMBOLS = (
     "b200sgm_compute_f32", "b200sgm_compute_device", "b200sgm_enqueue", "b200sgm_wait", "b200sgm_compute_xyz",
     "b200sgm_last_error", "b200sgm_version", "b200sgm_launch_count", "b200sgm_lane_stream", "b200sgm_debug_read",
     "b200sgm_debug_set_path", "b200sgm_profile", "b200sgm_stage_times", "b200sgm_alu_peak", "b200sgm_stage_timeline",
-    "b200sgm_set_camera", "b200sgm_rectify", "b200sgm_rectify_device", "b200sgm_rectify_maps",
+    "b200sgm_set_camera", "b200sgm_rectify", "b200sgm_rectify_device", "b200sgm_rectify_maps", "b200sgm_bm_compute",
 )
 
 STAGES = ("prefilter", "cost", "horizontal", "vertical_wta", "lrcheck", "median", "speckle")
@@ -173,6 +173,21 @@ class Engine:
         self._check(self.lib.b200sgm_rectify_maps(self.h, int(cam), int(W), int(H), m1.ctypes.data_as(ctypes.c_void_p),
                                                   m2.ctypes.data_as(ctypes.c_void_p)))
         return m1, m2
+
+    # ---- StereoBM (row N4): cv::StereoBM::compute of matcherOpenCVBlock.cpp:13-20 ----
+    def bm_compute(self, left, right, numDisparities=64, blockSize=9, minDisparity=0, preFilterCap=31, textureThreshold=10,
+                   uniquenessRatio=15, speckleWindowSize=0, speckleRange=0, disp12MaxDiff=-1) -> np.ndarray:
+        L, R = _u8(left), _u8(right)
+        if L.shape != R.shape:
+            raise ValueError("Images MUST be the same resolution")
+        H, W = L.shape
+        bp = (ctypes.c_int * 9)(minDisparity, numDisparities, blockSize, preFilterCap, textureThreshold, uniquenessRatio,
+                                speckleWindowSize, speckleRange, disp12MaxDiff)
+        out = np.empty((H, W), np.int16)
+        self._check(self.lib.b200sgm_bm_compute(self.h, bp, L.ctypes.data_as(ctypes.c_void_p), ctypes.c_size_t(L.strides[0]),
+                                                R.ctypes.data_as(ctypes.c_void_p), ctypes.c_size_t(R.strides[0]), W, H,
+                                                out.ctypes.data_as(ctypes.c_void_p), ctypes.c_size_t(W * 2)))
+        return out
 
     # ---- streaming with host buffers (pinned for true overlap) ----
     def enqueue(self, lane, left, right, disp_out):

@@ -141,6 +141,24 @@ int b200sgm_rectify_device(b200sgm_handle h, int lane, int cam, const uint8_t *d
 /* The CV_32FC1 maps of cv::initUndistortRectifyMap for `cam` at this size, copied to the host (H x W, tight). */
 int b200sgm_rectify_maps(b200sgm_handle h, int cam, int width, int height, float *map1, float *map2);
 
+/* ---- the package's other OpenCV matcher (row N4 of SURVEY.md section 8f): StereoBM ----------------------------- */
+
+/* Raw cv::StereoBM parameters as MatcherOpenCVBlock's setters install them (matcherOpenCVBlock.cpp:52-110 on top of
+ * StereoBM::create(64, 9), :13-16); PREFILTER_XSOBEL (OpenCV's default; the reference never changes it).  disp12MaxDiff must
+ * stay negative (OpenCV's default; generate_disparity.cpp:241-261 does not forward it). */
+typedef struct b200sgm_bm_params {
+    int minDisparity, numDisparities, blockSize, preFilterCap, textureThreshold, uniquenessRatio, speckleWindowSize,
+        speckleRange, disp12MaxDiff;
+} b200sgm_bm_params;
+
+/* matcher->compute(*left, *right, disparity_lr) of MatcherOpenCVBlock::forwardMatch (matcherOpenCVBlock.cpp:20): CV_8UC1 host
+ * images in, CV_16S disparity x16 out, filtered pixels = (minDisparity-1)*16.  Synchronous, lane 0.  Bit-exact with
+ * cv::StereoBM 4.13 except the `minDisparity` pixels at the start of the first row below the valid ROI when minDisparity > 0,
+ * where OpenCV leaves values it wrote past the end of the previous row (this engine returns filtered there). */
+int b200sgm_bm_compute(b200sgm_handle h, const b200sgm_bm_params *p, const uint8_t *left, size_t left_stride,
+                       const uint8_t *right, size_t right_stride, int width, int height, int16_t *disp,
+                       size_t disp_stride);
+
 /* ---- diagnostics ------------------------------------------------------------------------------------------ */
 
 const char *b200sgm_last_error(b200sgm_handle h);

@@ -1,0 +1,76 @@
+"""GPU parity for row N4 (StereoBM): b200sgm_bm_compute through the C ABI against the cv2 4.13 golden fixture and the numpy
+oracle; bit-exact outside the documented row-overflow pixels of OpenCV (minDisparity > 0)."""
+import os
+
+import numpy as np
+import pytest
+
+import b200sgm
+from b200sgm import synth, Engine
+from oracle import bm_oracle as bo
+
+overflow_mask = bo.overflow_mask
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_bm_matches_cv2_golden():
+    z = np.load(os.path.join(ROOT, "tests", "golden", "bm_small.npz"))
+    eng = Engine(0, 256, 128, 64, 1)
+    for n in range(int(z["n"])):
+        nd, bs, mind, cap, tex, uniq, sw, sr = (int(v) for v in z["c%d_p" % n])
+        got = eng.bm_compute(z["c%d_L" % n], z["c%d_R" % n], nd, bs, mind, cap, tex, uniq, sw, sr)
+        want = z["c%d_disp" % n]
+        keep = ~overflow_mask(got.shape, bs, mind)
+        assert np.array_equal(got[keep], want[keep]), "case %d: %d px differ from cv2" % (n, (got != want)[keep].sum())
+    eng.close()
+
+
+def test_bm_random_vs_oracle():
+    rng = np.random.default_rng(8)
+    eng = Engine(0, 640, 300, 256, 1)
+    done = 0
+    for it in range(40):
+        W, H = int(rng.integers(40, 640)), int(rng.integers(24, 300))
+        nd = int(rng.choice([16, 32, 48, 64, 128, 256])); bs = int(rng.choice([5, 7, 9, 15, 21, 31])); mind = int(rng.choice([0, 0, 4, -3, -20, 30]))
+        if bs >= min(W, H) or W - nd < 8:
+            continue
+        cap = int(rng.choice([1, 15, 31, 63])); tex = int(rng.choice([0, 10, 300, 2000])); uniq = int(rng.choice([0, 5, 15, 40]))
+        sw = int(rng.choice([0, 0, 50, 200])); sr = int(rng.choice([0, 1, 4, 32]))
+        L, R = synth.make_pair(W, H, nd, mind, 400 + it)
+        if it % 4 == 1:
+            R = np.clip(R.astype(int) + rng.integers(-20, 21, R.shape), 0, 255).astype(np.uint8)
+        if it % 4 == 2:
+            L = (L // 64 * 64).astype(np.uint8); R = (R // 64 * 64).astype(np.uint8)
+        want = bo.compute(L, R, nd, bs, mind, cap, tex, uniq, sw, sr)
+        got = eng.bm_compute(L, R, nd, bs, mind, cap, tex, uniq, sw, sr)
+        assert np.array_equal(got, want), "it %d (%dx%d nd %d bs %d minD %d): %d px differ" % (it, W, H, nd, bs, mind, (got != want).sum())
+        done += 1
+    eng.close()
+    assert done >= 25
+
+
+def test_bm_full_size_and_errors():
+    import time
+    W, H, nd = 2448, 2048, 256
+    L, R = synth.make_pair(W, H, nd, 0, 1000)
+    eng = Engine(0, W, H, nd, 1)
+    eng.bm_compute(L, R, nd, 9)
+    t0 = time.perf_counter()
+    got = eng.bm_compute(L, R, nd, 9, speckleWindowSize=100, speckleRange=32)
+    dt = time.perf_counter() - t0
+    # size-independent properties: borders and rows outside the valid ROI are filtered; a second run is identical
+    assert (got[:, :255 + 4] == -16).all() and (got[:4] == -16).all() and (got[-4:] == -16).all() and (got[:, -4:] == -16).all()
+    assert np.array_equal(got, eng.bm_compute(L, R, nd, 9, speckleWindowSize=100, speckleRange=32))
+    assert (got != -16).mean() > 0.3
+    # a band of rows against the oracle (the oracle needs the whole disparity range in memory: keep it small)
+    band = slice(1000, 1064)
+    want = bo.compute(L[band], R[band], nd, 9)
+    sub = eng.bm_compute(L[band], R[band], nd, 9)
+    assert np.array_equal(sub, want)
+    print("StereoBM 2448x2048x256 end to end (pageable host buffers): %.1f ms, valid %.1f%%" % (dt * 1e3, 100 * (got != -16).mean()))
+    for bad in (dict(numDisparities=20), dict(blockSize=8), dict(blockSize=3), dict(preFilterCap=0), dict(disp12MaxDiff=1), dict(textureThreshold=-1)):
+        with pytest.raises(b200sgm.B200SGMError):
+            eng.bm_compute(L[:64, :256], R[:64, :256], **{**dict(numDisparities=64), **bad})
+    eng.close()
