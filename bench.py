@@ -395,6 +395,46 @@ def run_b200(args, cfg):
         except Exception as e:  # pragma: no cover
             rect = {"error": str(e)}
 
+    # ---- row N4: the package's other OpenCV matcher, StereoBM, device-resident (rank 0), cv2 beside it at N=1
+    bm = None
+    if rank == 0:
+        try:
+            kw = dict(numDisparities=D, blockSize=9, speckleWindowSize=p.speckleWindowSize, speckleRange=p.speckleRange)
+            ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+            nrep = 8
+            for rep in range(nrep + 2):
+                if rep == 2:
+                    ev[0].record(streams[0])
+                i = rep % NF
+                eng.bm_compute_device(0, devL[i].data_ptr(), W, devR[i].data_ptr(), W, W, H, devD[i].data_ptr(), W * 2,
+                                      stream=streams[0].cuda_stream, **kw)
+            ev[1].record(streams[0])
+            streams[0].synchronize()
+            ms_bm = ev[0].elapsed_time(ev[1]) / nrep
+            bm = {"ms_per_frame": ms_bm, "frames_per_s": 1e3 / ms_bm, "params": kw,
+                  "note": "cv::StereoBM::compute of matcherOpenCVBlock.cpp:20 (first, unfused version: SAD volume materialised); "
+                          "not part of `value`"}
+            if world == 1 and not args.no_cpu_baseline:
+                try:
+                    import cv2
+                    m = cv2.StereoBM_create(64, 9)
+                    m.setNumDisparities(D); m.setBlockSize(9); m.setSpeckleWindowSize(p.speckleWindowSize); m.setSpeckleRange(p.speckleRange)
+                    l0, r0 = hostL[0].numpy(), hostR[0].numpy()
+                    ref0 = m.compute(l0, r0)
+                    t0 = time.perf_counter()
+                    for _ in range(3):
+                        m.compute(l0, r0)
+                    bm["cpu_cv2_ms_per_frame"] = (time.perf_counter() - t0) / 3 * 1e3
+                    bm["cpu_threads"] = cv2.getNumThreads()
+                    eng.bm_compute_device(0, devL[0].data_ptr(), W, devR[0].data_ptr(), W, W, H, devD[0].data_ptr(), W * 2,
+                                          stream=streams[0].cuda_stream, **kw)
+                    streams[0].synchronize()
+                    bm["matches_cv2"] = bool(np.array_equal(devD[0].cpu().numpy(), ref0))
+                except ImportError:
+                    pass
+        except Exception as e:  # pragma: no cover
+            bm = {"error": str(e)}
+
     # ---- CPU baseline beside it (rank 0, N=1 only)
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -411,7 +451,7 @@ def run_b200(args, cfg):
             "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "u16", "data": "synthetic", "config": workload(cfg, NF, lanes),
             "gpix_disp_per_s": fps * cfg.gpix_disp, "parity_checked_vs_golden_crc": checked,
-            "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu, "rectify": rect,
+            "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu, "rectify": rect, "stereobm": bm,
         }
         print(json.dumps(line), flush=True)
     eng.close()

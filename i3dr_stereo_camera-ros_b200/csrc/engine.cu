@@ -473,11 +473,11 @@ int b200sgm_rectify_maps(b200sgm_handle h, int cam, int width, int height, float
 }
 
 // ---- StereoBM (row N4): matcherOpenCVBlock.cpp:13-20 ---------------------------------------------------------------------
-int b200sgm_bm_compute(b200sgm_handle h, const b200sgm_bm_params* bp, const uint8_t* left, size_t left_stride, const uint8_t* right,
-                       size_t right_stride, int width, int height, int16_t* disp, size_t disp_stride)
+namespace {
+// cv::StereoBM's own argument checks (CV_Error -> forwardMatch() == -1 in the reference), then the kernels into ln.disp_out
+int bm_run(b200sgm_engine* h, Lane& ln, const b200sgm_bm_params* bp, const uint8_t* dL, size_t lp, const uint8_t* dR, size_t rp, int width,
+           int height, cudaStream_t st)
 {
-    if (!h || !bp || !left || !right || !disp) return B200SGM_EINVAL;
-    // cv::StereoBM's own argument checks (CV_Error -> forwardMatch() == -1 in the reference)
     if (bp->numDisparities <= 0 || bp->numDisparities % 16 != 0) return fail(h, B200SGM_EINVAL, "numDisparities must be positive and divisible by 16");
     if (bp->numDisparities > h->maxD) return fail(h, B200SGM_ESIZE, "numDisparities exceeds the engine's max_disparities");
     if (width <= 0 || height <= 0) return fail(h, B200SGM_EINVAL, "empty image");
@@ -488,22 +488,50 @@ int b200sgm_bm_compute(b200sgm_handle h, const b200sgm_bm_params* bp, const uint
     if (bp->textureThreshold < 0 || bp->uniquenessRatio < 0) return fail(h, B200SGM_EINVAL, "textureThreshold and uniquenessRatio must be non-negative");
     if (bp->disp12MaxDiff >= 0) return fail(h, B200SGM_EINVAL, "disp12MaxDiff >= 0 is not supported by the block matcher (the reference never sets it)");
     if ((bp->minDisparity + bp->numDisparities) * 16 >= 32768 || (bp->minDisparity - 1) * 16 < -32768) return fail(h, B200SGM_EINVAL, "disparity range does not fit CV_16S x16");
-    if (left_stride < size_t(width) || right_stride < size_t(width) || disp_stride < size_t(width) * 2) return fail(h, B200SGM_EINVAL, "stride smaller than a row");
+    if (lp < size_t(width) || rp < size_t(width)) return fail(h, B200SGM_EINVAL, "stride smaller than a row");
+    BmParams p{bp->minDisparity, bp->numDisparities, bp->blockSize, bp->preFilterCap, bp->textureThreshold, bp->uniquenessRatio,
+               bp->speckleWindowSize, bp->speckleRange};
+    int nl = 0;
+    const cudaError_t ce = launch_bm(dL, lp, dR, rp, width, height, p, reinterpret_cast<uint8_t*>(ln.disp_wta), ln.C, ln.csize, ln.disp_out,
+                                     ln.label, ln.parent, ln.runlen, ln.csize, h->num_sms, st, &nl);
+    h->launches += nl;
+    if (ce != cudaSuccess) return fail(h, B200SGM_ECUDA, std::string("block matcher launch: ") + cudaGetErrorString(ce));
+    return B200SGM_OK;
+}
+}  // namespace
+
+int b200sgm_bm_compute(b200sgm_handle h, const b200sgm_bm_params* bp, const uint8_t* left, size_t left_stride, const uint8_t* right,
+                       size_t right_stride, int width, int height, int16_t* disp, size_t disp_stride)
+{
+    if (!h || !bp || !left || !right || !disp) return B200SGM_EINVAL;
+    if (width > 0 && disp_stride < size_t(width) * 2) return fail(h, B200SGM_EINVAL, "stride smaller than a row");
+    if (width <= 0 || height <= 0) return fail(h, B200SGM_EINVAL, "empty image");
+    if (width > h->maxW || height > h->maxH) return fail(h, B200SGM_ESIZE, "image exceeds the engine's max size");
+    if (left_stride < size_t(width) || right_stride < size_t(width)) return fail(h, B200SGM_EINVAL, "stride smaller than a row");
     CUDA_TRY(h, cudaSetDevice(h->device));
     Lane& ln = h->lanes[0];
     if (ln.busy) return fail(h, B200SGM_ESTATE, "lane 0 is busy: call b200sgm_wait first");
     cudaStream_t st = ln.stream;
     CUDA_TRY(h, cudaMemcpy2DAsync(ln.left, width, left, left_stride, width, height, cudaMemcpyHostToDevice, st));
     CUDA_TRY(h, cudaMemcpy2DAsync(ln.right, width, right, right_stride, width, height, cudaMemcpyHostToDevice, st));
-    BmParams p{bp->minDisparity, bp->numDisparities, bp->blockSize, bp->preFilterCap, bp->textureThreshold, bp->uniquenessRatio,
-               bp->speckleWindowSize, bp->speckleRange};
-    int nl = 0;
-    const cudaError_t ce = launch_bm(ln.left, width, ln.right, width, width, height, p, reinterpret_cast<uint8_t*>(ln.disp_wta), ln.C, ln.csize,
-                                     ln.disp_out, ln.label, ln.parent, ln.runlen, ln.csize, h->num_sms, st, &nl);
-    h->launches += nl;
-    if (ce != cudaSuccess) return fail(h, B200SGM_ECUDA, std::string("block matcher launch: ") + cudaGetErrorString(ce));
+    if (int rc = bm_run(h, ln, bp, ln.left, width, ln.right, width, width, height, st)) return rc;
     CUDA_TRY(h, cudaMemcpy2DAsync(disp, disp_stride, ln.disp_out, size_t(width) * 2, size_t(width) * 2, height, cudaMemcpyDeviceToHost, st));
     CUDA_TRY(h, cudaStreamSynchronize(st));
+    return B200SGM_OK;
+}
+
+int b200sgm_bm_compute_device(b200sgm_handle h, int lane, const b200sgm_bm_params* bp, const uint8_t* d_left, size_t left_stride,
+                              const uint8_t* d_right, size_t right_stride, int width, int height, int16_t* d_disp, size_t disp_stride,
+                              void* cuda_stream)
+{
+    if (!h || !bp || !d_left || !d_right || !d_disp) return B200SGM_EINVAL;
+    if (int rc = lane_check(h, lane)) return rc;
+    if (width > 0 && disp_stride < size_t(width) * 2) return fail(h, B200SGM_EINVAL, "stride smaller than a row");
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    Lane& ln = h->lanes[lane];
+    cudaStream_t st = cuda_stream ? cudaStream_t(cuda_stream) : ln.stream;
+    if (int rc = bm_run(h, ln, bp, d_left, left_stride, d_right, right_stride, width, height, st)) return rc;
+    CUDA_TRY(h, cudaMemcpy2DAsync(d_disp, disp_stride, ln.disp_out, size_t(width) * 2, size_t(width) * 2, height, cudaMemcpyDeviceToDevice, st));
     return B200SGM_OK;
 }
 

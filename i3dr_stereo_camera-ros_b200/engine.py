@@ -22,6 +22,7 @@ SYMBOLS = (
     "b200sgm_last_error", "b200sgm_version", "b200sgm_launch_count", "b200sgm_lane_stream", "b200sgm_debug_read",
     "b200sgm_debug_set_path", "b200sgm_profile", "b200sgm_stage_times", "b200sgm_alu_peak", "b200sgm_stage_timeline",
     "b200sgm_set_camera", "b200sgm_rectify", "b200sgm_rectify_device", "b200sgm_rectify_maps", "b200sgm_bm_compute",
+    "b200sgm_bm_compute_device",
 )
 
 STAGES = ("prefilter", "cost", "horizontal", "vertical_wta", "lrcheck", "median", "speckle")
@@ -188,6 +189,14 @@ class Engine:
                                                 R.ctypes.data_as(ctypes.c_void_p), ctypes.c_size_t(R.strides[0]), W, H,
                                                 out.ctypes.data_as(ctypes.c_void_p), ctypes.c_size_t(W * 2)))
         return out
+
+    def bm_compute_device(self, lane, lptr, lstride, rptr, rstride, W, H, dptr, dstride, stream=0, numDisparities=64, blockSize=9,
+                          minDisparity=0, preFilterCap=31, textureThreshold=10, uniquenessRatio=15, speckleWindowSize=0, speckleRange=0):
+        bp = (ctypes.c_int * 9)(minDisparity, numDisparities, blockSize, preFilterCap, textureThreshold, uniquenessRatio,
+                                speckleWindowSize, speckleRange, -1)
+        self._check(self.lib.b200sgm_bm_compute_device(self.h, int(lane), bp, ctypes.c_void_p(lptr), ctypes.c_size_t(lstride),
+                                                       ctypes.c_void_p(rptr), ctypes.c_size_t(rstride), int(W), int(H),
+                                                       ctypes.c_void_p(dptr), ctypes.c_size_t(dstride), ctypes.c_void_p(stream)))
 
     # ---- streaming with host buffers (pinned for true overlap) ----
     def enqueue(self, lane, left, right, disp_out):

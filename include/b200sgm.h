@@ -159,6 +159,11 @@ int b200sgm_bm_compute(b200sgm_handle h, const b200sgm_bm_params *p, const uint8
                        const uint8_t *right, size_t right_stride, int width, int height, int16_t *disp,
                        size_t disp_stride);
 
+/* Device-resident variant, enqueued on `cuda_stream` (or the stream of lane `lane` when NULL), not synchronised. */
+int b200sgm_bm_compute_device(b200sgm_handle h, int lane, const b200sgm_bm_params *p, const uint8_t *d_left,
+                              size_t left_stride, const uint8_t *d_right, size_t right_stride, int width, int height,
+                              int16_t *d_disp, size_t disp_stride, void *cuda_stream);
+
 /* ---- diagnostics ------------------------------------------------------------------------------------------ */
 
 const char *b200sgm_last_error(b200sgm_handle h);
