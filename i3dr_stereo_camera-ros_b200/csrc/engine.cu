@@ -198,7 +198,7 @@ int b200sgm_create(int device, int max_width, int max_height, int max_disparitie
         ok = ok && cudaMalloc(&ln.C, vol) == cudaSuccess && cudaMalloc(&ln.S, vol) == cudaSuccess;
         ok = ok && cudaMalloc(&ln.ckpt, horiz_ckpt_elems(max_width, max_height, int(Dp)) * sizeof(uint16_t)) == cudaSuccess;
         ok = ok && cudaMalloc(&ln.disp2key, npix * 4) == cudaSuccess;
-        ok = ok && cudaMalloc(&ln.disp_wta, npix * 2) == cudaSuccess && cudaMalloc(&ln.disp_med, npix * 2) == cudaSuccess && cudaMalloc(&ln.disp_out, npix * 2) == cudaSuccess;
+        ok = ok && cudaMalloc(&ln.disp_wta, npix * 2 + 16) == cudaSuccess && cudaMalloc(&ln.disp_med, npix * 2) == cudaSuccess && cudaMalloc(&ln.disp_out, npix * 2) == cudaSuccess;
         ok = ok && cudaMalloc(&ln.label, npix * 4) == cudaSuccess && cudaMalloc(&ln.csize, npix * 4) == cudaSuccess;
         ok = ok && cudaMalloc(&ln.parent, npix * 4) == cudaSuccess && cudaMalloc(&ln.runlen, npix * 4) == cudaSuccess;
         ok = ok && cudaMalloc(&ln.f32a, npix * 4) == cudaSuccess && cudaMalloc(&ln.f32b, npix * 4) == cudaSuccess;

@@ -37,23 +37,42 @@ static __global__ void k_bm_prefilter(const uint8_t* __restrict__ imgL, size_t p
 __device__ __forceinline__ int bm_lc(const BmGeom& g, int xx) { return min(max(xx, -g.lofs), g.W - g.lofs - 1) + g.lofs; }
 __device__ __forceinline__ int bm_rc(const BmGeom& g, int xx) { return min(max(xx, -g.rofs), g.W - g.rofs - g.ndisp) + g.rofs; }
 
-// Horizontal window sums: HS[y][x][d] = sum_{dx} |PL[y][lc(x+dx)] - PR[y][rc(x+dx) + d]| (uint16: <= 255 * 2*cap), one thread per
-// (y, d) sliding along a segment of columns; grid = (ceil(ndisp / blockDim.x), H, segments).
+// Horizontal window sums: HS[y][x][d] = sum_{dx} |PL[y][lc(x+dx)] - PR[y][rc(x+dx) + d]| (uint16: <= 255 * 2*cap).  A thread owns FOUR
+// consecutive disparity indices of one row and slides along a segment of columns: the four right-image bytes of a window column
+// come from two aligned words + PRMT, the four absolute differences from one VABSDIFF4, and the four running sums live in two
+// 16x2 registers (no carries between halves: every partial sum is a sum of non-negative terms below 2^16).
+// block = (ndisp/4, rows per block); grid = (1, ceil(H / rows per block), column segments).
+__device__ __forceinline__ uint32_t bm_absdiff4(const uint8_t* __restrict__ l, const uint8_t* __restrict__ r, const BmGeom& g, int xx)
+{
+    const uint32_t l4 = uint32_t(l[bm_lc(g, xx)]) * 0x01010101u;
+    const uintptr_t ad = reinterpret_cast<uintptr_t>(r + bm_rc(g, xx));
+    const uint32_t* wa = reinterpret_cast<const uint32_t*>(ad & ~uintptr_t(3));
+    const uint32_t sh = uint32_t(ad & 3);
+    const uint32_t w0 = __ldg(wa), w1 = sh ? __ldg(wa + 1) : 0u;
+    return __vabsdiffu4(l4, __byte_perm(w0, w1, 0x3210u + 0x1111u * sh));
+}
+
 static __global__ void k_bm_hsad(const uint8_t* __restrict__ PL, const uint8_t* __restrict__ PR, BmGeom g, int seg_len,
                                  uint16_t* __restrict__ HS)
 {
-    const int d = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    const int d0 = threadIdx.x * 4, y = blockIdx.y * blockDim.y + threadIdx.y;
     const int x0 = blockIdx.z * seg_len, x1 = min(x0 + seg_len, g.width1);
-    if (d >= g.ndisp || x0 >= x1) return;
+    if (d0 >= g.ndisp || y >= g.H || x0 >= x1) return;
     const uint8_t* l = PL + size_t(y) * g.W;
-    const uint8_t* r = PR + size_t(y) * g.W + d;
+    const uint8_t* r = PR + size_t(y) * g.W + d0;
     const int w2 = g.wsz >> 1;
-    int hs = 0;
-    for (int dx = -w2; dx <= w2; dx++) hs += abs(int(l[bm_lc(g, x0 + dx)]) - int(r[bm_rc(g, x0 + dx)]));
-    uint16_t* o = HS + (size_t(y) * g.width1 + x0) * g.ndisp + d;
-    for (int x = x0; x < x1; x++, o += g.ndisp) {
-        *o = uint16_t(hs);
-        hs += abs(int(l[bm_lc(g, x + w2 + 1)]) - int(r[bm_rc(g, x + w2 + 1)])) - abs(int(l[bm_lc(g, x - w2)]) - int(r[bm_rc(g, x - w2)]));
+    uint32_t hA = 0, hB = 0;           // (hs[d0], hs[d0+1]), (hs[d0+2], hs[d0+3])
+    for (int dx = -w2; dx <= w2; dx++) {
+        const uint32_t a4 = bm_absdiff4(l, r, g, x0 + dx);
+        hA += __byte_perm(a4, 0, 0x4140); hB += __byte_perm(a4, 0, 0x4342);
+    }
+    uint2* o = reinterpret_cast<uint2*>(HS + (size_t(y) * g.width1 + x0) * g.ndisp + d0);
+    const size_t ostep = size_t(g.ndisp) / 4;
+    for (int x = x0; x < x1; x++, o += ostep) {
+        *o = make_uint2(hA, hB);
+        const uint32_t a4 = bm_absdiff4(l, r, g, x + w2 + 1), r4 = bm_absdiff4(l, r, g, x - w2);
+        hA = hA + __byte_perm(a4, 0, 0x4140) - __byte_perm(r4, 0, 0x4140);
+        hB = hB + __byte_perm(a4, 0, 0x4342) - __byte_perm(r4, 0, 0x4342);
     }
 }
 

@@ -30,12 +30,14 @@ cudaError_t launch_bm(const uint8_t* dL, size_t lp, const uint8_t* dR, size_t rp
             BM_LAUNCH_CHECK();
         }
         {
-            const int bd = std::min(256, (g.ndisp + 31) / 32 * 32);
-            int nseg = std::max(1, std::min(g.width1 / 64, (8 * num_sms * 2048 / bd) / std::max(1, H * ((g.ndisp + bd - 1) / bd))));
+            const int tx = g.ndisp / 4;                                   // threads along d (ndisp is a multiple of 16)
+            const int ty = std::max(1, 128 / tx);                         // rows per block
+            const int nby = (H + ty - 1) / ty;
+            int nseg = std::max(1, std::min(g.width1 / 64, (8 * num_sms * 16) / std::max(1, nby)));
             nseg = std::min(nseg, 64);
             const int seg_len = (g.width1 + nseg - 1) / nseg;
-            dim3 grid((g.ndisp + bd - 1) / bd, H, (g.width1 + seg_len - 1) / seg_len);
-            k_bm_hsad<<<grid, bd, 0, st>>>(PL, PR, g, seg_len, HS);
+            dim3 block(tx, ty), grid(1, nby, (g.width1 + seg_len - 1) / seg_len);
+            k_bm_hsad<<<grid, block, 0, st>>>(PL, PR, g, seg_len, HS);
             BM_LAUNCH_CHECK();
             dim3 gt((g.width1 + 255) / 256, H);
             k_bm_htext<<<gt, 256, 0, st>>>(PL, g, HT);
