@@ -164,6 +164,103 @@ static __global__ void __launch_bounds__(128) k_bm_match(const uint16_t* __restr
     }
 }
 
+// Same as k_bm_match with the lane <-> disparity mapping turned around for vector loads: lane l holds the NPL CONSECUTIVE indices
+// l*NPL .. l*NPL+NPL-1 (one 2*NPL-byte load per window row instead of NPL 2-byte loads); ndisp is a multiple of 16, so a lane is
+// either entirely inside [0, ndisp) or entirely outside.  NPL in {2, 4, 8}.
+template <int NPL>
+static __global__ void __launch_bounds__(128) k_bm_match_v(const uint16_t* __restrict__ HS, const int* __restrict__ HT, BmGeom g,
+                                                           int seg_rows, int16_t* __restrict__ disp)
+{
+    const int lane = threadIdx.x & 31;
+    const int x = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (x >= g.width1) return;
+    const int ya = blockIdx.y * seg_rows, yb = min(ya + seg_rows, g.H);
+    if (ya >= yb) return;
+    const int w2 = g.wsz >> 1, nd = g.ndisp;
+    const size_t rstride = size_t(g.width1) * nd;
+    const int dbase = lane * NPL;
+    const bool act = dbase < nd;
+    const uint16_t* hs = HS + size_t(x) * nd + (act ? dbase : 0);
+    auto cy = [&](int yy) { return min(max(yy, 0), g.H - 1); };
+    auto ldrow = [&](int yy, uint32_t (&w)[NPL / 2]) {
+        const uint16_t* p = hs + size_t(cy(yy)) * rstride;
+        if constexpr (NPL == 8) { const uint4 v = __ldg(reinterpret_cast<const uint4*>(p)); w[0] = v.x; w[1] = v.y; w[2] = v.z; w[3] = v.w; }
+        else if constexpr (NPL == 4) { const uint2 v = __ldg(reinterpret_cast<const uint2*>(p)); w[0] = v.x; w[1] = v.y; }
+        else { w[0] = __ldg(reinterpret_cast<const uint32_t*>(p)); }
+    };
+    int sad[NPL];
+#pragma unroll
+    for (int k = 0; k < NPL; k++) sad[k] = act ? 0 : 0x7FFFFFFF;
+    int tsum = 0;
+    for (int r = ya - w2; r <= ya + w2; r++) {
+        uint32_t w[NPL / 2];
+        ldrow(r, w);
+        if (act) {
+#pragma unroll
+            for (int k = 0; k < NPL / 2; k++) { sad[2 * k] += int(w[k] & 0xFFFFu); sad[2 * k + 1] += int(w[k] >> 16); }
+        }
+        tsum += HT[size_t(cy(r)) * g.width1 + x];
+    }
+    const bool in_row = g.lofs + x < g.W;
+    for (int y = ya; y < yb; y++) {
+        // prefetch the two rows of the slide
+        uint32_t wa[NPL / 2], wr[NPL / 2];
+        int ta = 0, tr = 0;
+        const bool more = y + 1 < yb;
+        if (more) {
+            ldrow(y + w2 + 1, wa); ldrow(y - w2, wr);
+            ta = HT[size_t(cy(y + w2 + 1)) * g.width1 + x]; tr = HT[size_t(cy(y - w2)) * g.width1 + x];
+        }
+        int m = sad[0];
+#pragma unroll
+        for (int k = 1; k < NPL; k++) m = min(m, sad[k]);
+        const int minsad = __reduce_min_sync(0xFFFFFFFFu, m);
+        int dc = 0x7FFFFFFF;
+#pragma unroll
+        for (int k = NPL - 1; k >= 0; k--) dc = sad[k] == minsad ? dbase + k : dc;      // first index inside the lane
+        const int mind = __reduce_min_sync(0xFFFFFFFFu, dc);
+        bool ok = tsum >= g.tex;
+        if (g.uniq > 0) {
+            const long long t64 = (long long)minsad + ((long long)minsad * g.uniq / 100);
+            const int thresh = int(min(t64, (long long)0x7FFFFFFE));
+            bool viol = false;
+#pragma unroll
+            for (int k = 0; k < NPL; k++) {
+                const int d = dbase + k;
+                viol = viol || (sad[k] <= thresh && (d < mind - 1 || d > mind + 1));
+            }
+            ok = ok && !__any_sync(0xFFFFFFFFu, viol);
+        }
+        const int jm = mind == 0 ? 1 : mind - 1, jp = mind == nd - 1 ? nd - 2 : mind + 1;
+        int vn = 0, vp = 0;
+#pragma unroll
+        for (int k = 0; k < NPL; k++) {
+            if (k == jm % NPL) vn = sad[k];
+            if (k == jp % NPL) vp = sad[k];
+        }
+        const int n = __shfl_sync(0xFFFFFFFFu, vn, jm / NPL), p = __shfl_sync(0xFFFFFFFFu, vp, jp / NPL);
+        if (lane == 0 && in_row) {
+            int out = g.FILTERED;
+            if (ok) {
+                const int den = p + n - 2 * minsad + abs(p - n);
+                const int q = den != 0 ? (p - n) * 256 / den : 0;            // C division: toward zero
+                out = ((nd - mind - 1 + g.mindisp) * 256 + q + 15) >> 4;
+            }
+            disp[size_t(y) * g.W + g.lofs + x] = int16_t(out);
+        }
+        if (more) {
+            if (act) {
+#pragma unroll
+                for (int k = 0; k < NPL / 2; k++) {
+                    sad[2 * k] += int(wa[k] & 0xFFFFu) - int(wr[k] & 0xFFFFu);
+                    sad[2 * k + 1] += int(wa[k] >> 16) - int(wr[k] >> 16);
+                }
+            }
+            tsum += ta - tr;
+        }
+    }
+}
+
 // getValidDisparityROI with full-image ROIs: everything outside [xmin, xmax) x [ymin, ymax) is FILTERED
 static __global__ void k_bm_mask(int16_t* __restrict__ disp, int W, int H, int xmin, int xmax, int ymin, int ymax, int FILTERED)
 {

@@ -48,7 +48,10 @@ cudaError_t launch_bm(const uint8_t* dL, size_t lp, const uint8_t* dR, size_t rp
             int nseg = std::max(1, std::min(H / 64, (16 * num_sms * 4) / std::max(1, g.width1)));
             const int seg_rows = (H + nseg - 1) / nseg;
             dim3 grid((g.width1 + 3) / 4, (H + seg_rows - 1) / seg_rows);
-            if (npl <= 1) k_bm_match<1><<<grid, 128, 0, st>>>(HS, HT, g, seg_rows, disp);
+            if (npl == 2) k_bm_match_v<2><<<grid, 128, 0, st>>>(HS, HT, g, seg_rows, disp);
+            else if (npl > 2 && npl <= 4) k_bm_match_v<4><<<grid, 128, 0, st>>>(HS, HT, g, seg_rows, disp);
+            else if (npl > 4 && npl <= 8) k_bm_match_v<8><<<grid, 128, 0, st>>>(HS, HT, g, seg_rows, disp);
+            else if (npl <= 1) k_bm_match<1><<<grid, 128, 0, st>>>(HS, HT, g, seg_rows, disp);
             else if (npl <= 2) k_bm_match<2><<<grid, 128, 0, st>>>(HS, HT, g, seg_rows, disp);
             else if (npl <= 4) k_bm_match<4><<<grid, 128, 0, st>>>(HS, HT, g, seg_rows, disp);
             else if (npl <= 8) k_bm_match<8><<<grid, 128, 0, st>>>(HS, HT, g, seg_rows, disp);
