@@ -78,8 +78,8 @@ HARNESS = os.path.join(HOST, "harness")
 
 def build_host(force: bool = False) -> str:
     """Builds the ROS/OpenCV-free harness around the C++ matcher adapter (host/matcherB200SGM.cpp)."""
-    srcs = [os.path.join(HOST, "harness.cpp"), os.path.join(HOST, "matcherB200SGM.cpp")]
-    deps = srcs + [os.path.join(HOST, f) for f in ("matcherB200SGM.h", "matcher_interface.h", "cv_stub.h")] + [LIB]
+    srcs = [os.path.join(HOST, "harness.cpp"), os.path.join(HOST, "matcherB200SGM.cpp"), os.path.join(HOST, "matcherB200BM.cpp")]
+    deps = srcs + [os.path.join(HOST, f) for f in ("matcherB200SGM.h", "matcherB200BM.h", "matcher_interface.h", "cv_stub.h")] + [LIB]
     if not force and os.path.exists(HARNESS) and all(os.path.getmtime(d) <= os.path.getmtime(HARNESS) for d in deps):
         return HARNESS
     cmd = ["g++", "-std=c++17", "-O2", "-DB200SGM_STANDALONE", "-I" + os.path.join(HERE, "..", "include"), "-I" + HOST,

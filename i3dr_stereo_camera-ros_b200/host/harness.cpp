@@ -3,6 +3,7 @@
 // src/init_stereo_matchers.cpp:39-66).  Reads two raw 8-bit images, writes the CV_32F disparity the node would receive.
 //
 //   harness <left.raw> <right.raw> <width> <height> <out.f32> minD D window uniq speckleRange speckleSize cap p1 p2 [fullDP]
+//           [algorithm: 0 = B200 SGM (default), 1 = B200 block matcher] [textureThreshold]
 #include <cstdio>
 #include <cstdlib>
 #include <fstream>
@@ -10,9 +11,12 @@
 #include <vector>
 
 #include "matcherB200SGM.h"
+#include "matcherB200BM.h"
 
 static AbstractStereoMatcher *matcher = nullptr;
 static MatcherB200SGM *b200sgm_matcher = nullptr;
+static MatcherB200BM *b200bm_matcher = nullptr;
+static int _stereo_algorithm = 0;   // 0: B200 SGM, 1: B200 block matcher
 static bool isFirstImagesRecevied = false;
 
 static int _min_disparity = 9, _disparity_range = 64, _correlation_window_size = 15, _uniqueness_ratio = 15;
@@ -34,14 +38,15 @@ static void updateMatcher()   // generate_disparity.cpp:241-261, same order
   matcher->setTextureThreshold(_texture_threshold);
   matcher->setPreFilterSize(_preFilterSize);
   matcher->setInterpolation(_interp);
-  b200sgm_matcher->setFullDP(_fullDP);   // the hook the reference never wired
+  if (_stereo_algorithm == 0) b200sgm_matcher->setFullDP(_fullDP);   // the hook the reference never wired
 }
 
 static void init_matcher(cv::Size image_size)   // generate_disparity.cpp:263-331
 {
   std::string empty_str = " ";
   b200sgm_matcher = new MatcherB200SGM(empty_str, image_size);
-  matcher = b200sgm_matcher;
+  b200bm_matcher = new MatcherB200BM(empty_str, image_size);
+  matcher = _stereo_algorithm == 1 ? static_cast<AbstractStereoMatcher *>(b200bm_matcher) : b200sgm_matcher;
   updateMatcher();
 }
 
@@ -85,12 +90,15 @@ int main(int argc, char **argv)
   _uniqueness_ratio = atoi(argv[9]); _speckle_range = atoi(argv[10]); _speckle_size = atoi(argv[11]);
   _preFilterCap = atoi(argv[12]); _p1 = float(atof(argv[13])); _p2 = float(atof(argv[14]));
   _fullDP = argc > 15 && atoi(argv[15]) != 0;
+  _stereo_algorithm = argc > 16 ? atoi(argv[16]) : 0;
+  if (argc > 17) _texture_threshold = atoi(argv[17]);
 
   // warm-up exactly like init_stereo_matchers.cpp:41-56: a 10x10 zero pair through setImages/match/getDisparity
   {
     cv::Mat l0 = cv::Mat::zeros(cv::Size(10, 10), CV_8UC1), r0 = cv::Mat::zeros(cv::Size(10, 10), CV_8UC1);
     cv::Mat d0 = stereo_match(l0, r0);
-    if (d0.empty()) { std::cerr << "warm-up failed" << std::endl; return 1; }
+    // the block matcher refuses a 10x10 pair when the window does not fit, exactly like cv::StereoBM throws in the reference
+    if (d0.empty() && _stereo_algorithm == 0) { std::cerr << "warm-up failed" << std::endl; return 1; }
   }
   cv::Mat left(cv::Size(W, H), CV_8UC1), right(cv::Size(W, H), CV_8UC1);
   if (!read_raw(argv[1], left) || !read_raw(argv[2], right)) { std::cerr << "cannot read input" << std::endl; return 2; }
