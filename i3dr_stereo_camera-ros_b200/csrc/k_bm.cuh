@@ -261,6 +261,107 @@ static __global__ void __launch_bounds__(128) k_bm_match_v(const uint16_t* __res
     }
 }
 
+// Packed variant of k_bm_match_v for window sums that fit 16 bits ((blockSize + 1) * blockSize * 2 * preFilterCap <= 65535, i.e.
+// every window the reference's launch files use): the NPL sums of a lane live in NPL/2 16x2 registers (slide = two packed
+// adds), and the first minimum comes out of ONE warp reduction over keys (sum << 16 | index).  NPL in {2, 4, 8}.
+template <int NPL>
+static __global__ void __launch_bounds__(128) k_bm_match_p(const uint16_t* __restrict__ HS, const int* __restrict__ HT, BmGeom g,
+                                                           int seg_rows, int16_t* __restrict__ disp)
+{
+    constexpr int NW = NPL / 2;
+    const int lane = threadIdx.x & 31;
+    const int x = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (x >= g.width1) return;
+    const int ya = blockIdx.y * seg_rows, yb = min(ya + seg_rows, g.H);
+    if (ya >= yb) return;
+    const int w2 = g.wsz >> 1, nd = g.ndisp;
+    const size_t rstride = size_t(g.width1) * nd;
+    const int dbase = lane * NPL;
+    const bool act = dbase < nd;
+    const uint16_t* hs = HS + size_t(x) * nd + (act ? dbase : 0);
+    auto cy = [&](int yy) { return min(max(yy, 0), g.H - 1); };
+    auto ldrow = [&](int yy, uint32_t (&w)[NW]) {
+        const uint16_t* p = hs + size_t(cy(yy)) * rstride;
+        if constexpr (NPL == 8) { const uint4 v = __ldg(reinterpret_cast<const uint4*>(p)); w[0] = v.x; w[1] = v.y; w[2] = v.z; w[3] = v.w; }
+        else if constexpr (NPL == 4) { const uint2 v = __ldg(reinterpret_cast<const uint2*>(p)); w[0] = v.x; w[1] = v.y; }
+        else { w[0] = __ldg(reinterpret_cast<const uint32_t*>(p)); }
+    };
+    uint32_t s2[NW];
+#pragma unroll
+    for (int k = 0; k < NW; k++) s2[k] = 0;
+    int tsum = 0;
+    for (int r = ya - w2; r <= ya + w2; r++) {
+        uint32_t w[NW];
+        ldrow(r, w);
+#pragma unroll
+        for (int k = 0; k < NW; k++) s2[k] += w[k];
+        tsum += HT[size_t(cy(r)) * g.width1 + x];
+    }
+    if (!act) {
+#pragma unroll
+        for (int k = 0; k < NW; k++) s2[k] = 0xFFFFFFFFu;
+    }
+    const bool in_row = g.lofs + x < g.W;
+    for (int y = ya; y < yb; y++) {
+        uint32_t wa[NW], wr[NW];
+        int ta = 0, tr = 0;
+        const bool more = y + 1 < yb;
+        if (more) {
+            ldrow(y + w2 + 1, wa); ldrow(y - w2, wr);
+            ta = HT[size_t(cy(y + w2 + 1)) * g.width1 + x]; tr = HT[size_t(cy(y - w2)) * g.width1 + x];
+        }
+        // key = sum << 16 | index: the minimum key is the minimum sum and, among equals, the first index
+        uint32_t key = 0xFFFFFFFFu;
+#pragma unroll
+        for (int k = 0; k < NW; k++) {
+            const uint32_t klo = (s2[k] << 16) | uint32_t(dbase + 2 * k), khi = (s2[k] & 0xFFFF0000u) | uint32_t(dbase + 2 * k + 1);
+            key = min(key, min(klo, khi));
+        }
+        key = __reduce_min_sync(0xFFFFFFFFu, key);
+        const int minsad = int(key >> 16), mind = int(key & 0xFFFFu);
+        bool ok = tsum >= g.tex;
+        if (g.uniq > 0) {
+            const long long t64 = (long long)minsad + ((long long)minsad * g.uniq / 100);
+            const uint32_t thr2 = uint32_t(min(t64, (long long)0xFFFE)) * 0x10001u;
+            uint32_t viol = 0;
+#pragma unroll
+            for (int k = 0; k < NW; k++) {
+                uint32_t le = __vcmpleu2(s2[k], thr2);                      // 0xFFFF per half with sum <= thresh
+                const int d0 = dbase + 2 * k;
+                if (unsigned(d0 - mind + 1) < 3u) le &= 0xFFFF0000u;        // indices mind-1 .. mind+1 are exempt
+                if (unsigned(d0 + 1 - mind + 1) < 3u) le &= 0x0000FFFFu;
+                viol |= le;
+            }
+            ok = ok && !__any_sync(0xFFFFFFFFu, viol != 0);
+        }
+        const int jm = mind == 0 ? 1 : mind - 1, jp = mind == nd - 1 ? nd - 2 : mind + 1;
+        uint32_t wn = 0, wp = 0;
+#pragma unroll
+        for (int k = 0; k < NW; k++) {
+            if (k == (jm % NPL) / 2) wn = s2[k];
+            if (k == (jp % NPL) / 2) wp = s2[k];
+        }
+        wn = __shfl_sync(0xFFFFFFFFu, wn, jm / NPL); wp = __shfl_sync(0xFFFFFFFFu, wp, jp / NPL);
+        const int n = int((jm & 1) ? (wn >> 16) : (wn & 0xFFFFu)), p = int((jp & 1) ? (wp >> 16) : (wp & 0xFFFFu));
+        if (lane == 0 && in_row) {
+            int out = g.FILTERED;
+            if (ok) {
+                const int den = p + n - 2 * minsad + abs(p - n);
+                const int q = den != 0 ? (p - n) * 256 / den : 0;            // C division: toward zero
+                out = ((nd - mind - 1 + g.mindisp) * 256 + q + 15) >> 4;
+            }
+            disp[size_t(y) * g.W + g.lofs + x] = int16_t(out);
+        }
+        if (more) {
+            if (act) {
+#pragma unroll
+                for (int k = 0; k < NW; k++) s2[k] = s2[k] + wa[k] - wr[k];
+            }
+            tsum += ta - tr;
+        }
+    }
+}
+
 // getValidDisparityROI with full-image ROIs: everything outside [xmin, xmax) x [ymin, ymax) is FILTERED
 static __global__ void k_bm_mask(int16_t* __restrict__ disp, int W, int H, int xmin, int xmax, int ymin, int ymax, int FILTERED)
 {

@@ -48,7 +48,11 @@ cudaError_t launch_bm(const uint8_t* dL, size_t lp, const uint8_t* dR, size_t rp
             int nseg = std::max(1, std::min(H / 64, (16 * num_sms * 4) / std::max(1, g.width1)));
             const int seg_rows = (H + nseg - 1) / nseg;
             dim3 grid((g.width1 + 3) / 4, (H + seg_rows - 1) / seg_rows);
-            if (npl == 2) k_bm_match_v<2><<<grid, 128, 0, st>>>(HS, HT, g, seg_rows, disp);
+            const bool pack16 = (long long)(g.wsz + 1) * g.wsz * 2 * g.cap <= 65535 && g.ndisp <= 65535;
+            if (pack16 && npl == 2) k_bm_match_p<2><<<grid, 128, 0, st>>>(HS, HT, g, seg_rows, disp);
+            else if (pack16 && npl > 2 && npl <= 4) k_bm_match_p<4><<<grid, 128, 0, st>>>(HS, HT, g, seg_rows, disp);
+            else if (pack16 && npl > 4 && npl <= 8) k_bm_match_p<8><<<grid, 128, 0, st>>>(HS, HT, g, seg_rows, disp);
+            else if (npl == 2) k_bm_match_v<2><<<grid, 128, 0, st>>>(HS, HT, g, seg_rows, disp);
             else if (npl > 2 && npl <= 4) k_bm_match_v<4><<<grid, 128, 0, st>>>(HS, HT, g, seg_rows, disp);
             else if (npl > 4 && npl <= 8) k_bm_match_v<8><<<grid, 128, 0, st>>>(HS, HT, g, seg_rows, disp);
             else if (npl <= 1) k_bm_match<1><<<grid, 128, 0, st>>>(HS, HT, g, seg_rows, disp);
