@@ -221,7 +221,9 @@ static __global__ void __launch_bounds__(128) k_bm_match_v(const uint16_t* __res
         const int mind = __reduce_min_sync(0xFFFFFFFFu, dc);
         bool ok = tsum >= g.tex;
         if (g.uniq > 0) {
-            const long long t64 = (long long)minsad + ((long long)minsad * g.uniq / 100);
+            // minsad <= 255 * 255 * 126 < 2^23: the product fits 32 bits for uniquenessRatio <= 500
+            const long long t64 = g.uniq <= 500 ? (long long)(uint32_t(minsad) + uint32_t(minsad) * uint32_t(g.uniq) / 100u)
+                                                : (long long)minsad + ((long long)minsad * g.uniq / 100);
             const int thresh = int(min(t64, (long long)0x7FFFFFFE));
             bool viol = false;
 #pragma unroll
@@ -321,7 +323,9 @@ static __global__ void __launch_bounds__(128) k_bm_match_p(const uint16_t* __res
         const int minsad = int(key >> 16), mind = int(key & 0xFFFFu);
         bool ok = tsum >= g.tex;
         if (g.uniq > 0) {
-            const long long t64 = (long long)minsad + ((long long)minsad * g.uniq / 100);
+            // minsad < 2^16: the product fits 32 bits for any uniquenessRatio below 2^16 (unsigned division by a constant)
+            const long long t64 = g.uniq < 65536 ? (long long)(uint32_t(minsad) + uint32_t(minsad) * uint32_t(g.uniq) / 100u)
+                                                 : (long long)minsad + ((long long)minsad * g.uniq / 100);
             const uint32_t thr2 = uint32_t(min(t64, (long long)0xFFFE)) * 0x10001u;
             uint32_t viol = 0;
 #pragma unroll
