@@ -46,6 +46,7 @@ def parse():
     ap.add_argument("--lanes", type=int, default=4, help="frames in flight per GPU")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-side", action="store_true", help="skip the c1/c2/cL/c5 block and the plugin-call measurement")
     ap.add_argument("--cpu-frames", type=int, default=0, help="frames in the CPU sample (default: one per core)")
     return ap.parse_args()
 
@@ -79,6 +80,35 @@ def cpu_sample(cfg, frames, n_threads):
         list(ex.map(work, frames))
         dt = time.perf_counter() - t0
     return len(frames) / dt, kind, dt
+
+
+def reference_outputs(cfg, pairs, n_threads):
+    """cv::StereoSGBM (cv2, the reference's call sequence) on every pair, frame-parallel; the oracle port when cv2 is absent."""
+    from concurrent.futures import ThreadPoolExecutor
+    from oracle import cv2_reference as ref
+    p = cfg.params
+    if ref.have_cv2():
+        import cv2
+        cv2.setNumThreads(1)
+        tl = threading.local()
+
+        def work(fr):
+            if not hasattr(tl, "m"):
+                tl.m = ref.make_matcher(p)
+            return tl.m.compute(fr[0], fr[1])
+        kind = "cv2 %s" % cv2.__version__
+    else:
+        from oracle import oracle
+
+        def work(fr):
+            return oracle.compute(fr[0], fr[1], p)
+        kind = "oracle port"
+    with ThreadPoolExecutor(max(1, n_threads)) as ex:
+        return list(ex.map(work, pairs)), kind
+
+
+def count_equal(outs, refs):
+    return sum(int(np.array_equal(o, r)) for o, r in zip(outs, refs))
 
 
 def cpu_model():
@@ -119,6 +149,16 @@ def run_reference(args, cfg):
         "gpu_launches": 0,
     }
     emit(line)
+
+
+def launch_summary_path(name):
+    """Newest committed ncu launch summary of a config (profiles/rN_launch_summary_<config>.json)."""
+    import glob
+    key = "c3" if name in ("c4", "c5") else name
+    cands = sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_launch_summary_%s.json" % key)))
+    if not cands:
+        raise FileNotFoundError(key)
+    return cands[-1]
 
 
 def workload(cfg, frames, lanes):
@@ -287,6 +327,21 @@ def run_b200(args, cfg):
                "h2d_bytes_per_step": 2 * W * H * NF * world, "d2h_bytes_per_step": 2 * W * H * NF * world,
                "api": "b200sgm_enqueue/b200sgm_wait, pinned host buffers, %d lanes" % lanes}
 
+    # ---- parity of EVERY frame of the timed runs (all lanes; device-resident outputs and the e2e host outputs) against
+    # cv::StereoSGBM on the host cores; a mismatch fails the run (exit code 3 after the JSON line)
+    cores = os.cpu_count() or 1
+    pairs = [(hostL[i].numpy(), hostR[i].numpy()) for i in range(n_unique)]
+    refs, ref_kind = reference_outputs(cfg, pairs, max(1, cores // world))
+    dev_out = devD.cpu().numpy()
+    n_checked = NF + (NF if e2e is not None else 0)
+    n_ok = count_equal([dev_out[i] for i in range(NF)], [refs[i % n_unique] for i in range(NF)])
+    if e2e is not None:
+        n_ok += count_equal([hostD[i].numpy() for i in range(NF)], [refs[i % n_unique] for i in range(NF)])
+    pt = torch.tensor([n_checked, n_ok], dtype=torch.int64, device=dev)
+    if world > 1:
+        dist.all_reduce(pt, op=dist.ReduceOp.SUM)
+    parity_checked, parity_ok = int(pt[0].item()), int(pt[1].item())
+
     # ---- roofline of the dominant stage: stage events on one lane, frames back to back (rank 0)
     roofline, stages = None, None
     if rank == 0:
@@ -321,13 +376,13 @@ def run_b200(args, cfg):
         # measured DRAM traffic per launch from the committed ncu launch list of this config (profiles/), if present
         prof, traffic, kern_traffic = None, None, {}
         try:
-            prof = json.load(open(os.path.join(ROOT, "profiles", "r1_launch_summary_%s.json" % cfg.name)))
+            prof = json.load(open(launch_summary_path(cfg.name)))
             traffic = prof.get("frame_dram_bytes")
             for k in prof.get("kernels", []):
                 kern_traffic.setdefault(k["kernel"].split("<")[0], []).append(k.get("dram_read_bytes", 0) + k.get("dram_write_bytes", 0))
         except Exception:
             pass
-        stage_kernel = {"cost": "k_cost_tile2", "horizontal": "k_horiz", "vertical_wta": "k_vert"}
+        stage_kernel = {"cost": "k_cost_tile2", "horizontal": "k_horiz", "vertical_wta": "k_sweep"}
         # algorithmic int16 ops per cell of each volume stage (BT 21 + block sum 4; 9 per path; WTA 5)
         n_h, n_v = 2, (6 if p.mode else 3)
         stage_ops = {"cost": 25 * W1 * H * D, "horizontal": 9 * n_h * W1 * H * D, "vertical_wta": (9 * n_v + 5) * W1 * H * D}
@@ -435,6 +490,21 @@ def run_b200(args, cfg):
         except Exception as e:  # pragma: no cover
             bm = {"error": str(e)}
 
+    # ---- the other BASELINE.json configurations (+ cL, the reference's launch default), N = 1 only: device-resident fps,
+    # stage times, roofline fractions and parity of every timed frame against cv::StereoSGBM
+    side, plugin = None, None
+    if rank == 0 and world == 1 and not args.no_side:
+        side = {}
+        for name in ("c1", "c2", "cL", "c5"):
+            try:
+                side[name] = side_config(torch, dev, CONFIGS[name], alu[0] if roofline else None, hbm_peak if roofline else 6457.1)
+            except Exception as e:  # pragma: no cover
+                side[name] = {"error": repr(e)}
+        try:
+            plugin = plugin_call(cfg, hostL, hostR, refs, n_unique)
+        except Exception as e:  # pragma: no cover
+            plugin = {"error": repr(e)}
+
     # ---- CPU baseline beside it (rank 0, N=1 only)
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -451,12 +521,138 @@ def run_b200(args, cfg):
             "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "u16", "data": "synthetic", "config": workload(cfg, NF, lanes),
             "gpix_disp_per_s": fps * cfg.gpix_disp, "parity_checked_vs_golden_crc": checked,
+            "parity_frames_checked": parity_checked, "parity_frames_ok": parity_ok, "parity_reference": ref_kind,
+            "configs": side, "e2e_plugin": plugin,
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu, "rectify": rect, "stereobm": bm,
         }
         emit(line)
     eng.close()
     if world > 1:
         dist.destroy_process_group()
+    if parity_ok != parity_checked:
+        sys.stderr.write("bench.py: PARITY FAILURE: %d of %d frames differ from %s\n" % (parity_checked - parity_ok, parity_checked, ref_kind))
+        raise SystemExit(3)
+
+
+def side_config(torch, dev, cfg, alu_peak, hbm_peak, frames=8, lanes=4, reps=4):
+    """One of the other configurations on the same GPU: `frames` distinct pairs resident in HBM cycled over `lanes` lanes
+    (the lanes' cost volumes exceed L2 for every config but c1, whose 4 x 71 MB of volumes still do), CUDA events around
+    `reps` passes, stage events on one lane, every output compared with cv::StereoSGBM."""
+    p = cfg.params
+    W, H, D = cfg.width, cfg.height, p.numDisparities
+    eng = b200sgm.Engine(dev.index or 0, W, H, D, lanes, p)
+    try:
+        pairs = [synth.make_pair(W, H, D, p.minDisparity, 1000 + i) for i in range(frames)]
+        hL = torch.stack([torch.from_numpy(a) for a, _ in pairs]).pin_memory()
+        hR = torch.stack([torch.from_numpy(b) for _, b in pairs]).pin_memory()
+        dL, dR = hL.to(dev), hR.to(dev)
+        dD = torch.empty((frames, H, W), dtype=torch.int16, device=dev)
+        streams = [torch.cuda.Stream(device=dev) for _ in range(lanes)]
+        out = {"workload": workload(cfg, frames, lanes)["workload"]}
+
+        def one_pass():
+            for i in range(frames):
+                ln = i % lanes
+                eng.compute_device(ln, dL[i].data_ptr(), W, dR[i].data_ptr(), W, W, H, dD[i].data_ptr(), W * 2, stream=streams[ln].cuda_stream)
+
+        if cfg.name == "c5":
+            # c3 + processDisparity + reprojection through the host-buffer call b200sgm_compute_xyz (pinned buffers);
+            # 120 MB per frame cross PCIe (2 x 5 MB in; disparity 10, dmat 20, depth 20, cloud <= 80 MB out)
+            cam = b200sgm.C5_CAMERA
+            from oracle import oracle
+            q = oracle.calc_q(cam["fx"], cam["cx"], cam["cxr"], cam["cy"], cam["p14"])
+            fT = np.float32(0.3 * 2400.0)
+            min_disp = float(fT / np.float32(cam["depth_max"]))
+            eng.compute_xyz(pairs[0][0], pairs[0][1], q, cam["depth_min"], cam["depth_max"], min_disp, float("inf"))
+            t0 = time.perf_counter()
+            n_pts = 0
+            for i in range(frames):
+                disp, dmat, depth, pts, n = eng.compute_xyz(hL[i].numpy(), hR[i].numpy(), q, cam["depth_min"], cam["depth_max"], min_disp, float("inf"))
+                n_pts += n
+            dt = (time.perf_counter() - t0) / frames
+            by = 2 * W * H + W * H * (2 + 4 + 4) + 16 * (n_pts // frames)
+            out.update({"api": "b200sgm_compute_xyz, host buffers, synchronous, 1 lane", "ms_per_frame": dt * 1e3, "frames_per_s": 1.0 / dt,
+                        "points_per_frame": n_pts // frames, "pcie_bytes_per_frame": by, "pcie_gbs": by / dt / 1e9,
+                        "note": "PCIe-bound: the roof is the host link (about 25 GB/s per direction for pageable numpy outputs)"})
+            refs, kind = reference_outputs(cfg, pairs[-1:], 1)
+            out["parity_frames_checked"], out["parity_frames_ok"], out["parity_reference"] = 1, count_equal([disp], refs), kind
+            return out
+        for _ in range(2):
+            one_pass()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        main = torch.cuda.current_stream()
+        e0.record(main)
+        for st in streams:
+            st.wait_event(e0)
+        for _ in range(reps):
+            one_pass()
+        for st in streams:
+            ev = torch.cuda.Event(); ev.record(st); main.wait_event(ev)
+        e1.record(main)
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / (reps * frames)
+        eng.profile(True); eng.stage_times(0)
+        for i in range(frames):
+            eng.compute_device(0, dL[i].data_ptr(), W, dR[i].data_ptr(), W, W, H, dD[i].data_ptr(), W * 2, stream=0)
+        st_ms, nfr = eng.stage_times(0)
+        eng.profile(False)
+        stages = {k: v / max(nfr, 1) for k, v in st_ms.items()}
+        frame_ms = sum(stages.values())
+        W1 = p.w1(W)
+        R = 8 if p.mode else 5
+        alg_ops = W1 * H * D * (30 + 9 * R)
+        alg_bytes = 4 * W * H if p.mode == 0 else 4 * W * H + 4 * W1 * H * D
+        tops = alg_ops / (frame_ms * 1e-3) / 1e12
+        traffic = None
+        try:
+            traffic = json.load(open(launch_summary_path(cfg.name))).get("frame_dram_bytes")
+        except Exception:
+            pass
+        one_pass()
+        torch.cuda.synchronize()
+        refs, kind = reference_outputs(cfg, pairs, os.cpu_count() or 1)
+        got = dD.cpu().numpy()
+        out.update({"frames_per_s": 1e3 / ms, "ms_per_frame_pipelined": ms, "stage_ms_per_frame": stages, "single_lane_ms": frame_ms,
+                    "roofline": {"bound": "alu", "achieved": tops, "peak": alu_peak, "unit": "Tops/s (elementary int16 ops)",
+                                 "frac": tops / alu_peak if alu_peak else None, "traffic": traffic,
+                                 "hbm_frac_algorithmic": alg_bytes / (frame_ms * 1e-3) / 1e9 / hbm_peak,
+                                 "hbm_frac_traffic": traffic / (frame_ms * 1e-3) / 1e9 / hbm_peak if traffic else None},
+                    "parity_frames_checked": frames, "parity_frames_ok": count_equal([got[i] for i in range(frames)], refs),
+                    "parity_reference": kind, "warning": eng.last_warning})
+        return out
+    finally:
+        eng.close()
+
+
+def plugin_call(cfg, hostL, hostR, refs, n_unique, frames=8):
+    """The call the ROS node makes: MatcherB200SGM::setImages / match / getDisparity (host/matcherB200SGM.cpp) on pageable
+    cv::Mat-like buffers, one frame at a time, one lane -- timed through the C++ harness loop (host/harness --bench), which runs
+    init_matcher + updateMatcher + stereo_match of generate_disparity.cpp:241-368 around the adapter."""
+    import importlib
+    import tempfile
+    b = importlib.import_module("i3dr_stereo_camera-ros_b200.build")
+    harness = b.build_host()
+    p = cfg.params
+    W, H = cfg.width, cfg.height
+    with tempfile.TemporaryDirectory() as td:
+        lp, rp, op = os.path.join(td, "l.raw"), os.path.join(td, "r.raw"), os.path.join(td, "d.f32")
+        hostL[0].numpy().tofile(lp); hostR[0].numpy().tofile(rp)
+        args = [harness, lp, rp, W, H, op, p.minDisparity, p.numDisparities, p.blockSize, p.uniquenessRatio, p.speckleRange,
+                p.speckleWindowSize, p.preFilterCap, p.P1, p.P2, p.mode, 0, 10, "--bench", frames]
+        r = subprocess.run([str(a) for a in args], capture_output=True, text=True, timeout=600)
+        if r.returncode != 0:
+            return {"error": r.stderr[-400:]}
+        ms = None
+        for line in r.stderr.splitlines():
+            if line.startswith("bench_ms_per_frame"):
+                ms = float(line.split()[1])
+        got = np.fromfile(op, np.float32).reshape(H, W)
+        ok = bool(np.array_equal(got, refs[0].astype(np.float32)))
+    return {"api": "MatcherB200SGM::setImages/match/getDisparity via host/harness (b200sgm_compute_f32, pageable buffers, 1 lane)",
+            "ms_per_frame": ms, "frames_per_s": 1e3 / ms if ms else None, "frames": frames, "matches_reference": ok,
+            "h2d_bytes_per_frame": 2 * W * H, "d2h_bytes_per_frame": 4 * W * H,
+            "note": "compare with the reference's stereo_match() on cv::StereoSGBM: cpu_baseline single-frame latency = cores / value"}
 
 
 _REAL_STDOUT = None

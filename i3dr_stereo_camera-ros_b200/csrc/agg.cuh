@@ -1,10 +1,11 @@
-// Host launchers of the aggregation stages (k_horiz + cooperative k_vert, or the generic per-direction kernels),
+// Host launchers of the aggregation stages (k_horiz + cooperative k_sweep, or the generic per-direction kernels),
 // templated on N; instantiated once per N in agg_n*.cu so that the instantiations compile in parallel.
 #pragma once
 #include "engine_internal.h"
 #include "k_path.cuh"
 #include "k_wta.cuh"
 #include "k_fused.cuh"
+#include "k_sweep.cuh"
 
 template <int N>
 int launch_paths_generic(b200sgm_engine* h, Lane& ln, const Eff& e, cudaStream_t st)
@@ -32,58 +33,69 @@ int launch_paths_generic(b200sgm_engine* h, Lane& ln, const Eff& e, cudaStream_t
     return B200SGM_OK;
 }
 
-// ---- fused path: k_horiz + cooperative k_vert ---------------------------------------------------------
-struct VertPlan { bool ok; int nstrips, twmax; size_t smem; };
+// ---- fused path: k_horiz + cooperative k_sweep --------------------------------------------------------
+struct SweepPlan { bool ok; int nstrips, twmax; size_t smem; };
 
-inline VertPlan plan_vert(const b200sgm_engine* h, const Eff& e)
+template <int N> struct SweepCfg { static constexpr int RING = N >= 8 ? 4 : 8, LDG = N >= 8 ? 2 : 4, MAXT = sweep_max_threads(N); };
+
+template <int N>
+inline SweepPlan plan_sweep(const b200sgm_engine* h, const Eff& e, bool wta)
 {
-    VertPlan p{false, 0, 0, 0};
-    if (e.W1 < 2) return p;
+    SweepPlan p{false, 0, 0, 0};
+    if (e.W1 < 4) return p;
     int n = std::min(h->num_sms, e.W1 / 2);
     n = std::min(n, kMaxStrips);
-    int tw = (e.W1 + n - 1) / n;
-    if (tw > kVertMaxWarps) return p;      // wider than one co-resident wave of strips: use the hybrid path
+    const int tw = (e.W1 + n - 1) / n;
+    // wider than one co-resident wave of strips (or than a CTA has warps): use the hybrid path
+    if (tw > kSweepMaxTW || 32 * (2 * tw + 1) > SweepCfg<N>::MAXT) return p;
     p.nstrips = n; p.twmax = tw;
-    p.smem = vert_smem_bytes(tw, e.Dp);
-    p.ok = p.smem <= 200 * 1024;
+    p.smem = sweep_smem_bytes(tw, e.Dp, SweepCfg<N>::RING, SweepCfg<N>::LDG, wta);
+    p.ok = p.smem <= size_t(h->max_smem_optin);
     return p;
 }
 
 template <int N, bool UP, bool DO_WTA, bool FULL, bool CLAMP_EACH>
-int launch_vert_t(b200sgm_engine* h, Lane& ln, const Eff& e, const VertPlan& vp, cudaStream_t st)
+int launch_sweep_t(b200sgm_engine* h, Lane& ln, const Eff& e, const SweepPlan& vp, cudaStream_t st)
 {
-    VertGeom g;
+    SweepGeom g;
     g.w = WtaGeom{e.W, e.H, e.W1, e.minX1, e.minD, e.D, e.Dp, e.uniq, e.d12, e.INVALID};
     g.nstrips = vp.nstrips; g.twmax = vp.twmax;
     g.P1 = e.P1; g.P2 = e.P2;
     g.spin_limit = (long long)h->clock_khz * 500;   // ~0.5 s of SM clock ticks
     { static const int dbg = [] { const char* v = getenv("B200SGM_DEBUG_VERT"); return v ? atoi(v) : 0; }(); g.debug_flags = dbg; }
-    // two agent warps per CTA when they fit next to the column warps (1024 threads per CTA)
-    int nthreads = (DO_WTA ? 64 : 32) * vp.twmax;
-    { static const bool no_agents = getenv("B200SGM_NO_AGENTS") != nullptr; g.agents = (!no_agents && nthreads + 64 <= 1024) ? 1 : 0; }
-    if (g.agents) nthreads += 64;
-    auto kern = k_vert<N, UP, DO_WTA, FULL, CLAMP_EACH>;
-    CUDA_TRY(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(vp.smem)));
-    CUDA_TRY(h, cudaMemsetAsync(ln.xbuf, 0, size_t(2) * vp.nstrips * kXbufGen * (e.Dp / 2) * sizeof(uint2), st));
+    const int nthreads = 32 * ((DO_WTA ? 2 : 1) * vp.twmax + 1);
+    auto kern = k_sweep<N, SweepCfg<N>::RING, SweepCfg<N>::LDG, UP, DO_WTA, FULL, CLAMP_EACH>;
+    {
+        static std::atomic<unsigned long long> attr_done{0};   // per instantiation and device: raise the dynamic shared-memory limit once
+        const unsigned long long bit = 1ull << (h->device & 63);
+        if (!(attr_done.load() & bit)) {
+            CUDA_TRY(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_smem_optin));
+            attr_done.fetch_or(bit);
+        }
+    }
+    CUDA_TRY(h, cudaMemsetAsync(ln.xbuf, 0, sweep_xbuf_bytes(vp.nstrips, e.Dp), st));
     const uint16_t* Cp = ln.C; uint16_t* Sp = ln.S; int16_t* dp = ln.disp_wta; uint32_t* kp = ln.disp2key;
     uint2* xb = ln.xbuf; int* er = ln.d_err;
     void* args[] = {(void*)&Cp, (void*)&Sp, (void*)&g, (void*)&dp, (void*)&kp, (void*)&xb, (void*)&er};
     {
-        std::lock_guard<std::mutex> lk(h->mu);
-        if (h->coop_prev[0]) CUDA_TRY(h, cudaStreamWaitEvent(st, h->coop_prev[0], 0));
+        CoopGate& gate = coop_gate(h->device);
+        std::lock_guard<std::mutex> lk(gate.mu);
+        if (!gate.ev[0]) {
+            CUDA_TRY(h, cudaEventCreateWithFlags(&gate.ev[0], cudaEventDisableTiming));
+            CUDA_TRY(h, cudaEventCreateWithFlags(&gate.ev[1], cudaEventDisableTiming));
+        }
+        if (gate.any) CUDA_TRY(h, cudaStreamWaitEvent(st, gate.ev[gate.idx], 0));
         CUDA_TRY(h, cudaLaunchCooperativeKernel((void*)kern, dim3(vp.nstrips), dim3(nthreads), args, vp.smem, st));
         h->launches++;
-        cudaEvent_t ev = ln.coop_ev[ln.coop_idx];
-        ln.coop_idx ^= 1;
-        CUDA_TRY(h, cudaEventRecord(ev, st));
-        h->coop_prev[1] = h->coop_prev[0];
-        h->coop_prev[0] = ev;
+        gate.idx ^= 1;
+        CUDA_TRY(h, cudaEventRecord(gate.ev[gate.idx], st));
+        gate.any = true;
     }
     return B200SGM_OK;
 }
 
 template <int N, bool UP, bool DO_WTA>
-int launch_vert(b200sgm_engine* h, Lane& ln, const Eff& e, const VertPlan& vp, cudaStream_t st)
+int launch_sweep(b200sgm_engine* h, Lane& ln, const Eff& e, const SweepPlan& vp, cudaStream_t st)
 {
     const bool full = e.Dp == e.D && e.D == 64 * N;
     // worst-case cost of a cell: bs^2 * (2*ftzero + 63) (A.5 value bounds); one final clamp is enough when
@@ -93,10 +105,10 @@ int launch_vert(b200sgm_engine* h, Lane& ln, const Eff& e, const VertPlan& vp, c
     // S_h arrives unclamped (<= 2*cmax) in MODE_SGBM / first sweep, clamped (<= kMaxCost) in the second sweep of MODE_HH
     const bool clamp_each = kMaxCost + 3 * cmax > 65535 || 5 * cmax > 65535;
     if (full) {
-        if (clamp_each) return launch_vert_t<N, UP, DO_WTA, true, true>(h, ln, e, vp, st);
-        return launch_vert_t<N, UP, DO_WTA, true, false>(h, ln, e, vp, st);
+        if (clamp_each) return launch_sweep_t<N, UP, DO_WTA, true, true>(h, ln, e, vp, st);
+        return launch_sweep_t<N, UP, DO_WTA, true, false>(h, ln, e, vp, st);
     }
-    return launch_vert_t<N, UP, DO_WTA, false, true>(h, ln, e, vp, st);
+    return launch_sweep_t<N, UP, DO_WTA, false, true>(h, ln, e, vp, st);
 }
 
 template <int N>
@@ -111,12 +123,19 @@ int launch_fused(b200sgm_engine* h, Lane& ln, const Eff& e, cudaStream_t st, boo
         const long long bs = 2 * e.SW2 + 1;
         const bool clamp = !full || 2 * (bs * bs * (2 * e.ftzero + 63) + e.P2) > 65535;
         auto kern = !full ? k_horiz<N, false, true> : (clamp ? k_horiz<N, true, true> : k_horiz<N, true, false>);
-        CUDA_TRY(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(hsmem)));
-        kern<<<(e.H + wpb - 1) / wpb, 32 * wpb, hsmem, st>>>(ln.C, ln.S, ln.ckpt, e.W1, e.H, e.Dp, e.P1, e.P2);
+        static std::atomic<unsigned long long> attr_done[3] = {{0}, {0}, {0}};
+        const int ki = !full ? 0 : (clamp ? 1 : 2);
+        const unsigned long long bit = 1ull << (h->device & 63);
+        if (!(attr_done[ki].load() & bit)) {
+            CUDA_TRY(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+            attr_done[ki].fetch_or(bit);
+        }
+        kern<<<(e.H + wpb - 1) / wpb, 32 * wpb, hsmem, st>>>(ln.C, ln.S, ln.ckpt, e.W1, e.H, e.Dp, e.D, e.P1, e.P2,
+                                                              reinterpret_cast<unsigned*>(ln.d_err) + 3);
         LAUNCH_CHECK(h);
     }
     prof_mark(h, ln, 3, st);
-    VertPlan vp = plan_vert(h, e);
+    const SweepPlan vp = plan_sweep<N>(h, e, true);
     if (hybrid || !vp.ok) {
         static const int dirs_sgbm[3][2] = {{1, 1}, {0, 1}, {-1, 1}};
         static const int dirs_hh[6][2] = {{1, 1}, {0, 1}, {-1, 1}, {-1, -1}, {0, -1}, {1, -1}};
@@ -139,15 +158,13 @@ int launch_fused(b200sgm_engine* h, Lane& ln, const Eff& e, cudaStream_t st, boo
     }
     int rc;
     if (e.mode == B200SGM_MODE_HH) {
-        rc = launch_vert<N, false, false>(h, ln, e, vp, st);
+        rc = launch_sweep<N, false, false>(h, ln, e, vp, st);
         if (rc) return rc;
-        rc = launch_vert<N, true, true>(h, ln, e, vp, st);
+        rc = launch_sweep<N, true, true>(h, ln, e, vp, st);
     } else {
-        rc = launch_vert<N, false, true>(h, ln, e, vp, st);
+        rc = launch_sweep<N, false, true>(h, ln, e, vp, st);
     }
-    if (rc) return rc;
-    CUDA_TRY(h, cudaMemcpyAsync(ln.h_err, ln.d_err, sizeof(int), cudaMemcpyDeviceToHost, st));
-    return B200SGM_OK;
+    return rc;
 }
 
 template <int N>

@@ -4,7 +4,14 @@
 // No CPU fallback exists: every result is produced by the kernels below.
 #include "engine_internal.h"
 #include "k_fused.cuh"   // geometry helpers only; the kernels are instantiated in agg_n*.cu
+#include "k_sweep.cuh"
 #include "k_post.cuh"
+
+CoopGate& coop_gate(int device)
+{
+    static CoopGate gates[64];
+    return gates[device & 63];
+}
 
 namespace {
 
@@ -18,8 +25,12 @@ int nreg_for(int D)
 // A.1 parameter normalisation + geometry.  Returns 0 or B200SGM_EINVAL with h->err set.
 int make_eff(b200sgm_engine* h, int W, int H, Eff& e)
 {
-    if (!h->have_params) return fail(h, B200SGM_ESTATE, "b200sgm_set_params has not been called");
-    const b200sgm_params& p = h->raw;
+    b200sgm_params p;
+    {
+        std::lock_guard<std::mutex> lk(h->mu);     // set_params may run on another thread
+        if (!h->have_params) return fail(h, B200SGM_ESTATE, "b200sgm_set_params has not been called");
+        p = h->raw;
+    }
     if (p.numDisparities <= 0) return fail(h, B200SGM_EINVAL, "numDisparities must be > 0");
     if (p.numDisparities > h->maxD) return fail(h, B200SGM_ESIZE, "numDisparities exceeds the engine's max_disparities");
     if (W <= 0 || H <= 0) return fail(h, B200SGM_EINVAL, "empty image");
@@ -98,6 +109,8 @@ int run_pipeline(b200sgm_engine* h, Lane& ln, const Eff& e, const uint8_t* dL, s
         }
         if (ln.prof_count == kProfRing) { CUDA_TRY(h, cudaStreamSynchronize(st)); prof_harvest(ln, h->prof_ref); }
     }
+    CUDA_TRY(h, cudaMemsetAsync(ln.d_err, 0, kStatusWords * sizeof(int), st));   // a failed frame must not poison the next one
+    ln.last_P2 = e.P2;
     prof_mark(h, ln, 0, st);
     {
         launch_prefilter(dL, lp, dR, rp, W, H, e.ftzero, ln.feat_l, ln.feat_r, st);
@@ -140,6 +153,18 @@ int run_pipeline(b200sgm_engine* h, Lane& ln, const Eff& e, const uint8_t* dL, s
     }
     prof_mark(h, ln, 7, st);
     if (h->profile && !ln.prof_events.empty()) { ln.prof_head = (ln.prof_head + 1) % kProfRing; ln.prof_count++; }
+    CUDA_TRY(h, cudaMemcpyAsync(ln.h_err, ln.d_err, kStatusWords * sizeof(int), cudaMemcpyDeviceToHost, st));
+    return B200SGM_OK;
+}
+
+// Status of the last frame of `ln` once its stream has been synchronised: error, warning (> 0) or OK.
+int frame_status(b200sgm_engine* h, Lane& ln)
+{
+    if (ln.h_err[0]) return fail(h, B200SGM_ECUDA, "fused aggregation kernel: an inter-strip wait timed out; the disparity of this frame is invalid");
+    if (ln.h_err[3] + ln.last_P2 > kMaxCost) {
+        h->err = "cost volume reached " + std::to_string(ln.h_err[3]) + " (+P2 > 32767): outside cv::StereoSGBM's int16 contract, results may differ from OpenCV";
+        return B200SGM_WARN_COST_RANGE;
+    }
     return B200SGM_OK;
 }
 
@@ -159,7 +184,6 @@ void free_lane(Lane& ln)
     if (ln.h_total) cudaFreeHost(ln.h_total);
     cudaFree(ln.xbuf); cudaFree(ln.d_err);
     if (ln.h_err) cudaFreeHost(ln.h_err);
-    for (auto ev : ln.coop_ev) if (ev) cudaEventDestroy(ev);
     for (auto ev : ln.prof_events) cudaEventDestroy(ev);
     if (ln.done) cudaEventDestroy(ln.done);
     if (ln.stream) cudaStreamDestroy(ln.stream);
@@ -184,6 +208,7 @@ int b200sgm_create(int device, int max_width, int max_height, int max_disparitie
     h->device = device; h->maxW = max_width; h->maxH = max_height; h->maxD = max_disparities;
     cudaDeviceGetAttribute(&h->num_sms, cudaDevAttrMultiProcessorCount, device);
     cudaDeviceGetAttribute(&h->clock_khz, cudaDevAttrClockRate, device);
+    cudaDeviceGetAttribute(&h->max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
     const size_t npix = size_t(max_width) * max_height;
     const int nreg = nreg_for(max_disparities);
     const size_t Dp = size_t((max_disparities + 2 * nreg - 1) / (2 * nreg) * (2 * nreg));
@@ -205,12 +230,10 @@ int b200sgm_create(int device, int max_width, int max_height, int max_disparitie
         ok = ok && cudaMalloc(&ln.points, npix * sizeof(float4)) == cudaSuccess;
         ok = ok && cudaMalloc(&ln.block_count, ((npix + 255) / 256 + 1) * 4) == cudaSuccess && cudaMalloc(&ln.total, 4) == cudaSuccess;
         ok = ok && cudaMallocHost(&ln.h_total, 4) == cudaSuccess;
-        ok = ok && cudaMalloc(&ln.xbuf, size_t(2) * kMaxStrips * kXbufGen * (Dp / 2) * sizeof(uint2)) == cudaSuccess;
-        ok = ok && cudaMalloc(&ln.d_err, 4 * sizeof(int)) == cudaSuccess && cudaMemset(ln.d_err, 0, 4 * sizeof(int)) == cudaSuccess;
-        ok = ok && cudaMallocHost(&ln.h_err, sizeof(int)) == cudaSuccess;
-        if (ok) *ln.h_err = 0;
-        ok = ok && cudaEventCreateWithFlags(&ln.coop_ev[0], cudaEventDisableTiming) == cudaSuccess;
-        ok = ok && cudaEventCreateWithFlags(&ln.coop_ev[1], cudaEventDisableTiming) == cudaSuccess;
+        ok = ok && cudaMalloc(&ln.xbuf, sweep_xbuf_bytes(kMaxStrips, int(Dp))) == cudaSuccess;
+        ok = ok && cudaMalloc(&ln.d_err, kStatusWords * sizeof(int)) == cudaSuccess && cudaMemset(ln.d_err, 0, kStatusWords * sizeof(int)) == cudaSuccess;
+        ok = ok && cudaMallocHost(&ln.h_err, kStatusWords * sizeof(int)) == cudaSuccess;
+        if (ok) memset(ln.h_err, 0, kStatusWords * sizeof(int));
         if (!ok) break;
     }
     if (!ok) {
@@ -291,7 +314,7 @@ int b200sgm_enqueue(b200sgm_handle h, int lane, const uint8_t* left, size_t left
     CUDA_TRY(h, cudaMemcpy2DAsync(ln.left, width, left, left_stride, width, height, cudaMemcpyHostToDevice, st));
     CUDA_TRY(h, cudaMemcpy2DAsync(ln.right, width, right, right_stride, width, height, cudaMemcpyHostToDevice, st));
     rc = run_pipeline(h, ln, e, ln.left, width, ln.right, width, st);
-    if (rc) return rc;
+    if (rc) { cudaStreamSynchronize(st); return rc; }   // the copies from the caller's buffers are already enqueued: let them finish
     CUDA_TRY(h, cudaMemcpy2DAsync(disp, disp_stride, ln.disp_out, size_t(width) * 2, size_t(width) * 2, height, cudaMemcpyDeviceToHost, st));
     CUDA_TRY(h, cudaEventRecord(ln.done, st));
     ln.busy = true;
@@ -309,8 +332,15 @@ int b200sgm_wait(b200sgm_handle h, int lane)
     ln.busy = false;
     CUDA_TRY(h, cudaEventSynchronize(ln.done));
     CUDA_TRY(h, cudaGetLastError());
-    if (*ln.h_err) return fail(h, B200SGM_ECUDA, "fused aggregation kernel: inter-strip flag wait timed out");
-    return B200SGM_OK;
+    return frame_status(h, ln);
+}
+
+int b200sgm_lane_status(b200sgm_handle h, int lane)
+{
+    if (!h) return B200SGM_EINVAL;
+    int rc = lane_check(h, lane);
+    if (rc) return rc;
+    return frame_status(h, h->lanes[lane]);
 }
 
 int b200sgm_compute(b200sgm_handle h, const uint8_t* left, size_t left_stride, const uint8_t* right, size_t right_stride,
@@ -342,7 +372,7 @@ int b200sgm_compute_f32(b200sgm_handle h, const uint8_t* left, size_t left_strid
     LAUNCH_CHECK(h);
     CUDA_TRY(h, cudaMemcpy2DAsync(disp32, disp_stride, ln.f32a, size_t(width) * 4, size_t(width) * 4, height, cudaMemcpyDeviceToHost, st));
     CUDA_TRY(h, cudaStreamSynchronize(st));
-    return B200SGM_OK;
+    return frame_status(h, ln);
 }
 
 int b200sgm_compute_xyz(b200sgm_handle h, const uint8_t* left, size_t left_stride, const uint8_t* right, size_t right_stride,
@@ -382,7 +412,7 @@ int b200sgm_compute_xyz(b200sgm_handle h, const uint8_t* left, size_t left_strid
     const uint32_t n = *ln.h_total;
     if (count) *count = n;
     if (points && n) CUDA_TRY(h, cudaMemcpy(points, ln.points, size_t(n) * sizeof(b200sgm_point), cudaMemcpyDeviceToHost));
-    return B200SGM_OK;
+    return frame_status(h, ln);
 }
 
 const char* b200sgm_last_error(b200sgm_handle h) { return h ? h->err.c_str() : "null handle"; }
@@ -421,8 +451,12 @@ int ensure_maps(b200sgm_engine* h, int cam, int w, int hgt, bool want_float, cud
         r.dirty = true;
     }
     if (r.dirty || r.W != w || r.H != hgt) {
+        // The map buffers are shared by every lane and stream: nobody may still be reading the old maps while they are
+        // rebuilt, and nobody may start remapping before the new ones are complete.  Rare (once per camera and size).
+        CUDA_TRY(h, cudaDeviceSynchronize());
         launch_rectify_maps(r.cam, w, hgt, r.ent, r.map1, r.map2, st);
         LAUNCH_CHECK(h);
+        CUDA_TRY(h, cudaStreamSynchronize(st));
         r.W = w; r.H = hgt; r.dirty = false;
     }
     return B200SGM_OK;

@@ -33,11 +33,12 @@ struct Lane {
     float4* points = nullptr;                       // W x H
     uint32_t *block_count = nullptr, *total = nullptr;
     uint32_t* h_total = nullptr;                    // pinned
-    uint2* xbuf = nullptr;                          // k_vert exchange records (LL protocol)
-    int* d_err = nullptr;                           // device error word of the fused kernels
-    int* h_err = nullptr;                           // pinned copy
-    cudaEvent_t coop_ev[2] = {nullptr, nullptr};   // alternating: MODE_HH launches two sweeps per frame
-    int coop_idx = 0;
+    uint2* xbuf = nullptr;                          // k_sweep inter-strip records (LL protocol) and progress words
+    // device status words of the frame in flight: [0] inter-strip wait timed out, [1] late exchange records (debug),
+    // [2] poll iterations (debug), [3] largest cost-volume cell seen by k_horiz (overflow guard)
+    int* d_err = nullptr;
+    int* h_err = nullptr;                           // pinned copy of the 4 words, refreshed at the end of every frame
+    int last_P2 = 0;                                // P2 of the frame whose status h_err holds
     // stage profiling (b200sgm_profile): ring of event sets, harvested by b200sgm_stage_times
     std::vector<cudaEvent_t> prof_events;           // kProfRing * (kStages + 1)
     int prof_head = 0, prof_count = 0;
@@ -48,7 +49,20 @@ struct Lane {
 
 constexpr int kStages = 7;    // prefilter, cost, horizontal, vertical+wta, lrcheck, median, speckle
 constexpr int kProfRing = 256;
-constexpr int kMaxStrips = 1024;
+constexpr int kMaxStrips = 320;
+constexpr int kStatusWords = 4;
+
+// Cooperative sweeps of ALL engines of a process on one device are serialised: one sweep fills every SM, and two
+// partially resident sweeps would spin on CTAs that can never be scheduled.  Process-wide, keyed by device; the events
+// are never destroyed (they outlive any engine).  coop_serialise() makes `st` wait for the previous sweep on `device`;
+// coop_published() records the sweep just launched on `st`.  Hold the returned lock across both calls.
+struct CoopGate {
+    std::mutex mu;
+    cudaEvent_t ev[2] = {nullptr, nullptr};
+    int idx = 0;
+    bool any = false;
+};
+CoopGate& coop_gate(int device);
 constexpr int kVertMaxWarps = 16;
 
 
@@ -64,9 +78,7 @@ struct b200sgm_engine {
     bool profile = false;
     cudaEvent_t prof_ref = nullptr;   // time origin of the stage timeline
     int num_sms = 148;
-    // cooperative (k_vert) launches of all lanes: one sweep fills the register file of every SM (1024 threads x 64
-    // registers), and two partially resident sweeps would spin on CTAs that can never be scheduled -> serialise them
-    cudaEvent_t coop_prev[2] = {nullptr, nullptr};
+    int max_smem_optin = 227 * 1024;
     int clock_khz = 1965000;
     std::mutex mu;
     // rectification (row N2): per camera (0 left, 1 right) the model and the cached fixed-point maps

@@ -59,7 +59,8 @@ inline size_t horiz_smem_per_warp(int Dp) { return size_t(kHRingB + kHRingF + 2 
 // CLAMP: saturate S_h (needed when 2*(Cmax+P2) could exceed 65535; padded cells are masked again before the WTA)
 template <int N, bool FULL, bool CLAMP>
 __global__ void __launch_bounds__(64) k_horiz(const uint16_t* __restrict__ Cvol, uint16_t* __restrict__ Sh,
-                                              uint16_t* __restrict__ ckpt, int W1, int H, int Dp_rt, int P1, int P2)
+                                              uint16_t* __restrict__ ckpt, int W1, int H, int Dp_rt, int D, int P1, int P2,
+                                              unsigned* __restrict__ maxc)
 {
     extern __shared__ __align__(16) uint16_t smem_h[];
     const int Dp = FULL ? 64 * N : Dp_rt;
@@ -87,6 +88,20 @@ __global__ void __launch_bounds__(64) k_horiz(const uint16_t* __restrict__ Cvol,
     };
 
     uint32_t Lt[N], Ln[N], Cc[N];
+    // Overflow guard: the largest cost-volume cell of the frame (phase B's -> stream sees every column once).  This
+    // kernel is HBM bound, the extra packed max per register is free.  cv::StereoSGBM keeps C and L in int16: a frame
+    // whose largest C + P2 exceeds 32767 is outside its defined behaviour and is reported by the host (b200sgm_wait).
+    uint32_t cmx = 0;
+    auto track = [&](const uint32_t (&c)[N]) {
+#pragma unroll
+        for (int j = 0; j < N; j++) {
+            if (FULL) cmx = __vmaxu2(cmx, c[j]);
+            else {
+                const int k = lane * N + j;
+                cmx = __vmaxu2(cmx, c[j] & ((k < D ? 0xFFFFu : 0u) | (k + (Dp >> 1) < D ? 0xFFFF0000u : 0u)));
+            }
+        }
+    };
     // ---------------- phase A: <- chain from x = W1-1 down to kHT, checkpoints only ----------------
     // ring slot of column x is x & 7; column x - 7 is requested while column x is processed
     if (W1 > kHT) {
@@ -162,6 +177,7 @@ __global__ void __launch_bounds__(64) k_horiz(const uint16_t* __restrict__ Cvol,
         if (u >= 0 && u < W1) {
             uint32_t Lb[N];
             ldC(ringF + (u & 3) * Dp, Cc);
+            if (active) track(Cc);
             if (active) ld_regs<N>(tiles + (((u >> 3) & 1) * kHT + (u & 7)) * Dp, Lb);
             path_step<N>(Cc, Lt, Ln, lc);
             if (active) {
@@ -193,6 +209,7 @@ __global__ void __launch_bounds__(64) k_horiz(const uint16_t* __restrict__ Cvol,
                 uint32_t Cb[N], Lnb[N], Lb[N];
                 ld_regs<N>(ringB + i * Dp, Cb);
                 ld_regs<N>(ringF + (i & 3) * Dp, Cc);
+                track(Cc);
                 ld_regs<N>(tcur + i * Dp, Lb);
                 path_step<N>(Cb, Ltb, Lnb, lc);
                 path_step<N>(Cc, Lt, Ln, lc);
@@ -205,6 +222,8 @@ __global__ void __launch_bounds__(64) k_horiz(const uint16_t* __restrict__ Cvol,
     }
     for (; it < W1; it++) iterB(it);
     cp_async_wait<0>();
+    cmx = __reduce_max_sync(kFullMask, max(cmx & 0xFFFFu, cmx >> 16));
+    if (lane == 0 && cmx > 0) atomicMax(maxc, cmx);
 }
 
 // ------------------------------------------------------------------------------------------------

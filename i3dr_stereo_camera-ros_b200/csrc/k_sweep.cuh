@@ -1,0 +1,410 @@
+// Vertical sweep (A.5 paths "down", "down-right", "down-left" -- or their mirror images for the second pass of
+// MODE_HH -- summed with S_h, fused with the winner-take-all A.6): the diagonal-skewed, one-directional version.
+//
+// The W1 valid columns are covered by W1 CHAINS on a cylinder: chain c sits at column x = (c + r) mod W1 in sweep
+// row r, i.e. it walks down a down-right diagonal and re-enters at column 0 (as a fresh diagonal) after leaving at
+// column W1-1.  With that labelling the three predecessors of cell (x, r) are
+//     down-right path : (x-1, r-1) = chain c   itself            -> state stays in the warp's registers
+//     down path       : (x,   r-1) = chain c+1 at row r-1        -> from the next warp, previous row
+//     down-left path  : (x+1, r-1) = chain c+2 at row r-1        -> from the warp after that, previous row
+// so every dependency points the SAME way (towards higher chain numbers, cyclically).  A strip of consecutive chains
+// = one CTA, one warp per chain; the strip needs per row three records from the strip to its right (its first
+// chain's down/down-left states and its second chain's down-left state) and nothing from the strip to its left.
+// Compared with plain column strips (which need both neighbours every row and therefore march in lock step):
+//   * neighbouring strips are coupled one way with kXK rows of slack (a strip may run up to kXK rows ahead of its
+//     consumer), neighbouring warps inside a strip one way with LDG rows of slack -- stalls no longer line up;
+//   * no CTA-wide barrier: warps hand over through shared-memory row counters (data first, counter second, both by
+//     the same warp through the in-order shared-memory pipe), the WTA warps likewise;
+//   * one diagonal path never leaves the register file.
+// Image borders are predicates: at x == 0 the down-right predecessor is outside (state 0), at x == W1-1 the
+// down-left one is; row 0 starts from all-zero states.
+#pragma once
+#include <type_traits>
+#include "sgm_types.h"
+#include "k_path.cuh"
+#include "k_wta.cuh"
+#include "k_fused.cuh"
+
+namespace b200sgm {
+
+constexpr int kXK = 16;          // generations of inter-strip records in global memory
+constexpr int kSweepMaxTW = 15;  // chains (= path warps) per strip: 15 path + 15 WTA + 1 agent = 31 warps
+constexpr int kSweepFlagInts = 64;
+
+// Threads per CTA the register file is budgeted for: 64 registers per thread up to 256 disparities, 72 / 128 / 255 beyond.
+constexpr int sweep_max_threads(int n) { return n <= 4 ? 1024 : n == 8 ? 896 : n == 16 ? 512 : 256; }
+
+struct SweepGeom {
+    WtaGeom w;
+    int nstrips;
+    int twmax;            // chains of the widest strip
+    int P1, P2;
+    long long spin_limit; // clock64 ticks before a wait gives up
+    int debug_flags;      // 8: timing experiment, ignore record tags (wrong results)
+};
+
+// xbuf: [0, 4 KB) progress words (one int per strip), then records [3 kinds][nstrips][kXK][Dp/2] of {data, tag}
+inline size_t sweep_xbuf_bytes(int nstrips, int Dp) { return 4096 + size_t(3) * nstrips * kXK * (Dp / 2) * sizeof(uint2); }
+// dynamic smem (uint16): Ld[LDG][2 kinds][tw][Dp] | Cring[tw][RING][Dp] | Sring[tw][RING][Dp] | stage[kStage][tw][Dp] | flags
+inline size_t sweep_smem_bytes(int tw, int Dp, int ring, int ldg, bool wta)
+{
+    return (size_t(ldg) * 2 * tw + size_t(2) * ring * tw + (wta ? size_t(kStage) * tw : 0)) * Dp * sizeof(uint16_t) + kSweepFlagInts * sizeof(int);
+}
+
+__device__ __forceinline__ uint2* sweep_rec(uint2* xbuf, int nstrips, int Dp, int kind, int strip, int gen)
+{
+    return xbuf + 512 + (size_t((kind * nstrips + strip) * kXK + gen)) * (Dp / 2);
+}
+__device__ __forceinline__ int ld_flag(const int* p)
+{
+    int v;
+    asm volatile("ld.volatile.shared.b32 %0, [%1];" : "=r"(v) : "r"(uint32_t(__cvta_generic_to_shared(p))) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_flag(int* p, int v)
+{
+    asm volatile("st.volatile.shared.b32 [%0], %1;" ::"r"(uint32_t(__cvta_generic_to_shared(p))), "r"(v) : "memory");
+}
+__device__ __forceinline__ int ld_relaxed_gpu(const int* p)
+{
+    int v;
+    asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_relaxed_gpu(int* p, int v) { asm volatile("st.relaxed.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
+
+// Waits until ready() holds.  SLEEP > 0: back off between polls (waits that are expected to block).  A wait that
+// exceeds the limit, or that sees the error word set by somebody else, raises the error word and marks this warp dead:
+// it then stops waiting altogether (the frame is reported as failed by the host).
+template <int SLEEP, typename F>
+__device__ __forceinline__ void sweep_wait(F ready, long long limit, int* err, bool& dead)
+{
+    if (dead || ready()) return;
+    const long long t0 = clock64();
+    int spins = 0;
+    while (!ready()) {
+        if (SLEEP > 0) __nanosleep(SLEEP);
+        if ((++spins & 63) == 0 && (clock64() - t0 > limit || *reinterpret_cast<volatile int*>(err))) {
+            atomicExch(err, 1);
+            dead = true;
+            break;
+        }
+    }
+}
+
+// Scalar part of the WTA for up to 32 sweep rows of chain c starting at sweep row rb: lane l resolves row rb + l.
+template <bool UP>
+__device__ __forceinline__ void wta_flush_diag(const WtaAcc& acc, int cnt, const WtaGeom& g, const WtaCtx& w, int c, int rb, int lane,
+                                               int16_t* __restrict__ disp, uint32_t* __restrict__ disp2key)
+{
+    if (lane >= cnt) return;
+    const int r = rb + lane;
+    const int x1 = (c + r) % g.W1;
+    const int y = UP ? g.H - 1 - r : r;
+    const int minS = int(acc.key >> 16), best = int(acc.key & 0xFFFFu);
+    const uint32_t n100 = uint32_t(minS * 100 + w.f - 1);
+    const uint32_t thr = min(w.f == 1 ? n100 : __umulhi(n100, w.umagic), 0xFFFFu);
+    const bool reject = (acc.mm & 0xFFFFu) < thr || minS >= kMaxCost;
+    int dfix = best * 16;
+    if (best > 0 && best < g.D - 1) {
+        const int den = max(acc.sm + acc.sp - 2 * minS, 1);
+        dfix += __float2int_rz(__fdiv_rn(float((acc.sm - acc.sp) * 16 + den), float(den * 2)));
+    }
+    const int x = x1 + g.minX1;
+    if (!reject) {
+        const int x2 = x - best - g.minD;
+        if (x2 >= 0 && x2 < g.W) atomicMin(disp2key + size_t(y) * g.W + x2, (uint32_t(minS) << 16) | uint32_t(0xFFFF - x));
+    }
+    disp[size_t(y) * g.W + x] = int16_t(reject ? g.INVALID : dfix + g.minD * 16);
+}
+
+// Launch: nstrips CTAs (all co-resident: cooperative launch), 32 * (2 * twmax + 1) threads (32 * (twmax + 1) when !DO_WTA):
+//   path warps  [0, twmax)         one per chain: the three path updates of a row and the sum S
+//   WTA warps   [twmax, 2 twmax)   one per chain: resolve parked rows of S two at a time (A.6), trailing by <= kStage rows
+//   agent warp  (last)             plays the two chains to the right of the strip: polls the neighbour strip's records of each
+//                                  row in global memory and drops them into the shared-memory slots those chains would fill
+// RING : rows of C / S_h in flight per chain (cp.async rings);  LDG : generations of hand-over state between neighbouring warps
+// FULL : Dp == D == 64 N;  CLAMP_EACH : saturate after every addition of the sum
+template <int N, int RING, int LDG, bool UP, bool DO_WTA, bool FULL, bool CLAMP_EACH>
+__global__ void __launch_bounds__(sweep_max_threads(N), 1) k_sweep(const uint16_t* __restrict__ Cvol, uint16_t* __restrict__ Svol, SweepGeom g,
+                                                                    int16_t* __restrict__ disp, uint32_t* __restrict__ disp2key,
+                                                                    uint2* __restrict__ xbuf, int* __restrict__ err)
+{
+    static_assert(LDG == 2 || LDG == 4, "generation index must be an immediate of the 4-row unrolled loop");
+    static_assert(RING == 4 || RING == 8, "ring depth");
+    extern __shared__ __align__(16) uint16_t smem_s[];
+    const int W1 = g.w.W1, H = g.w.H, Dp = FULL ? 64 * N : g.w.Dp;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int b = blockIdx.x, n = g.nstrips, tw = g.twmax;
+    const int c0 = int((long long)b * W1 / n), c1 = int((long long)(b + 1) * W1 / n);
+    const int TW = c1 - c0;                                  // 2 <= TW <= tw
+    // Ld[gen][kind][slot][Dp]: slot s holds what path warp s READS: kind 0 = down state of chain c0+s+1, kind 1 = down-left
+    // state of chain c0+s+2 (normalised).  Warp j therefore writes kind 0 into slot j-1 and kind 1 into slot j-2.
+    uint16_t* Ld = smem_s;
+    const int kindStride = tw * Dp, genStride = 2 * tw * Dp;
+    uint16_t* ringbase = Ld + size_t(LDG) * genStride;
+    uint16_t* sringbase = ringbase + size_t(RING) * tw * Dp;
+    uint16_t* stagebase = sringbase + size_t(RING) * tw * Dp;
+    int* flags = reinterpret_cast<int*>(stagebase + (DO_WTA ? size_t(kStage) * tw * Dp : 0));
+    int* done = flags;            // [tw + 2] rows whose down / down-left states chain j has published (tw, tw+1: the agent)
+    int* wfill = flags + 24;      // [tw] rows of S parked by path warp j
+    int* wtake = flags + 40;      // [tw] rows of S consumed by WTA warp j
+    {
+        uint32_t* z = reinterpret_cast<uint32_t*>(Ld);
+        const int nz = LDG * genStride / 2;
+        for (int i = threadIdx.x; i < nz; i += blockDim.x) z[i] = 0;
+        if (threadIdx.x < kSweepFlagInts) flags[threadIdx.x] = 0;
+    }
+    __syncthreads();
+    const LaneCtx lc = make_lane_ctx<N>(lane, Dp, g.P1, g.P2);
+    const bool active = FULL || lc.active;
+    const int lo = lane * 2 * N;
+    const int agent_w = DO_WTA ? 2 * tw : tw;
+    bool dead = false;
+
+    if (w == agent_w) {
+        // ================================ agent warp ================================
+        const int nb = b + 1 == n ? 0 : b + 1;
+        const uint2* recV0 = sweep_rec(xbuf, n, Dp, 0, nb, 0) + lane * N;    // down state of the neighbour's first chain
+        const uint2* recB0 = sweep_rec(xbuf, n, Dp, 1, nb, 0) + lane * N;    // its down-left state
+        const uint2* recB1 = sweep_rec(xbuf, n, Dp, 2, nb, 0) + lane * N;    // down-left state of the neighbour's second chain
+        uint16_t* dV0 = Ld + (TW - 1) * Dp + lo;                             // kind 0, slot TW-1 (read by warp TW-1)
+        uint16_t* dB0 = Ld + kindStride + (TW - 2) * Dp + lo;                // kind 1, slot TW-2 (read by warp TW-2)
+        uint16_t* dB1 = Ld + kindStride + (TW - 1) * Dp + lo;                // kind 1, slot TW-1 (read by warp TW-1)
+        int* prog = reinterpret_cast<int*>(xbuf) + b;
+        const int recGen = Dp / 2;
+        for (int rr = 0; rr + 1 < H; rr++) {
+            // generation rr % LDG still holds row rr - LDG until warps TW-1 and TW-2 have loaded it (their row rr - LDG + 1)
+            const int need = rr - LDG + 2;
+            if (need > 0) sweep_wait<40>([&] { return min(ld_flag(done + TW - 1), ld_flag(done + TW - 2)) >= need; }, g.spin_limit, err, dead);
+            uint32_t dv0[N], db0[N], db1[N];
+#pragma unroll
+            for (int q = 0; q < N; q++) { dv0[q] = 0; db0[q] = 0; db1[q] = 0; }
+            const int go = (rr & (kXK - 1)) * recGen;
+            const uint32_t tag = uint32_t(rr + 1);
+            auto poll = [&] {
+                bool ok = true;
+                if (active) {
+#pragma unroll
+                    for (int q = 0; q < N; q++) {
+                        const uint2 a = ld_volatile_v2(recV0 + go + q), bb = ld_volatile_v2(recB0 + go + q), cc = ld_volatile_v2(recB1 + go + q);
+                        dv0[q] = a.x; db0[q] = bb.x; db1[q] = cc.x;
+                        ok = ok && a.y == tag && bb.y == tag && cc.y == tag;
+                    }
+                }
+                return __all_sync(kFullMask, ok) || (g.debug_flags & 8);
+            };
+            sweep_wait<0>(poll, g.spin_limit, err, dead);
+            if (active) {
+                const int go2 = (rr & (LDG - 1)) * genStride;
+                st_regs<N>(dV0 + go2, dv0); st_regs<N>(dB0 + go2, db0); st_regs<N>(dB1 + go2, db1);
+            }
+            __syncwarp();
+            if (lane == 0) {
+                st_flag(done + TW, rr + 1);
+                st_flag(done + TW + 1, rr + 1);
+                st_relaxed_gpu(prog, rr + 1);
+            }
+        }
+        return;
+    }
+    const bool wta_role = DO_WTA && w >= tw;
+    const int j = wta_role ? w - tw : w;
+    if (j >= TW) return;
+    const int c = c0 + j;                              // this warp's chain
+    const int ringSlot = tw * Dp;                      // slot stride of the stage ring [slot][warp][Dp]
+    uint16_t* stage = stagebase + size_t(j) * Dp;      // + slot * ringSlot
+
+    if (wta_role) {
+        // ================================ WTA warps ================================
+        WtaCtx wc;
+        wc.Dh = Dp >> 1;
+        wc.kk0 = uint32_t(lane * N) | (uint32_t(lane * N + wc.Dh) << 16);
+        wc.f = 100 - g.w.uniq;
+        wc.umagic = wc.f > 0 ? uint32_t((1ull << 32) / uint32_t(wc.f)) + 1u : 0u;
+        WtaAcc acc{0xFFFFFFFFu, 0u, 0, 0};
+        int pending = 0, rb = 0;            // rows parked in acc, first of them
+        auto batch = [&](auto q0_tag, int r, int cnt) {
+            constexpr int Q0 = decltype(q0_tag)::value;
+            sweep_wait<40>([&] { return ld_flag(wfill + j) >= r + cnt; }, g.spin_limit, err, dead);
+            uint16_t* sc = stage + Q0 * ringSlot;
+            if (wc.f > 0) {
+                wta_vec<N>(sc, ringSlot, r, g.w, wc, lane, active, acc);   // a row past the end lands in a lane >= cnt of the flush
+                pending += cnt;
+                if (((r + kWB) & 31) == 0 || r + kWB >= H) {
+                    wta_flush_diag<UP>(acc, pending, g.w, wc, c, rb, lane, disp, disp2key);
+                    rb += pending;
+                    pending = 0;
+                }
+            } else {
+                __syncwarp();
+                for (int q = 0; q < cnt; q++) {
+                    const int rr = r + q, x1 = (c + rr) % W1, y = UP ? H - 1 - rr : rr;
+                    const int d = wta_slow<N>(sc + q * ringSlot, g.w, wc, x1, lane, active, disp2key + size_t(y) * g.w.W);
+                    if (lane == 0) disp[size_t(y) * g.w.W + x1 + g.w.minX1] = int16_t(d);
+                }
+            }
+            __syncwarp();
+            if (lane == 0) st_flag(wtake + j, r + cnt);
+        };
+        static_assert(kWB == 2 && kStage == 4, "two batches per stage-ring revolution");
+        int r = 0;
+        for (; r + 3 < H; r += 4) {
+            batch(std::integral_constant<int, 0>{}, r, 2);
+            batch(std::integral_constant<int, 2>{}, r + 2, 2);
+        }
+        if (r < H) batch(std::integral_constant<int, 0>{}, r, min(2, H - r));
+        if (r + 2 < H) batch(std::integral_constant<int, 2>{}, r + 2, 1);
+        return;
+    }
+
+    // ================================ path warps ================================
+    const bool producer = j <= 1;                              // the strip to the left needs my states
+    const int cb = b == 0 ? n - 1 : b - 1;                     // ... that strip
+    const int* prog_c = reinterpret_cast<const int*>(xbuf) + cb;
+    uint2* pubV = sweep_rec(xbuf, n, Dp, 0, b, 0) + lane * N;
+    uint2* pubB = sweep_rec(xbuf, n, Dp, j == 0 ? 1 : 2, b, 0) + lane * N;
+    const int recGen = Dp / 2;
+    const uint16_t* rdV = Ld + size_t(j) * Dp + lo;            // + gen * genStride
+    const uint16_t* rdB = Ld + kindStride + size_t(j) * Dp + lo;
+    uint16_t* wrV = Ld + size_t(max(j - 1, 0)) * Dp + lo;      // j == 0: never stored
+    uint16_t* wrB = Ld + kindStride + size_t(max(j - 2, 0)) * Dp + lo;   // j <= 1: never stored
+    const int* flagV = done + j + 1;
+    const int* flagB = done + j + 2;
+    uint16_t* ring = ringbase + size_t(j) * RING * Dp + lo;
+    uint16_t* sring = sringbase + size_t(j) * RING * Dp + lo;
+    const int Dh = Dp >> 1;
+    const ptrdiff_t rowStep = (UP ? -1 : 1) * ptrdiff_t(W1) * Dp + Dp;   // next sweep row, next column
+    const ptrdiff_t wrapBack = ptrdiff_t(W1) * Dp;
+    const int ystart = UP ? H - 1 : 0;
+    ptrdiff_t offPf = (ptrdiff_t(ystart) * W1 + c) * Dp + lo;   // next row to prefetch, its column
+    int xPf = c;
+    ptrdiff_t offCur = offPf;                                   // row being computed (first pass of MODE_HH stores there)
+    int xcur = c;
+    auto issue = [&](int row_) {
+        if (row_ < H && active) {
+            cp_async_lane<N>(ring + (row_ & (RING - 1)) * Dp, Cvol + offPf);
+            cp_async_lane<N>(sring + (row_ & (RING - 1)) * Dp, Svol + offPf);
+        }
+        offPf += rowStep;
+        if (++xPf == W1) { xPf = 0; offPf -= wrapBack; }
+    };
+#pragma unroll
+    for (int i = 0; i < RING - 1; i++) { issue(i); cp_async_commit(); }
+
+    uint32_t LtA[N];           // the down-right path: this chain's own state
+#pragma unroll
+    for (int q = 0; q < N; q++) LtA[q] = 0;
+    int space_known = j == 0 ? 0x7FFFFFFF : 0;   // rows the readers of my hand-over slots are known to have published
+    int prog_known = 0, prog_next = 0;           // producers: record rows the left strip's agent has taken
+
+    auto row = [&](auto q_tag, int r) {
+        constexpr int Q = decltype(q_tag)::value;          // r & 3
+        constexpr int GEN = Q % LDG, PGEN = (Q + 3) % LDG;  // hand-over generation written (row r) / read (row r-1)
+        issue(r + RING - 1);
+        cp_async_commit();
+        if (producer) {
+            prog_known = max(prog_known, prog_next);
+            prog_next = ld_relaxed_gpu(prog_c);            // inspected one row later: the round trip stays off this row's path
+        }
+        const int fV = ld_flag(flagV), fB = ld_flag(flagB);
+        uint32_t LtV[N], LtB[N], Cc[N], S[N], Ln[N];
+        if (active) {
+            ld_regs<N>(rdV + PGEN * genStride, LtV); ld_regs<N>(rdB + PGEN * genStride, LtB);
+        } else {
+#pragma unroll
+            for (int q = 0; q < N; q++) { LtV[q] = 0; LtB[q] = 0; }
+        }
+        cp_async_wait<RING - 1>();     // this thread's copies of row r have landed (each lane reads only its own bytes)
+        if (active) {
+            ld_regs<N>(ring + (r & (RING - 1)) * Dp, Cc); ld_regs<N>(sring + (r & (RING - 1)) * Dp, S);
+        } else {
+#pragma unroll
+            for (int q = 0; q < N; q++) { Cc[q] = kMaxCostX2; S[q] = 0; }
+        }
+        if (fV < r || fB < r) {        // a neighbour has not published row r-1 yet: wait, then load again
+            sweep_wait<0>([&] { return ld_flag(flagV) >= r && ld_flag(flagB) >= r; }, g.spin_limit, err, dead);
+            if (active) { ld_regs<N>(rdV + PGEN * genStride, LtV); ld_regs<N>(rdB + PGEN * genStride, LtB); }
+        }
+        if (xcur == W1 - 1) {
+#pragma unroll
+            for (int q = 0; q < N; q++) LtB[q] = 0;
+        }
+        if (xcur == 0) {
+#pragma unroll
+            for (int q = 0; q < N; q++) LtA[q] = 0;
+        }
+        auto add = [&](const uint32_t (&L)[N]) {
+#pragma unroll
+            for (int q = 0; q < N; q++) S[q] = CLAMP_EACH ? __vminu2(S[q] + L[q], kMaxCostX2) : S[q] + L[q];
+        };
+        // ---- down and down-left: the states the next warps wait for
+        path_step<N>(Cc, LtV, Ln, lc);
+        add(Ln);
+        path_step<N>(Cc, LtB, Ln, lc);
+        add(Ln);
+        if (r - LDG + 2 > space_known) {   // generation GEN still holds row r-LDG until warps j-1 / j-2 have loaded it
+            const int need = r - LDG + 2;
+            sweep_wait<0>([&] { space_known = min(ld_flag(done + max(j - 1, 0)), ld_flag(done + max(j - 2, 0))); return space_known >= need; },
+                          g.spin_limit, err, dead);
+        }
+        if (active) {
+            if (j >= 1) st_regs<N>(wrV + GEN * genStride, LtV);
+            if (j >= 2) st_regs<N>(wrB + GEN * genStride, LtB);
+        }
+        __syncwarp();
+        if (lane == 0) st_flag(done + j, r + 1);
+        if (producer) {
+            const int need = r - kXK + 1;      // generation r % kXK held row r - kXK
+            if (need > prog_known) sweep_wait<0>([&] { prog_known = ld_relaxed_gpu(prog_c); return prog_known >= need; }, g.spin_limit, err, dead);
+            if (active) {
+                const int go = (r & (kXK - 1)) * recGen;
+#pragma unroll
+                for (int q = 0; q < N; q++) {
+                    if (j == 0) st_volatile_v2(pubV + go + q, LtV[q], uint32_t(r + 1));
+                    st_volatile_v2(pubB + go + q, LtB[q], uint32_t(r + 1));
+                }
+            }
+        }
+        // ---- down-right: registers only
+        path_step<N>(Cc, LtA, Ln, lc);
+        add(Ln);
+        if (!CLAMP_EACH) {
+#pragma unroll
+            for (int q = 0; q < N; q++) S[q] = __vminu2(S[q], kMaxCostX2);
+        }
+        if (DO_WTA) {
+            if (!FULL) {
+#pragma unroll
+                for (int q = 0; q < N; q++) {   // cells beyond D never win and never veto
+                    const int k = lane * N + q;
+                    if (k >= g.w.D) S[q] = 0xFFFFFFFFu;
+                    else if (k + Dh >= g.w.D) S[q] |= 0xFFFF0000u;
+                }
+            }
+            if (r >= kStage) sweep_wait<0>([&] { return ld_flag(wtake + j) >= r - kStage + 1; }, g.spin_limit, err, dead);
+            if (active) st_regs<N>(stage + Q * ringSlot + lo, S);
+            __syncwarp();
+            if (lane == 0) st_flag(wfill + j, r + 1);
+        } else {
+            if (active) st_regs<N>(Svol + offCur, S);
+        }
+        offCur += rowStep;
+        if (++xcur == W1) { xcur = 0; offCur -= wrapBack; }
+    };
+
+    int r = 0;
+    for (; r + 3 < H; r += 4) {
+        row(std::integral_constant<int, 0>{}, r);
+        row(std::integral_constant<int, 1>{}, r + 1);
+        row(std::integral_constant<int, 2>{}, r + 2);
+        row(std::integral_constant<int, 3>{}, r + 3);
+    }
+    const int rem = H - r;
+    if (rem > 0) row(std::integral_constant<int, 0>{}, r);
+    if (rem > 1) row(std::integral_constant<int, 1>{}, r + 1);
+    if (rem > 2) row(std::integral_constant<int, 2>{}, r + 2);
+    cp_async_wait<0>();
+}
+
+}  // namespace b200sgm

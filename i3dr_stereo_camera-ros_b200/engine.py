@@ -22,7 +22,7 @@ SYMBOLS = (
     "b200sgm_last_error", "b200sgm_version", "b200sgm_launch_count", "b200sgm_lane_stream", "b200sgm_debug_read",
     "b200sgm_debug_set_path", "b200sgm_profile", "b200sgm_stage_times", "b200sgm_alu_peak", "b200sgm_stage_timeline",
     "b200sgm_set_camera", "b200sgm_rectify", "b200sgm_rectify_device", "b200sgm_rectify_maps", "b200sgm_bm_compute",
-    "b200sgm_bm_compute_device",
+    "b200sgm_bm_compute_device", "b200sgm_lane_status",
 )
 
 STAGES = ("prefilter", "cost", "horizontal", "vertical_wta", "lrcheck", "median", "speckle")
@@ -77,6 +77,7 @@ class Engine:
         self.device = device
         self.lanes = lanes
         self.params = None
+        self.last_warning = None
         if params is not None:
             self.set_params(params)
 
@@ -92,8 +93,16 @@ class Engine:
             pass
 
     def _check(self, rc):
-        if rc != 0:
+        """Negative codes raise; positive codes are warnings (the result was delivered): kept in `last_warning`."""
+        if rc < 0:
             raise B200SGMError(rc, self.lib.b200sgm_last_error(self.h).decode())
+        self.last_warning = (rc, self.lib.b200sgm_last_error(self.h).decode()) if rc > 0 else None
+
+    def lane_status(self, lane=0) -> int:
+        """Status of the last frame of `lane` (after the caller synchronised its stream): 0, WARN_COST_RANGE (1); raises on error."""
+        rc = self.lib.b200sgm_lane_status(self.h, int(lane))
+        self._check(rc)
+        return rc
 
     def set_params(self, p: SGBMParams):
         cp = p.to_c()

@@ -3,8 +3,12 @@
 // src/init_stereo_matchers.cpp:39-66).  Reads two raw 8-bit images, writes the CV_32F disparity the node would receive.
 //
 //   harness <left.raw> <right.raw> <width> <height> <out.f32> minD D window uniq speckleRange speckleSize cap p1 p2 [fullDP]
-//           [algorithm: 0 = B200 SGM (default), 1 = B200 block matcher] [textureThreshold]
+//           [algorithm: 0 = B200 SGM (default), 1 = B200 block matcher] [textureThreshold] [--bench N]
+// --bench N: after the first match, times N more stereo_match() calls on the same pair (the per-frame cost the node pays:
+// setImages copy + match + getDisparity copy) and prints "bench_ms_per_frame <ms>" on stderr.
+#include <chrono>
 #include <cstdio>
+#include <cstring>
 #include <cstdlib>
 #include <fstream>
 #include <iostream>
@@ -92,6 +96,9 @@ int main(int argc, char **argv)
   _fullDP = argc > 15 && atoi(argv[15]) != 0;
   _stereo_algorithm = argc > 16 ? atoi(argv[16]) : 0;
   if (argc > 17) _texture_threshold = atoi(argv[17]);
+  int bench_frames = 0;
+  for (int i = 15; i + 1 < argc; i++)
+    if (!strcmp(argv[i], "--bench")) bench_frames = atoi(argv[i + 1]);
 
   // warm-up exactly like init_stereo_matchers.cpp:41-56: a 10x10 zero pair through setImages/match/getDisparity
   {
@@ -105,6 +112,15 @@ int main(int argc, char **argv)
   cv::Mat disp = stereo_match(left, right);
   if (disp.empty()) return 1;
   if (disp.type() != CV_32F) { std::cerr << "unexpected disparity type" << std::endl; return 1; }
+  if (bench_frames > 0) {
+    const auto t0 = std::chrono::steady_clock::now();
+    for (int i = 0; i < bench_frames; i++) {
+      cv::Mat d = stereo_match(left, right);
+      if (d.empty()) return 1;
+    }
+    const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count() / bench_frames;
+    std::cerr << "bench_ms_per_frame " << ms << std::endl;
+  }
   std::ofstream o(argv[5], std::ios::binary);
   for (int y = 0; y < disp.rows; y++) o.write(reinterpret_cast<const char *>(disp.data + y * disp.step), size_t(disp.cols) * 4);
   // mismatched sizes must leave the previous images untouched and still succeed (abstractStereoMatcher.cpp:21-24)

@@ -75,6 +75,13 @@ CONFIGS = {
 }
 CONFIGS["c4"] = Config("c4", 2448, 2048, CONFIGS["c3"].params, "stream of c3 frames sharded over GPUs")
 CONFIGS["c5"] = Config("c5", 2448, 2048, CONFIGS["c3"].params, "c3 + processDisparity + reprojection to XYZ")
+# cL: what `roslaunch ... stereo_algorithm:=1` installs (/root/reference/launch/stereo_matcher.launch:37-48) on the camera's
+# default frame (launch/stereo_capture.launch:14-15).  blockSize 21 with preFilterCap 7 sits in the regime where the int16
+# cost bound bs^2 * (2*ftzero + 63) = 41 013 exceeds 32 767 on adversarial data.
+CONFIGS["cL"] = Config("cL", 2448, 2048,
+                       SGBMParams(minDisparity=147, numDisparities=480, blockSize=21, uniquenessRatio=2, speckleWindowSize=1000,
+                                  speckleRange=4, preFilterCap=7, P1=200, P2=400),
+                       "2448x2048, minD 147, 480 disparities, window 21: the reference's launch-file default for SGBM")
 
 # c5 camera model: fx=f=2400, cx=cxr=1224, cy=1024, baseline 0.3 m
 C5_CAMERA = dict(fx=2400.0, cx=1224.0, cxr=1224.0, cy=1024.0, p14=-2400.0 * 0.3, depth_min=0.0, depth_max=10.0)

@@ -28,6 +28,11 @@ extern "C" {
 #define B200SGM_ECUDA (-2)    /* CUDA runtime error (no device, launch failure, out of memory) */
 #define B200SGM_ESIZE (-3)    /* image larger than the engine was created for                  */
 #define B200SGM_ESTATE (-4)   /* call sequence error (e.g. wait on an idle lane)               */
+/* Positive = warning: the result was produced and delivered, but the frame left cv::StereoSGBM's defined range: some
+ * cost-volume cell C satisfied C + P2 > 32767, where OpenCV's int16 arithmetic wraps or saturates depending on its
+ * build (possible only when blockSize^2 * (2*max(preFilterCap,15)|1 + 63) + P2 > 32767, e.g. the launch-file default
+ * window 21).  Returned by b200sgm_wait / b200sgm_compute* / b200sgm_lane_status; b200sgm_last_error has the figure. */
+#define B200SGM_WARN_COST_RANGE 1
 
 #define B200SGM_MODE_SGBM 0   /* 5 aggregation paths, single top-down sweep (cv::StereoSGBM::MODE_SGBM) */
 #define B200SGM_MODE_HH 1     /* 8 aggregation paths, two sweeps            (cv::StereoSGBM::MODE_HH)   */
@@ -109,6 +114,10 @@ int b200sgm_compute_device(b200sgm_handle h, int lane, const uint8_t *d_left, si
 int b200sgm_enqueue(b200sgm_handle h, int lane, const uint8_t *left, size_t left_stride, const uint8_t *right,
                     size_t right_stride, int width, int height, int16_t *disp, size_t disp_stride);
 int b200sgm_wait(b200sgm_handle h, int lane);
+/* Status of the most recent frame of `lane` for callers of b200sgm_compute_device: call after synchronising the
+ * stream the frame ran on.  B200SGM_OK, B200SGM_WARN_COST_RANGE, or B200SGM_ECUDA when the frame's aggregation kernel
+ * gave up on an inter-strip wait (its disparity is then invalid; the next frame starts from a clean state). */
+int b200sgm_lane_status(b200sgm_handle h, int lane);
 
 /* ---- the steps either side of the path (rows a11 and R of SURVEY.md section 8) ----------------------------- */
 

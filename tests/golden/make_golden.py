@@ -57,7 +57,7 @@ def main():
     import cv2
     crc["opencv_version"] = cv2.__version__
     crc["numpy_version"] = np.__version__
-    for name in ("c1", "c2", "c3"):
+    for name in ("c1", "c2", "c3", "cL"):
         c = CONFIGS[name]
         p = c.params
         L, R = synth.make_pair(c.width, c.height, p.numDisparities, p.minDisparity, 1000)

@@ -189,6 +189,56 @@ def test_config_c3_full_size_golden_crc_and_properties(golden_crc):
     eng.close()
 
 
+def test_config_cL_reference_launch_default(golden_crc):
+    """cL = what `roslaunch stereo_matcher.launch stereo_algorithm:=1` installs (/root/reference/launch/stereo_matcher.launch:37-48):
+    2448x2048, minD 147, 480 disparities, window 21, uniqueness 2, speckle 1000/4, cap 7.  Pinned by the cv2 golden CRC (and by
+    cv2 live when importable); must run on the fused path (480 disparities: 8 packed registers per lane) without warnings."""
+    c = CONFIGS["cL"]
+    p = c.params
+    L, R = synth.make_pair(c.width, c.height, p.numDisparities, p.minDisparity, 1000)
+    assert synth.crc32(L) == golden_crc["cL"]["left"] and synth.crc32(R) == golden_crc["cL"]["right"]
+    eng = Engine(0, c.width, c.height, p.numDisparities, 1, p)
+    got = eng.compute(L, R)
+    assert eng.last_warning is None
+    assert synth.crc32(got) == golden_crc["cL"]["disp"]
+    assert int(got.astype(np.int64).sum()) == golden_crc["cL"]["disp_sum"]
+    assert (got[:, :p.min_x1()] == p.invalid()).all()
+    if ref.have_cv2():
+        L2, R2 = synth.make_pair(c.width, c.height, p.numDisparities, p.minDisparity, 1001)
+        assert np.array_equal(eng.compute(L2, R2), ref.compute(L2, R2, p))
+    eng.close()
+
+
+def test_wide_disparity_ranges_on_the_fused_path():
+    """Disparity counts above 256 (8 and 16 packed registers per lane, shallower rings) against the oracle, incl. padded counts."""
+    for W, H, D, minD, bs in [(700, 60, 480, 147, 21), (640, 48, 512, 0, 9), (600, 40, 320, -16, 5), (1400, 30, 1024, 0, 5)]:
+        p = SGBMParams(minDisparity=minD, numDisparities=D, blockSize=bs, preFilterCap=7 if bs == 21 else 31)
+        L, R = synth.make_pair(W, H, D, minD, 5 + D)
+        for mode in (0, 1):
+            q = p.replace(mode=mode)
+            assert np.array_equal(run_gpu(L, R, q), oracle.compute(L, R, q)), (W, H, D, minD, bs, mode)
+
+
+def test_cost_range_warning_and_lane_status():
+    """int16 contract guard: a frame whose largest cost-volume cell + P2 exceeds 32767 is delivered with a warning
+    (B200SGM_WARN_COST_RANGE) -- uncorrelated noise through a 21x21 window at the launch-default cap; the same images
+    inside the contract (window 9) raise nothing.  A failed or flagged frame does not poison the next one."""
+    rng = np.random.default_rng(5)
+    W, H, D = 400, 120, 64
+    L = rng.integers(0, 256, (H, W)).astype(np.uint8)
+    R = rng.integers(0, 256, (H, W)).astype(np.uint8)
+    eng = Engine(0, W, H, D, 1, SGBMParams(numDisparities=D, blockSize=21, preFilterCap=63, P2=8000))
+    eng.compute(L, R)
+    assert eng.last_warning is not None and eng.last_warning[0] == 1, eng.last_warning
+    assert eng.lane_status(0) == 1
+    p = SGBMParams(numDisparities=D)
+    eng.set_params(p)
+    got = eng.compute(L, R)
+    assert eng.last_warning is None and eng.lane_status(0) == 0
+    assert np.array_equal(got, oracle.compute(L, R, p))
+    eng.close()
+
+
 @pytest.mark.skipif(not ref.have_cv2(), reason="cv2 not importable")
 def test_live_cv2_reference_call_sequence():
     """Same inputs through the reference's own call sequence on OpenCV (oracle/cv2_reference.py)."""
