@@ -63,6 +63,17 @@ int launch_sweep_t(b200sgm_engine* h, Lane& ln, const Eff& e, const SweepPlan& v
     g.P1 = e.P1; g.P2 = e.P2;
     g.spin_limit = (long long)h->clock_khz * 500;   // ~0.5 s of SM clock ticks
     { static const int dbg = [] { const char* v = getenv("B200SGM_DEBUG_VERT"); return v ? atoi(v) : 0; }(); g.debug_flags = dbg; }
+    { static const int slp = [] { const char* v = getenv("B200SGM_SLEEP_NS"); return v ? atoi(v) : 40; }(); g.sleep_ns = slp; }
+    g.trace = nullptr; g.trace_strip = 0; g.trace_row0 = 0;
+    {
+        static const char* tr = getenv("B200SGM_TRACE");     // "strip,row0": development only
+        if (tr && DO_WTA) {
+            if (!h->trace) { CUDA_TRY(h, cudaMalloc(&h->trace, kTraceBytes)); }
+            CUDA_TRY(h, cudaMemsetAsync(h->trace, 0, kTraceBytes, st));
+            g.trace = h->trace;
+            sscanf(tr, "%d,%d", &g.trace_strip, &g.trace_row0);
+        }
+    }
     const int nthreads = 32 * ((DO_WTA ? 2 : 1) * vp.twmax + 1);
     auto kern = k_sweep<N, SweepCfg<N>::RING, SweepCfg<N>::LDG, UP, DO_WTA, FULL, CLAMP_EACH>;
     {

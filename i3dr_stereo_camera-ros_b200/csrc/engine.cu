@@ -252,7 +252,7 @@ int b200sgm_destroy(b200sgm_handle h)
     cudaSetDevice(h->device);
     for (Lane& ln : h->lanes) { if (ln.stream) cudaStreamSynchronize(ln.stream); free_lane(ln); }
     for (auto& r : h->rect) { cudaFree(r.ent); cudaFree(r.map1); cudaFree(r.map2); }
-    cudaFree(h->d_wtab); cudaFree(h->rect_src); cudaFree(h->rect_dst);
+    cudaFree(h->d_wtab); cudaFree(h->rect_src); cudaFree(h->rect_dst); cudaFree(h->trace);
     delete h;
     return B200SGM_OK;
 }
@@ -641,8 +641,10 @@ int b200sgm_debug_read(b200sgm_handle h, int lane, const char* what, void* host,
     else if (!strcmp(what, "S")) src = ln.S;
     else if (!strcmp(what, "wta")) src = ln.disp_wta;
     else if (!strcmp(what, "median")) src = ln.disp_med;
-    else if (!strcmp(what, "stats")) src = ln.d_err;     // {error flag, late exchange records, poll iterations, -}
+    else if (!strcmp(what, "stats")) src = ln.d_err;     // {error flag, late exchange records, poll iterations, max cost}
+    else if (!strcmp(what, "trace")) src = h->trace;      // k_sweep time stamps (B200SGM_TRACE), kTraceBytes
     else return fail(h, B200SGM_EINVAL, "unknown debug buffer");
+    if (!src) return fail(h, B200SGM_ESTATE, "debug buffer not allocated");
     if (dp) {
         Eff e;
         if (make_eff(h, 1, 1, e) == 0) *dp = e.Dp;

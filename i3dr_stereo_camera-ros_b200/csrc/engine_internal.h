@@ -51,6 +51,7 @@ constexpr int kStages = 7;    // prefilter, cost, horizontal, vertical+wta, lrch
 constexpr int kProfRing = 256;
 constexpr int kMaxStrips = 320;
 constexpr int kStatusWords = 4;
+constexpr size_t kTraceBytes = 32 * 32 * 4 * sizeof(long long);
 
 // Cooperative sweeps of ALL engines of a process on one device are serialised: one sweep fills every SM, and two
 // partially resident sweeps would spin on CTAs that can never be scheduled.  Process-wide, keyed by device; the events
@@ -79,6 +80,7 @@ struct b200sgm_engine {
     cudaEvent_t prof_ref = nullptr;   // time origin of the stage timeline
     int num_sms = 148;
     int max_smem_optin = 227 * 1024;
+    long long* trace = nullptr;                   // development: k_sweep time stamps (B200SGM_TRACE)
     int clock_khz = 1965000;
     std::mutex mu;
     // rectification (row N2): per camera (0 left, 1 right) the model and the cached fixed-point maps

@@ -41,7 +41,11 @@ struct SweepGeom {
     int P1, P2;
     long long spin_limit; // clock64 ticks before a wait gives up
     int debug_flags;      // 8: timing experiment, ignore record tags (wrong results)
+    int sleep_ns;         // back-off of the waits that are expected to block (WTA warps, agent); 0 = spin
+    long long* trace;     // development: clock64 stamps of strip `trace_strip`, rows trace_row0 .. +31 (nullptr = off)
+    int trace_strip, trace_row0;
 };
+constexpr int kTracePoints = 4;
 
 // xbuf: [0, 4 KB) progress words (one int per strip), then records [3 kinds][nstrips][kXK][Dp/2] of {data, tag}
 inline size_t sweep_xbuf_bytes(int nstrips, int Dp) { return 4096 + size_t(3) * nstrips * kXK * (Dp / 2) * sizeof(uint2); }
@@ -61,6 +65,11 @@ __device__ __forceinline__ int ld_flag(const int* p)
     asm volatile("ld.volatile.shared.b32 %0, [%1];" : "=r"(v) : "r"(uint32_t(__cvta_generic_to_shared(p))) : "memory");
     return v;
 }
+__device__ __forceinline__ void st_flag_fenced(int* p, int v, bool fence)
+{
+    if (fence) __threadfence_block();
+    asm volatile("st.volatile.shared.b32 [%0], %1;" ::"r"(uint32_t(__cvta_generic_to_shared(p))), "r"(v) : "memory");
+}
 __device__ __forceinline__ void st_flag(int* p, int v)
 {
     asm volatile("st.volatile.shared.b32 [%0], %1;" ::"r"(uint32_t(__cvta_generic_to_shared(p))), "r"(v) : "memory");
@@ -73,17 +82,17 @@ __device__ __forceinline__ int ld_relaxed_gpu(const int* p)
 }
 __device__ __forceinline__ void st_relaxed_gpu(int* p, int v) { asm volatile("st.relaxed.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
 
-// Waits until ready() holds.  SLEEP > 0: back off between polls (waits that are expected to block).  A wait that
+// Waits until ready() holds.  sleep_ns > 0: back off between polls (waits that are expected to block).  A wait that
 // exceeds the limit, or that sees the error word set by somebody else, raises the error word and marks this warp dead:
 // it then stops waiting altogether (the frame is reported as failed by the host).
-template <int SLEEP, typename F>
-__device__ __forceinline__ void sweep_wait(F ready, long long limit, int* err, bool& dead)
+template <typename F>
+__device__ __forceinline__ void sweep_wait(int sleep_ns, F ready, long long limit, int* err, bool& dead)
 {
     if (dead || ready()) return;
     const long long t0 = clock64();
     int spins = 0;
     while (!ready()) {
-        if (SLEEP > 0) __nanosleep(SLEEP);
+        if (sleep_ns > 0) __nanosleep(sleep_ns);
         if ((++spins & 63) == 0 && (clock64() - t0 > limit || *reinterpret_cast<volatile int*>(err))) {
             atomicExch(err, 1);
             dead = true;
@@ -161,6 +170,13 @@ __global__ void __launch_bounds__(sweep_max_threads(N), 1) k_sweep(const uint16_
     const int lo = lane * 2 * N;
     const int agent_w = DO_WTA ? 2 * tw : tw;
     bool dead = false;
+    const bool fence = (g.debug_flags & 32) != 0;   // experiment: membar.cta between hand-over data and its row counter
+    const int psleep = (g.debug_flags & 64) ? g.sleep_ns : 0;   // experiment: path-warp waits back off as well
+    // trace slot of this warp: [warp][row - trace_row0][point]
+    auto stamp = [&](int r, int k) {
+        if (g.trace != nullptr && b == g.trace_strip && lane == 0 && unsigned(r - g.trace_row0) < 32u)
+            g.trace[(size_t(w) * 32 + (r - g.trace_row0)) * kTracePoints + k] = clock64();
+    };
 
     if (w == agent_w) {
         // ================================ agent warp ================================
@@ -176,7 +192,8 @@ __global__ void __launch_bounds__(sweep_max_threads(N), 1) k_sweep(const uint16_
         for (int rr = 0; rr + 1 < H; rr++) {
             // generation rr % LDG still holds row rr - LDG until warps TW-1 and TW-2 have loaded it (their row rr - LDG + 1)
             const int need = rr - LDG + 2;
-            if (need > 0) sweep_wait<40>([&] { return min(ld_flag(done + TW - 1), ld_flag(done + TW - 2)) >= need; }, g.spin_limit, err, dead);
+            if (need > 0) sweep_wait(g.sleep_ns, [&] { return min(ld_flag(done + TW - 1), ld_flag(done + TW - 2)) >= need; }, g.spin_limit, err, dead);
+            stamp(rr, 0);
             uint32_t dv0[N], db0[N], db1[N];
 #pragma unroll
             for (int q = 0; q < N; q++) { dv0[q] = 0; db0[q] = 0; db1[q] = 0; }
@@ -194,11 +211,13 @@ __global__ void __launch_bounds__(sweep_max_threads(N), 1) k_sweep(const uint16_
                 }
                 return __all_sync(kFullMask, ok) || (g.debug_flags & 8);
             };
-            sweep_wait<0>(poll, g.spin_limit, err, dead);
+            sweep_wait(0, poll, g.spin_limit, err, dead);
+            stamp(rr, 1);
             if (active) {
                 const int go2 = (rr & (LDG - 1)) * genStride;
                 st_regs<N>(dV0 + go2, dv0); st_regs<N>(dB0 + go2, db0); st_regs<N>(dB1 + go2, db1);
             }
+            if (fence) __threadfence_block();
             __syncwarp();
             if (lane == 0) {
                 st_flag(done + TW, rr + 1);
@@ -226,7 +245,9 @@ __global__ void __launch_bounds__(sweep_max_threads(N), 1) k_sweep(const uint16_
         int pending = 0, rb = 0;            // rows parked in acc, first of them
         auto batch = [&](auto q0_tag, int r, int cnt) {
             constexpr int Q0 = decltype(q0_tag)::value;
-            sweep_wait<40>([&] { return ld_flag(wfill + j) >= r + cnt; }, g.spin_limit, err, dead);
+            stamp(r, 0);
+            sweep_wait(g.sleep_ns, [&] { return ld_flag(wfill + j) >= r + cnt; }, g.spin_limit, err, dead);
+            stamp(r, 1);
             uint16_t* sc = stage + Q0 * ringSlot;
             if (wc.f > 0) {
                 wta_vec<N>(sc, ringSlot, r, g.w, wc, lane, active, acc);   // a row past the end lands in a lane >= cnt of the flush
@@ -244,8 +265,10 @@ __global__ void __launch_bounds__(sweep_max_threads(N), 1) k_sweep(const uint16_
                     if (lane == 0) disp[size_t(y) * g.w.W + x1 + g.w.minX1] = int16_t(d);
                 }
             }
+            if (fence) __threadfence_block();
             __syncwarp();
             if (lane == 0) st_flag(wtake + j, r + cnt);
+            stamp(r, 2);
         };
         static_assert(kWB == 2 && kStage == 4, "two batches per stage-ring revolution");
         int r = 0;
@@ -301,6 +324,7 @@ __global__ void __launch_bounds__(sweep_max_threads(N), 1) k_sweep(const uint16_
     auto row = [&](auto q_tag, int r) {
         constexpr int Q = decltype(q_tag)::value;          // r & 3
         constexpr int GEN = Q % LDG, PGEN = (Q + 3) % LDG;  // hand-over generation written (row r) / read (row r-1)
+        stamp(r, 0);
         issue(r + RING - 1);
         cp_async_commit();
         if (producer) {
@@ -323,9 +347,10 @@ __global__ void __launch_bounds__(sweep_max_threads(N), 1) k_sweep(const uint16_
             for (int q = 0; q < N; q++) { Cc[q] = kMaxCostX2; S[q] = 0; }
         }
         if (fV < r || fB < r) {        // a neighbour has not published row r-1 yet: wait, then load again
-            sweep_wait<0>([&] { return ld_flag(flagV) >= r && ld_flag(flagB) >= r; }, g.spin_limit, err, dead);
+            sweep_wait(psleep, [&] { return ld_flag(flagV) >= r && ld_flag(flagB) >= r; }, g.spin_limit, err, dead);
             if (active) { ld_regs<N>(rdV + PGEN * genStride, LtV); ld_regs<N>(rdB + PGEN * genStride, LtB); }
         }
+        stamp(r, 1);
         if (xcur == W1 - 1) {
 #pragma unroll
             for (int q = 0; q < N; q++) LtB[q] = 0;
@@ -345,18 +370,20 @@ __global__ void __launch_bounds__(sweep_max_threads(N), 1) k_sweep(const uint16_
         add(Ln);
         if (r - LDG + 2 > space_known) {   // generation GEN still holds row r-LDG until warps j-1 / j-2 have loaded it
             const int need = r - LDG + 2;
-            sweep_wait<0>([&] { space_known = min(ld_flag(done + max(j - 1, 0)), ld_flag(done + max(j - 2, 0))); return space_known >= need; },
+            sweep_wait(psleep, [&] { space_known = min(ld_flag(done + max(j - 1, 0)), ld_flag(done + max(j - 2, 0))); return space_known >= need; },
                           g.spin_limit, err, dead);
         }
         if (active) {
             if (j >= 1) st_regs<N>(wrV + GEN * genStride, LtV);
             if (j >= 2) st_regs<N>(wrB + GEN * genStride, LtB);
         }
+        if (fence) __threadfence_block();
         __syncwarp();
         if (lane == 0) st_flag(done + j, r + 1);
+        stamp(r, 2);
         if (producer) {
             const int need = r - kXK + 1;      // generation r % kXK held row r - kXK
-            if (need > prog_known) sweep_wait<0>([&] { prog_known = ld_relaxed_gpu(prog_c); return prog_known >= need; }, g.spin_limit, err, dead);
+            if (need > prog_known) sweep_wait(psleep, [&] { prog_known = ld_relaxed_gpu(prog_c); return prog_known >= need; }, g.spin_limit, err, dead);
             if (active) {
                 const int go = (r & (kXK - 1)) * recGen;
 #pragma unroll
@@ -382,13 +409,15 @@ __global__ void __launch_bounds__(sweep_max_threads(N), 1) k_sweep(const uint16_
                     else if (k + Dh >= g.w.D) S[q] |= 0xFFFF0000u;
                 }
             }
-            if (r >= kStage) sweep_wait<0>([&] { return ld_flag(wtake + j) >= r - kStage + 1; }, g.spin_limit, err, dead);
+            if (r >= kStage) sweep_wait(psleep, [&] { return ld_flag(wtake + j) >= r - kStage + 1; }, g.spin_limit, err, dead);
             if (active) st_regs<N>(stage + Q * ringSlot + lo, S);
+            if (fence) __threadfence_block();
             __syncwarp();
             if (lane == 0) st_flag(wfill + j, r + 1);
         } else {
             if (active) st_regs<N>(Svol + offCur, S);
         }
+        stamp(r, 3);
         offCur += rowStep;
         if (++xcur == W1) { xcur = 0; offCur -= wrapBack; }
     };
