@@ -36,7 +36,7 @@ int launch_paths_generic(b200sgm_engine* h, Lane& ln, const Eff& e, cudaStream_t
 // ---- fused path: k_horiz + cooperative k_sweep --------------------------------------------------------
 struct SweepPlan { bool ok; int nstrips, twmax; size_t smem; };
 
-template <int N> struct SweepCfg { static constexpr int RING = N >= 8 ? 4 : 8, LDG = N >= 8 ? 2 : 4, MAXT = sweep_max_threads(N); };
+template <int N> struct SweepCfg { static constexpr int RING = N >= 8 ? 4 : 8, MAXT = sweep_max_threads(N); };
 
 template <int N>
 inline SweepPlan plan_sweep(const b200sgm_engine* h, const Eff& e, bool wta)
@@ -49,7 +49,7 @@ inline SweepPlan plan_sweep(const b200sgm_engine* h, const Eff& e, bool wta)
     // wider than one co-resident wave of strips (or than a CTA has warps): use the hybrid path
     if (tw > kSweepMaxTW || 32 * (2 * tw + 1) > SweepCfg<N>::MAXT) return p;
     p.nstrips = n; p.twmax = tw;
-    p.smem = sweep_smem_bytes(tw, e.Dp, SweepCfg<N>::RING, SweepCfg<N>::LDG, wta);
+    p.smem = sweep_smem_bytes(tw, e.Dp, SweepCfg<N>::RING, wta);
     p.ok = p.smem <= size_t(h->max_smem_optin);
     return p;
 }
@@ -63,7 +63,6 @@ int launch_sweep_t(b200sgm_engine* h, Lane& ln, const Eff& e, const SweepPlan& v
     g.P1 = e.P1; g.P2 = e.P2;
     g.spin_limit = (long long)h->clock_khz * 500;   // ~0.5 s of SM clock ticks
     { static const int dbg = [] { const char* v = getenv("B200SGM_DEBUG_VERT"); return v ? atoi(v) : 0; }(); g.debug_flags = dbg; }
-    { static const int slp = [] { const char* v = getenv("B200SGM_SLEEP_NS"); return v ? atoi(v) : 40; }(); g.sleep_ns = slp; }
     g.trace = nullptr; g.trace_strip = 0; g.trace_row0 = 0;
     {
         static const char* tr = getenv("B200SGM_TRACE");     // "strip,row0": development only
@@ -75,7 +74,7 @@ int launch_sweep_t(b200sgm_engine* h, Lane& ln, const Eff& e, const SweepPlan& v
         }
     }
     const int nthreads = 32 * ((DO_WTA ? 2 : 1) * vp.twmax + 1);
-    auto kern = k_sweep<N, SweepCfg<N>::RING, SweepCfg<N>::LDG, UP, DO_WTA, FULL, CLAMP_EACH>;
+    auto kern = k_sweep<N, SweepCfg<N>::RING, UP, DO_WTA, FULL, CLAMP_EACH>;
     {
         static std::atomic<unsigned long long> attr_done{0};   // per instantiation and device: raise the dynamic shared-memory limit once
         const unsigned long long bit = 1ull << (h->device & 63);

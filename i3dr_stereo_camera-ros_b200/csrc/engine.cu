@@ -182,7 +182,7 @@ void free_lane(Lane& ln)
     cudaFree(ln.disp2key); cudaFree(ln.disp_wta); cudaFree(ln.disp_med); cudaFree(ln.disp_out); cudaFree(ln.label);
     cudaFree(ln.csize); cudaFree(ln.parent); cudaFree(ln.runlen); cudaFree(ln.f32a); cudaFree(ln.f32b); cudaFree(ln.points); cudaFree(ln.block_count); cudaFree(ln.total);
     if (ln.h_total) cudaFreeHost(ln.h_total);
-    cudaFree(ln.xbuf); cudaFree(ln.d_err);
+    cudaFree(ln.xbuf); cudaFree(ln.d_err); cudaFree(ln.color);
     if (ln.h_err) cudaFreeHost(ln.h_err);
     for (auto ev : ln.prof_events) cudaEventDestroy(ev);
     if (ln.done) cudaEventDestroy(ln.done);
@@ -395,13 +395,25 @@ int b200sgm_compute_xyz(b200sgm_handle h, const uint8_t* left, size_t left_strid
     if (rc) return rc;
     const int npix = width * height;
     const int nblk = (npix + 255) / 256;
-    ReprojGeom g{width, height, rp->q03, rp->q13, rp->wz, rp->q32, rp->q33, rp->depth_min, rp->depth_max, rp->min_disparity, rp->max_disparity};
+    if (rp->color && (rp->color_channels != 1 && rp->color_channels != 3)) return fail(h, B200SGM_EINVAL, "color_channels must be 1 (MONO8) or 3 (BGR8)");
+    if (rp->color && rp->color_stride < size_t(width) * rp->color_channels) return fail(h, B200SGM_EINVAL, "color stride smaller than a row");
+    ReprojGeom g{width, height, rp->q03, rp->q13, rp->wz, rp->q32, rp->q33, rp->min_disparity, rp->max_disparity, rp->depth_min, rp->depth_max};
+    const uint8_t* d_color = ln.left;
+    size_t color_pitch = size_t(width);
+    int channels = 1;
+    if (rp->color && points) {
+        channels = rp->color_channels;
+        color_pitch = size_t(width) * channels;
+        if (!ln.color) CUDA_TRY(h, cudaMalloc(&ln.color, size_t(h->maxW) * h->maxH * 3));
+        CUDA_TRY(h, cudaMemcpy2DAsync(ln.color, color_pitch, rp->color, rp->color_stride, color_pitch, height, cudaMemcpyHostToDevice, st));
+        d_color = ln.color;
+    }
     k_reproject_count<<<nblk, 256, 0, st>>>(ln.disp_out, g, ln.f32a, ln.f32b, ln.block_count);
     LAUNCH_CHECK(h);
     k_scan_blocks<<<1, 1024, 0, st>>>(ln.block_count, nblk, ln.total);
     LAUNCH_CHECK(h);
     if (points) {
-        k_reproject_write<<<nblk, 256, 0, st>>>(ln.disp_out, ln.left, size_t(width), g, ln.block_count, ln.points);
+        k_reproject_write<<<nblk, 256, 0, st>>>(ln.disp_out, d_color, color_pitch, channels, g, ln.block_count, ln.points);
         LAUNCH_CHECK(h);
     }
     CUDA_TRY(h, cudaMemcpyAsync(ln.h_total, ln.total, 4, cudaMemcpyDeviceToHost, st));
@@ -413,6 +425,22 @@ int b200sgm_compute_xyz(b200sgm_handle h, const uint8_t* left, size_t left_strid
     if (count) *count = n;
     if (points && n) CUDA_TRY(h, cudaMemcpy(points, ln.points, size_t(n) * sizeof(b200sgm_point), cudaMemcpyDeviceToHost));
     return frame_status(h, ln);
+}
+
+void b200sgm_reproject_from_camera(b200sgm_reproject* rp, const double* Kl, const double* Pl, const double* Pr, double depth_min, double depth_max)
+{
+    if (!rp || !Kl || !Pl || !Pr) return;
+    // calc_q (disparity_to_depth.cpp:62-85): note fx comes from K_l, the principal points from P_l / P_r
+    const double cx = Pl[2], cxr = Pr[2], cy = Pl[6], fx = Kl[0];
+    const double T = -Pr[3] / fx;
+    rp->q03 = float(-cx); rp->q13 = float(-cy); rp->wz = float(fx); rp->q32 = float(1.0 / T); rp->q33 = float(-(cx - cxr) / T);
+    // processDisparity (generate_disparity.cpp:441-450): DisparityImage.f / .T are float32 fields
+    const float f32 = float(Pl[0]), T32 = float(-Pr[3] / Pr[0]);
+    const float tf = T32 * f32;
+    rp->min_disparity = float(double(tf) / depth_max);
+    rp->max_disparity = float(double(tf) / depth_min);     // depth_min == 0 -> +inf, like the reference
+    rp->depth_min = depth_min; rp->depth_max = depth_max;
+    rp->color = nullptr; rp->color_stride = 0; rp->color_channels = 0;
 }
 
 const char* b200sgm_last_error(b200sgm_handle h) { return h ? h->err.c_str() : "null handle"; }

@@ -175,7 +175,8 @@ static __global__ void k_to_f32(const int16_t* __restrict__ src, float* __restri
 // and an order-preserving compaction of the kept points (row-major scan order).
 struct ReprojGeom {
     int W, H;
-    float q03, q13, wz, q32, q33, depth_min, depth_max, min_disp, max_disp;
+    float q03, q13, wz, q32, q33, min_disp, max_disp;
+    double depth_min, depth_max;     // the reference compares the float Z with its double parameters (disparity_to_depth.cpp:175)
 };
 
 __device__ __forceinline__ bool reproject_pixel(const ReprojGeom& g, int i, int j, int d16, float& dm, float& X, float& Y, float& Z)
@@ -189,7 +190,7 @@ __device__ __forceinline__ bool reproject_pixel(const ReprojGeom& g, int i, int 
     X = __fdiv_rn(__fadd_rn(float(j), g.q03), w);
     Y = __fdiv_rn(__fadd_rn(float(i), g.q13), w);
     Z = __fdiv_rn(g.wz, w);
-    return w > 0.0f && Z > 0.0f && Z <= g.depth_max && Z >= g.depth_min;
+    return w > 0.0f && Z > 0.0f && double(Z) <= g.depth_max && double(Z) >= g.depth_min;
 }
 
 // pass 1: dmat + depth + per-block kept count
@@ -244,8 +245,9 @@ static __global__ void __launch_bounds__(1024) k_scan_blocks(uint32_t* __restric
 }
 
 // pass 3: write the kept points at block offset + rank within the block
-static __global__ void __launch_bounds__(256) k_reproject_write(const int16_t* __restrict__ disp, const uint8_t* __restrict__ gray,
-                                                         size_t gray_pitch, ReprojGeom g,
+// color: MONO8 (channels 1) or BGR8 (channels 3) rows of `color_pitch` bytes (disparity_to_depth.cpp:111-125, :176-188)
+static __global__ void __launch_bounds__(256) k_reproject_write(const int16_t* __restrict__ disp, const uint8_t* __restrict__ color,
+                                                         size_t color_pitch, int channels, ReprojGeom g,
                                                          const uint32_t* __restrict__ block_offset, float4* __restrict__ pts)
 {
     __shared__ uint32_t warp_cnt[8];
@@ -266,8 +268,13 @@ static __global__ void __launch_bounds__(256) k_reproject_write(const int16_t* _
     for (int w = 0; w < wid; w++) off += warp_cnt[w];
     off += __popc(ballot & ((1u << lane) - 1u));
     if (keep) {
-        uint32_t gv = gray ? gray[size_t(i) * gray_pitch + j] : 0u;
-        pts[off] = make_float4(X, Y, Z, __uint_as_float((gv << 16) | (gv << 8) | gv));
+        uint32_t bb = 0, gg = 0, rr = 0;
+        if (color && channels == 1) bb = gg = rr = color[size_t(i) * color_pitch + j];
+        else if (color && channels == 3) {
+            const uint8_t* px = color + size_t(i) * color_pitch + 3 * j;
+            bb = px[0]; gg = px[1]; rr = px[2];
+        }
+        pts[off] = make_float4(X, Y, Z, __uint_as_float((rr << 16) | (gg << 8) | bb));
     }
 }
 

@@ -8,14 +8,16 @@
 //     down path       : (x,   r-1) = chain c+1 at row r-1        -> from the next warp, previous row
 //     down-left path  : (x+1, r-1) = chain c+2 at row r-1        -> from the warp after that, previous row
 // so every dependency points the SAME way (towards higher chain numbers, cyclically).  A strip of consecutive chains
-// = one CTA, one warp per chain; the strip needs per row three records from the strip to its right (its first
-// chain's down/down-left states and its second chain's down-left state) and nothing from the strip to its left.
-// Compared with plain column strips (which need both neighbours every row and therefore march in lock step):
-//   * neighbouring strips are coupled one way with kXK rows of slack (a strip may run up to kXK rows ahead of its
-//     consumer), neighbouring warps inside a strip one way with LDG rows of slack -- stalls no longer line up;
-//   * no CTA-wide barrier: warps hand over through shared-memory row counters (data first, counter second, both by
-//     the same warp through the in-order shared-memory pipe), the WTA warps likewise;
-//   * one diagonal path never leaves the register file.
+// = one CTA, one warp per chain; per row the strip needs three records from the strip to its right (its first chain's
+// down / down-left states and its second chain's down-left state) and nothing from the strip to its left.  Compared
+// with plain column strips (which need both neighbours every row):
+//   * a strip may run up to kXK rows BEHIND its right neighbour (one-way coupling with slack instead of a symmetric
+//     lock step of all strips), and the records it needs are usually there long before it asks;
+//   * one agent warp per CTA (instead of two that also compute) prefetches the records a row ahead into shared memory;
+//   * one diagonal path never leaves the register file (no shared-memory hand-over, no second parity buffer for it).
+// Inside a strip the path warps advance in lock step: one named barrier per row orders the hand-over of the down /
+// down-left states (named barriers carry the memory ordering; shared-memory flags polled by the consumers were tried
+// and are both slower and -- without a membar between a multi-wavefront STS.128 and the flag store -- unsafe).
 // Image borders are predicates: at x == 0 the down-right predecessor is outside (state 0), at x == W1-1 the
 // down-left one is; row 0 starts from all-zero states.
 #pragma once
@@ -28,8 +30,8 @@
 namespace b200sgm {
 
 constexpr int kXK = 16;          // generations of inter-strip records in global memory
+constexpr int kXR = 2;           // record rows staged in shared memory by the agent warp
 constexpr int kSweepMaxTW = 15;  // chains (= path warps) per strip: 15 path + 15 WTA + 1 agent = 31 warps
-constexpr int kSweepFlagInts = 64;
 
 // Threads per CTA the register file is budgeted for: 64 registers per thread up to 256 disparities, 72 / 128 / 255 beyond.
 constexpr int sweep_max_threads(int n) { return n <= 4 ? 1024 : n == 8 ? 896 : n == 16 ? 512 : 256; }
@@ -39,9 +41,8 @@ struct SweepGeom {
     int nstrips;
     int twmax;            // chains of the widest strip
     int P1, P2;
-    long long spin_limit; // clock64 ticks before a wait gives up
+    long long spin_limit; // clock64 ticks before a record wait gives up
     int debug_flags;      // 8: timing experiment, ignore record tags (wrong results)
-    int sleep_ns;         // back-off of the waits that are expected to block (WTA warps, agent); 0 = spin
     long long* trace;     // development: clock64 stamps of strip `trace_strip`, rows trace_row0 .. +31 (nullptr = off)
     int trace_strip, trace_row0;
 };
@@ -49,30 +50,15 @@ constexpr int kTracePoints = 4;
 
 // xbuf: [0, 4 KB) progress words (one int per strip), then records [3 kinds][nstrips][kXK][Dp/2] of {data, tag}
 inline size_t sweep_xbuf_bytes(int nstrips, int Dp) { return 4096 + size_t(3) * nstrips * kXK * (Dp / 2) * sizeof(uint2); }
-// dynamic smem (uint16): Ld[LDG][2 kinds][tw][Dp] | Cring[tw][RING][Dp] | Sring[tw][RING][Dp] | stage[kStage][tw][Dp] | flags
-inline size_t sweep_smem_bytes(int tw, int Dp, int ring, int ldg, bool wta)
+// dynamic smem (uint16): Ld[2 parity][2 kinds][tw][Dp] | Cring[tw][RING][Dp] | Sring[tw][RING][Dp] | stage[kStage][tw][Dp] | xring[kXR][3][Dp]
+inline size_t sweep_smem_bytes(int tw, int Dp, int ring, bool wta)
 {
-    return (size_t(ldg) * 2 * tw + size_t(2) * ring * tw + (wta ? size_t(kStage) * tw : 0)) * Dp * sizeof(uint16_t) + kSweepFlagInts * sizeof(int);
+    return (size_t(4) * tw + size_t(2) * ring * tw + (wta ? size_t(kStage) * tw : 0) + size_t(kXR) * 3) * Dp * sizeof(uint16_t);
 }
 
 __device__ __forceinline__ uint2* sweep_rec(uint2* xbuf, int nstrips, int Dp, int kind, int strip, int gen)
 {
     return xbuf + 512 + (size_t((kind * nstrips + strip) * kXK + gen)) * (Dp / 2);
-}
-__device__ __forceinline__ int ld_flag(const int* p)
-{
-    int v;
-    asm volatile("ld.volatile.shared.b32 %0, [%1];" : "=r"(v) : "r"(uint32_t(__cvta_generic_to_shared(p))) : "memory");
-    return v;
-}
-__device__ __forceinline__ void st_flag_fenced(int* p, int v, bool fence)
-{
-    if (fence) __threadfence_block();
-    asm volatile("st.volatile.shared.b32 [%0], %1;" ::"r"(uint32_t(__cvta_generic_to_shared(p))), "r"(v) : "memory");
-}
-__device__ __forceinline__ void st_flag(int* p, int v)
-{
-    asm volatile("st.volatile.shared.b32 [%0], %1;" ::"r"(uint32_t(__cvta_generic_to_shared(p))), "r"(v) : "memory");
 }
 __device__ __forceinline__ int ld_relaxed_gpu(const int* p)
 {
@@ -82,17 +68,15 @@ __device__ __forceinline__ int ld_relaxed_gpu(const int* p)
 }
 __device__ __forceinline__ void st_relaxed_gpu(int* p, int v) { asm volatile("st.relaxed.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
 
-// Waits until ready() holds.  sleep_ns > 0: back off between polls (waits that are expected to block).  A wait that
-// exceeds the limit, or that sees the error word set by somebody else, raises the error word and marks this warp dead:
-// it then stops waiting altogether (the frame is reported as failed by the host).
+// Spins until ready() holds.  A wait that exceeds the limit, or that sees the error word set by somebody else, raises the
+// error word and marks this warp dead: it then stops waiting altogether (the frame is reported as failed by the host).
 template <typename F>
-__device__ __forceinline__ void sweep_wait(int sleep_ns, F ready, long long limit, int* err, bool& dead)
+__device__ __forceinline__ void sweep_wait(F ready, long long limit, int* err, bool& dead)
 {
     if (dead || ready()) return;
     const long long t0 = clock64();
     int spins = 0;
     while (!ready()) {
-        if (sleep_ns > 0) __nanosleep(sleep_ns);
         if ((++spins & 63) == 0 && (clock64() - t0 > limit || *reinterpret_cast<volatile int*>(err))) {
             atomicExch(err, 1);
             dead = true;
@@ -128,54 +112,62 @@ __device__ __forceinline__ void wta_flush_diag(const WtaAcc& acc, int cnt, const
 }
 
 // Launch: nstrips CTAs (all co-resident: cooperative launch), 32 * (2 * twmax + 1) threads (32 * (twmax + 1) when !DO_WTA):
-//   path warps  [0, twmax)         one per chain: the three path updates of a row and the sum S
+//   path warps  [0, twmax)         one per chain: the three path updates of a row and the sum S; lock step, one barrier per row
 //   WTA warps   [twmax, 2 twmax)   one per chain: resolve parked rows of S two at a time (A.6), trailing by <= kStage rows
-//   agent warp  (last)             plays the two chains to the right of the strip: polls the neighbour strip's records of each
-//                                  row in global memory and drops them into the shared-memory slots those chains would fill
-// RING : rows of C / S_h in flight per chain (cp.async rings);  LDG : generations of hand-over state between neighbouring warps
+//   agent warp  (last)             polls the right neighbour strip's three records of each row in global memory, one row ahead of
+//                                  their use, and drops them into shared memory for the strip's last two chains
+// RING : rows of C / S_h in flight per chain (cp.async rings)
 // FULL : Dp == D == 64 N;  CLAMP_EACH : saturate after every addition of the sum
-template <int N, int RING, int LDG, bool UP, bool DO_WTA, bool FULL, bool CLAMP_EACH>
+template <int N, int RING, bool UP, bool DO_WTA, bool FULL, bool CLAMP_EACH>
 __global__ void __launch_bounds__(sweep_max_threads(N), 1) k_sweep(const uint16_t* __restrict__ Cvol, uint16_t* __restrict__ Svol, SweepGeom g,
                                                                     int16_t* __restrict__ disp, uint32_t* __restrict__ disp2key,
                                                                     uint2* __restrict__ xbuf, int* __restrict__ err)
 {
-    static_assert(LDG == 2 || LDG == 4, "generation index must be an immediate of the 4-row unrolled loop");
     static_assert(RING == 4 || RING == 8, "ring depth");
+    static_assert(kXR == 2 && kStage == 4, "slot indices are immediates of the 4-row unrolled loop");
     extern __shared__ __align__(16) uint16_t smem_s[];
     const int W1 = g.w.W1, H = g.w.H, Dp = FULL ? 64 * N : g.w.Dp;
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int b = blockIdx.x, n = g.nstrips, tw = g.twmax;
     const int c0 = int((long long)b * W1 / n), c1 = int((long long)(b + 1) * W1 / n);
     const int TW = c1 - c0;                                  // 2 <= TW <= tw
-    // Ld[gen][kind][slot][Dp]: slot s holds what path warp s READS: kind 0 = down state of chain c0+s+1, kind 1 = down-left
-    // state of chain c0+s+2 (normalised).  Warp j therefore writes kind 0 into slot j-1 and kind 1 into slot j-2.
+    // Ld[parity][kind][slot][Dp]: slot s holds what path warp s READS: kind 0 = down state of chain c0+s+1, kind 1 = down-left
+    // state of chain c0+s+2 (normalised).  Warp j therefore writes kind 0 into slot j-1 and kind 1 into slot j-2; what the
+    // last two warps read beyond the strip comes from the agent's xring[slot][record][Dp] (records: V0, B0, B1).
     uint16_t* Ld = smem_s;
-    const int kindStride = tw * Dp, genStride = 2 * tw * Dp;
-    uint16_t* ringbase = Ld + size_t(LDG) * genStride;
+    const int kindStride = tw * Dp, parStride = 2 * tw * Dp;
+    uint16_t* ringbase = Ld + size_t(2) * parStride;
     uint16_t* sringbase = ringbase + size_t(RING) * tw * Dp;
     uint16_t* stagebase = sringbase + size_t(RING) * tw * Dp;
-    int* flags = reinterpret_cast<int*>(stagebase + (DO_WTA ? size_t(kStage) * tw * Dp : 0));
-    int* done = flags;            // [tw + 2] rows whose down / down-left states chain j has published (tw, tw+1: the agent)
-    int* wfill = flags + 24;      // [tw] rows of S parked by path warp j
-    int* wtake = flags + 40;      // [tw] rows of S consumed by WTA warp j
+    uint16_t* xring = stagebase + (DO_WTA ? size_t(kStage) * tw * Dp : 0);
     {
         uint32_t* z = reinterpret_cast<uint32_t*>(Ld);
-        const int nz = LDG * genStride / 2;
+        const int nz = parStride;                      // both parities, in 32-bit words
         for (int i = threadIdx.x; i < nz; i += blockDim.x) z[i] = 0;
-        if (threadIdx.x < kSweepFlagInts) flags[threadIdx.x] = 0;
     }
     __syncthreads();
+    if (g.trace != nullptr && threadIdx.x == 0) g.trace[4096 + 2 * b] = clock64();     // per-strip begin / end (end: path warp 0)
     const LaneCtx lc = make_lane_ctx<N>(lane, Dp, g.P1, g.P2);
     const bool active = FULL || lc.active;
     const int lo = lane * 2 * N;
     const int agent_w = DO_WTA ? 2 * tw : tw;
     bool dead = false;
-    const bool fence = (g.debug_flags & 32) != 0;   // experiment: membar.cta between hand-over data and its row counter
-    const int psleep = (g.debug_flags & 64) ? g.sleep_ns : 0;   // experiment: path-warp waits back off as well
-    // trace slot of this warp: [warp][row - trace_row0][point]
+    // named barriers: the agent and the strip's last two path warps hand over through XFULL / XEMPTY (96 threads)
+    constexpr int BAR_ROW = 1, BAR_FULL = 2, BAR_EMPTY = 2 + kStage, BAR_XFULL = 2 + 2 * kStage, BAR_XEMPTY = BAR_XFULL + kXR;
+    static_assert(BAR_XEMPTY + kXR <= 16, "16 named barriers per CTA");
+    long long seg_acc[kTracePoints] = {0, 0, 0, 0}, seg_last = 0;      // trace_row0 == -2: time spent per segment over the whole sweep
     auto stamp = [&](int r, int k) {
-        if (g.trace != nullptr && b == g.trace_strip && lane == 0 && unsigned(r - g.trace_row0) < 32u)
-            g.trace[(size_t(w) * 32 + (r - g.trace_row0)) * kTracePoints + k] = clock64();
+        if (g.trace != nullptr && b == g.trace_strip && lane == 0) {
+            if (g.trace_row0 == -2) {
+                const long long now = clock64();
+                if (seg_last) seg_acc[k] += now - seg_last;
+                seg_last = now;
+                if (r >= H - 2) g.trace[w * kTracePoints + k] = seg_acc[k];
+            } else if (g.trace_row0 < 0) {                      // whole-sweep mode: row starts of path warp 0 and of the agent
+                if (k == 0 && r < 2048 && (w == 0 || w == agent_w)) g.trace[(w == 0 ? 0 : 2048) + r] = clock64();
+            } else if (unsigned(r - g.trace_row0) < 32u)
+                g.trace[(size_t(w) * 32 + (r - g.trace_row0)) * kTracePoints + k] = clock64();
+        }
     };
 
     if (w == agent_w) {
@@ -184,15 +176,10 @@ __global__ void __launch_bounds__(sweep_max_threads(N), 1) k_sweep(const uint16_
         const uint2* recV0 = sweep_rec(xbuf, n, Dp, 0, nb, 0) + lane * N;    // down state of the neighbour's first chain
         const uint2* recB0 = sweep_rec(xbuf, n, Dp, 1, nb, 0) + lane * N;    // its down-left state
         const uint2* recB1 = sweep_rec(xbuf, n, Dp, 2, nb, 0) + lane * N;    // down-left state of the neighbour's second chain
-        uint16_t* dV0 = Ld + (TW - 1) * Dp + lo;                             // kind 0, slot TW-1 (read by warp TW-1)
-        uint16_t* dB0 = Ld + kindStride + (TW - 2) * Dp + lo;                // kind 1, slot TW-2 (read by warp TW-2)
-        uint16_t* dB1 = Ld + kindStride + (TW - 1) * Dp + lo;                // kind 1, slot TW-1 (read by warp TW-1)
+        uint16_t* dst = xring + lo;
         int* prog = reinterpret_cast<int*>(xbuf) + b;
         const int recGen = Dp / 2;
         for (int rr = 0; rr + 1 < H; rr++) {
-            // generation rr % LDG still holds row rr - LDG until warps TW-1 and TW-2 have loaded it (their row rr - LDG + 1)
-            const int need = rr - LDG + 2;
-            if (need > 0) sweep_wait(g.sleep_ns, [&] { return min(ld_flag(done + TW - 1), ld_flag(done + TW - 2)) >= need; }, g.spin_limit, err, dead);
             stamp(rr, 0);
             uint32_t dv0[N], db0[N], db1[N];
 #pragma unroll
@@ -211,19 +198,17 @@ __global__ void __launch_bounds__(sweep_max_threads(N), 1) k_sweep(const uint16_
                 }
                 return __all_sync(kFullMask, ok) || (g.debug_flags & 8);
             };
-            sweep_wait(0, poll, g.spin_limit, err, dead);
+            sweep_wait(poll, g.spin_limit, err, dead);
             stamp(rr, 1);
+            if (lane == 0) st_relaxed_gpu(prog, rr + 1);     // the producer may reuse this record generation
+            // slot rr & 1 held record rr - 2 until the two consumers took it (their row rr - 1)
+            if (rr >= kXR) named_bar_sync(BAR_XEMPTY + (rr & (kXR - 1)), 96);
+            stamp(rr, 2);
             if (active) {
-                const int go2 = (rr & (LDG - 1)) * genStride;
-                st_regs<N>(dV0 + go2, dv0); st_regs<N>(dB0 + go2, db0); st_regs<N>(dB1 + go2, db1);
+                uint16_t* d = dst + (rr & (kXR - 1)) * 3 * Dp;
+                st_regs<N>(d, dv0); st_regs<N>(d + Dp, db0); st_regs<N>(d + 2 * Dp, db1);
             }
-            if (fence) __threadfence_block();
-            __syncwarp();
-            if (lane == 0) {
-                st_flag(done + TW, rr + 1);
-                st_flag(done + TW + 1, rr + 1);
-                st_relaxed_gpu(prog, rr + 1);
-            }
+            named_bar_arrive(BAR_XFULL + (rr & (kXR - 1)), 96);
         }
         return;
     }
@@ -233,6 +218,7 @@ __global__ void __launch_bounds__(sweep_max_threads(N), 1) k_sweep(const uint16_
     const int c = c0 + j;                              // this warp's chain
     const int ringSlot = tw * Dp;                      // slot stride of the stage ring [slot][warp][Dp]
     uint16_t* stage = stagebase + size_t(j) * Dp;      // + slot * ringSlot
+    const int nboth = 64 * TW, nrow = 32 * TW;
 
     if (wta_role) {
         // ================================ WTA warps ================================
@@ -245,9 +231,8 @@ __global__ void __launch_bounds__(sweep_max_threads(N), 1) k_sweep(const uint16_
         int pending = 0, rb = 0;            // rows parked in acc, first of them
         auto batch = [&](auto q0_tag, int r, int cnt) {
             constexpr int Q0 = decltype(q0_tag)::value;
-            stamp(r, 0);
-            sweep_wait(g.sleep_ns, [&] { return ld_flag(wfill + j) >= r + cnt; }, g.spin_limit, err, dead);
-            stamp(r, 1);
+            named_bar_sync(BAR_FULL + Q0, nboth);
+            if (cnt > 1) named_bar_sync(BAR_FULL + Q0 + 1, nboth);
             uint16_t* sc = stage + Q0 * ringSlot;
             if (wc.f > 0) {
                 wta_vec<N>(sc, ringSlot, r, g.w, wc, lane, active, acc);   // a row past the end lands in a lane >= cnt of the flush
@@ -264,13 +249,12 @@ __global__ void __launch_bounds__(sweep_max_threads(N), 1) k_sweep(const uint16_
                     const int d = wta_slow<N>(sc + q * ringSlot, g.w, wc, x1, lane, active, disp2key + size_t(y) * g.w.W);
                     if (lane == 0) disp[size_t(y) * g.w.W + x1 + g.w.minX1] = int16_t(d);
                 }
+                __syncwarp();
             }
-            if (fence) __threadfence_block();
-            __syncwarp();
-            if (lane == 0) st_flag(wtake + j, r + cnt);
-            stamp(r, 2);
+            if (r + kStage < H) named_bar_arrive(BAR_EMPTY + Q0, nboth);
+            if (cnt > 1 && r + 1 + kStage < H) named_bar_arrive(BAR_EMPTY + Q0 + 1, nboth);
         };
-        static_assert(kWB == 2 && kStage == 4, "two batches per stage-ring revolution");
+        static_assert(kWB == 2, "two batches per stage-ring revolution");
         int r = 0;
         for (; r + 3 < H; r += 4) {
             batch(std::integral_constant<int, 0>{}, r, 2);
@@ -283,17 +267,19 @@ __global__ void __launch_bounds__(sweep_max_threads(N), 1) k_sweep(const uint16_
 
     // ================================ path warps ================================
     const bool producer = j <= 1;                              // the strip to the left needs my states
-    const int cb = b == 0 ? n - 1 : b - 1;                     // ... that strip
+    const bool consumer = j >= TW - 2;                         // my down-left (and for the last chain also the down) state comes from the agent
+    const int cb = b == 0 ? n - 1 : b - 1;                     // the strip that consumes my records
     const int* prog_c = reinterpret_cast<const int*>(xbuf) + cb;
     uint2* pubV = sweep_rec(xbuf, n, Dp, 0, b, 0) + lane * N;
     uint2* pubB = sweep_rec(xbuf, n, Dp, j == 0 ? 1 : 2, b, 0) + lane * N;
     const int recGen = Dp / 2;
-    const uint16_t* rdV = Ld + size_t(j) * Dp + lo;            // + gen * genStride
-    const uint16_t* rdB = Ld + kindStride + size_t(j) * Dp + lo;
-    uint16_t* wrV = Ld + size_t(max(j - 1, 0)) * Dp + lo;      // j == 0: never stored
-    uint16_t* wrB = Ld + kindStride + size_t(max(j - 2, 0)) * Dp + lo;   // j <= 1: never stored
-    const int* flagV = done + j + 1;
-    const int* flagB = done + j + 2;
+    // sources of the two hand-over states: + (parity of row r-1) * stride
+    const uint16_t* rdV = (j == TW - 1 ? xring : Ld + size_t(j) * Dp) + lo;
+    const int rdVs = j == TW - 1 ? 3 * Dp : parStride;
+    const uint16_t* rdB = (consumer ? xring + (j == TW - 1 ? 2 : 1) * Dp : Ld + kindStride + size_t(j) * Dp) + lo;
+    const int rdBs = consumer ? 3 * Dp : parStride;
+    uint16_t* wrV = Ld + size_t(max(j - 1, 0)) * Dp + lo;                 // j == 0: never stored
+    uint16_t* wrB = Ld + kindStride + size_t(max(j - 2, 0)) * Dp + lo;    // j <= 1: never stored
     uint16_t* ring = ringbase + size_t(j) * RING * Dp + lo;
     uint16_t* sring = sringbase + size_t(j) * RING * Dp + lo;
     const int Dh = Dp >> 1;
@@ -318,27 +304,22 @@ __global__ void __launch_bounds__(sweep_max_threads(N), 1) k_sweep(const uint16_
     uint32_t LtA[N];           // the down-right path: this chain's own state
 #pragma unroll
     for (int q = 0; q < N; q++) LtA[q] = 0;
-    int space_known = j == 0 ? 0x7FFFFFFF : 0;   // rows the readers of my hand-over slots are known to have published
     int prog_known = 0, prog_next = 0;           // producers: record rows the left strip's agent has taken
 
-    auto row = [&](auto q_tag, int r) {
-        constexpr int Q = decltype(q_tag)::value;          // r & 3
-        constexpr int GEN = Q % LDG, PGEN = (Q + 3) % LDG;  // hand-over generation written (row r) / read (row r-1)
+    // one row; Q = r mod 4 (stage slot; parity = Q & 1); CONS = this warp takes states from the agent (it then runs its own
+    // diagonal first and the agent-fed steps last, so that a late record costs as little as possible)
+    auto row = [&](auto q_tag, auto cons_tag, int r) {
+        constexpr int Q = decltype(q_tag)::value;
+        constexpr bool CONS = decltype(cons_tag)::value;
+        constexpr int PAR = Q & 1, PREV = PAR ^ 1;
         stamp(r, 0);
         issue(r + RING - 1);
         cp_async_commit();
-        if (producer) {
+        if (producer && (!(g.debug_flags & 16) || (r & 7) == 0)) {
             prog_known = max(prog_known, prog_next);
             prog_next = ld_relaxed_gpu(prog_c);            // inspected one row later: the round trip stays off this row's path
         }
-        const int fV = ld_flag(flagV), fB = ld_flag(flagB);
         uint32_t LtV[N], LtB[N], Cc[N], S[N], Ln[N];
-        if (active) {
-            ld_regs<N>(rdV + PGEN * genStride, LtV); ld_regs<N>(rdB + PGEN * genStride, LtB);
-        } else {
-#pragma unroll
-            for (int q = 0; q < N; q++) { LtV[q] = 0; LtB[q] = 0; }
-        }
         cp_async_wait<RING - 1>();     // this thread's copies of row r have landed (each lane reads only its own bytes)
         if (active) {
             ld_regs<N>(ring + (r & (RING - 1)) * Dp, Cc); ld_regs<N>(sring + (r & (RING - 1)) * Dp, S);
@@ -346,44 +327,46 @@ __global__ void __launch_bounds__(sweep_max_threads(N), 1) k_sweep(const uint16_
 #pragma unroll
             for (int q = 0; q < N; q++) { Cc[q] = kMaxCostX2; S[q] = 0; }
         }
-        if (fV < r || fB < r) {        // a neighbour has not published row r-1 yet: wait, then load again
-            sweep_wait(psleep, [&] { return ld_flag(flagV) >= r && ld_flag(flagB) >= r; }, g.spin_limit, err, dead);
-            if (active) { ld_regs<N>(rdV + PGEN * genStride, LtV); ld_regs<N>(rdB + PGEN * genStride, LtB); }
+        auto add = [&](const uint32_t (&L)[N]) {
+#pragma unroll
+            for (int q = 0; q < N; q++) S[q] = CLAMP_EACH ? __vminu2(S[q] + L[q], kMaxCostX2) : S[q] + L[q];
+        };
+        auto step_a = [&] {            // down-right: registers only
+            if (xcur == 0) {
+#pragma unroll
+                for (int q = 0; q < N; q++) LtA[q] = 0;
+            }
+            path_step<N>(Cc, LtA, Ln, lc);
+            add(Ln);
+        };
+        if (CONS) {
+            step_a();
+            if (r > 0) named_bar_sync(BAR_XFULL + PREV, 96);      // the agent has staged the records of row r-1
         }
+        if (active && r > 0) {
+            ld_regs<N>(rdV + PREV * rdVs, LtV); ld_regs<N>(rdB + PREV * rdBs, LtB);
+        } else {
+#pragma unroll
+            for (int q = 0; q < N; q++) { LtV[q] = 0; LtB[q] = 0; }
+        }
+        if (CONS && r > 0 && r - 1 + kXR < H - 1) named_bar_arrive(BAR_XEMPTY + PREV, 96);   // the agent may refill the slot
         stamp(r, 1);
         if (xcur == W1 - 1) {
 #pragma unroll
             for (int q = 0; q < N; q++) LtB[q] = 0;
         }
-        if (xcur == 0) {
-#pragma unroll
-            for (int q = 0; q < N; q++) LtA[q] = 0;
-        }
-        auto add = [&](const uint32_t (&L)[N]) {
-#pragma unroll
-            for (int q = 0; q < N; q++) S[q] = CLAMP_EACH ? __vminu2(S[q] + L[q], kMaxCostX2) : S[q] + L[q];
-        };
-        // ---- down and down-left: the states the next warps wait for
+        // ---- down and down-left: the states the previous warps (or the strip to the left) wait for
         path_step<N>(Cc, LtV, Ln, lc);
         add(Ln);
         path_step<N>(Cc, LtB, Ln, lc);
         add(Ln);
-        if (r - LDG + 2 > space_known) {   // generation GEN still holds row r-LDG until warps j-1 / j-2 have loaded it
-            const int need = r - LDG + 2;
-            sweep_wait(psleep, [&] { space_known = min(ld_flag(done + max(j - 1, 0)), ld_flag(done + max(j - 2, 0))); return space_known >= need; },
-                          g.spin_limit, err, dead);
-        }
         if (active) {
-            if (j >= 1) st_regs<N>(wrV + GEN * genStride, LtV);
-            if (j >= 2) st_regs<N>(wrB + GEN * genStride, LtB);
+            if (j >= 1) st_regs<N>(wrV + PAR * parStride, LtV);
+            if (j >= 2) st_regs<N>(wrB + PAR * parStride, LtB);
         }
-        if (fence) __threadfence_block();
-        __syncwarp();
-        if (lane == 0) st_flag(done + j, r + 1);
-        stamp(r, 2);
         if (producer) {
             const int need = r - kXK + 1;      // generation r % kXK held row r - kXK
-            if (need > prog_known) sweep_wait(psleep, [&] { prog_known = ld_relaxed_gpu(prog_c); return prog_known >= need; }, g.spin_limit, err, dead);
+            if (need > prog_known) sweep_wait([&] { prog_known = ld_relaxed_gpu(prog_c); return prog_known >= need; }, g.spin_limit, err, dead);
             if (active) {
                 const int go = (r & (kXK - 1)) * recGen;
 #pragma unroll
@@ -393,9 +376,8 @@ __global__ void __launch_bounds__(sweep_max_threads(N), 1) k_sweep(const uint16_
                 }
             }
         }
-        // ---- down-right: registers only
-        path_step<N>(Cc, LtA, Ln, lc);
-        add(Ln);
+        stamp(r, 2);
+        if (!CONS) step_a();
         if (!CLAMP_EACH) {
 #pragma unroll
             for (int q = 0; q < N; q++) S[q] = __vminu2(S[q], kMaxCostX2);
@@ -409,31 +391,35 @@ __global__ void __launch_bounds__(sweep_max_threads(N), 1) k_sweep(const uint16_
                     else if (k + Dh >= g.w.D) S[q] |= 0xFFFF0000u;
                 }
             }
-            if (r >= kStage) sweep_wait(psleep, [&] { return ld_flag(wtake + j) >= r - kStage + 1; }, g.spin_limit, err, dead);
+            if (r >= kStage) named_bar_sync(BAR_EMPTY + Q, nboth);    // the WTA warps have taken row r - kStage
             if (active) st_regs<N>(stage + Q * ringSlot + lo, S);
-            if (fence) __threadfence_block();
-            __syncwarp();
-            if (lane == 0) st_flag(wfill + j, r + 1);
+            named_bar_arrive(BAR_FULL + Q, nboth);
         } else {
             if (active) st_regs<N>(Svol + offCur, S);
         }
-        stamp(r, 3);
         offCur += rowStep;
         if (++xcur == W1) { xcur = 0; offCur -= wrapBack; }
+        stamp(r, 3);
+        named_bar_sync(BAR_ROW, nrow);      // every warp's states of row r are in Ld[PAR]; row r-1's have been read
     };
 
-    int r = 0;
-    for (; r + 3 < H; r += 4) {
-        row(std::integral_constant<int, 0>{}, r);
-        row(std::integral_constant<int, 1>{}, r + 1);
-        row(std::integral_constant<int, 2>{}, r + 2);
-        row(std::integral_constant<int, 3>{}, r + 3);
-    }
-    const int rem = H - r;
-    if (rem > 0) row(std::integral_constant<int, 0>{}, r);
-    if (rem > 1) row(std::integral_constant<int, 1>{}, r + 1);
-    if (rem > 2) row(std::integral_constant<int, 2>{}, r + 2);
+    auto sweep = [&](auto cons_tag) {
+        int r = 0;
+        for (; r + 3 < H; r += 4) {
+            row(std::integral_constant<int, 0>{}, cons_tag, r);
+            row(std::integral_constant<int, 1>{}, cons_tag, r + 1);
+            row(std::integral_constant<int, 2>{}, cons_tag, r + 2);
+            row(std::integral_constant<int, 3>{}, cons_tag, r + 3);
+        }
+        const int rem = H - r;
+        if (rem > 0) row(std::integral_constant<int, 0>{}, cons_tag, r);
+        if (rem > 1) row(std::integral_constant<int, 1>{}, cons_tag, r + 1);
+        if (rem > 2) row(std::integral_constant<int, 2>{}, cons_tag, r + 2);
+    };
+    if (consumer) sweep(std::true_type{});
+    else sweep(std::false_type{});
     cp_async_wait<0>();
+    if (g.trace != nullptr && w == 0 && lane == 0) g.trace[4096 + 2 * b + 1] = clock64();
 }
 
 }  // namespace b200sgm

@@ -22,7 +22,7 @@ SYMBOLS = (
     "b200sgm_last_error", "b200sgm_version", "b200sgm_launch_count", "b200sgm_lane_stream", "b200sgm_debug_read",
     "b200sgm_debug_set_path", "b200sgm_profile", "b200sgm_stage_times", "b200sgm_alu_peak", "b200sgm_stage_timeline",
     "b200sgm_set_camera", "b200sgm_rectify", "b200sgm_rectify_device", "b200sgm_rectify_maps", "b200sgm_bm_compute",
-    "b200sgm_bm_compute_device", "b200sgm_lane_status",
+    "b200sgm_bm_compute_device", "b200sgm_lane_status", "b200sgm_reproject_from_camera",
 )
 
 STAGES = ("prefilter", "cost", "horizontal", "vertical_wta", "lrcheck", "median", "speckle")
@@ -35,8 +35,10 @@ class B200SGMError(RuntimeError):
 
 
 class CReproject(ctypes.Structure):
-    _fields_ = [(n, ctypes.c_float) for n in ("q03", "q13", "wz", "q32", "q33", "depth_min", "depth_max",
-                                              "min_disparity", "max_disparity")]
+    """Mirror of `b200sgm_reproject` in include/b200sgm.h."""
+    _fields_ = [(n, ctypes.c_float) for n in ("q03", "q13", "wz", "q32", "q33", "min_disparity", "max_disparity")] + \
+               [("depth_min", ctypes.c_double), ("depth_max", ctypes.c_double), ("color", ctypes.c_void_p),
+                ("color_stride", ctypes.c_size_t), ("color_channels", ctypes.c_int)]
 
 
 def load_library():
@@ -135,11 +137,19 @@ class Engine:
                                                  W, H, out.ctypes.data_as(ctypes.c_void_p), ctypes.c_size_t(W * 4)))
         return out
 
-    def compute_xyz(self, left, right, q, depth_min, depth_max, min_disparity, max_disparity, want_points=True):
+    def compute_xyz(self, left, right, q, depth_min, depth_max, min_disparity, max_disparity, want_points=True, color=None):
+        """Matching + processDisparity + reprojection.  `color`: None (the left image, MONO8), (H, W) uint8 or (H, W, 3) BGR8."""
         L, R = _u8(left), _u8(right)
         H, W = L.shape
-        rp = CReproject(float(q[0]), float(q[1]), float(q[2]), float(q[3]), float(q[4]), float(depth_min), float(depth_max),
-                        float(min_disparity), float(max_disparity))
+        rp = CReproject(float(q[0]), float(q[1]), float(q[2]), float(q[3]), float(q[4]), float(min_disparity), float(max_disparity),
+                        float(depth_min), float(depth_max), None, 0, 0)
+        if color is not None:
+            color = np.ascontiguousarray(color, np.uint8)
+            if color.shape[:2] != (H, W) or color.ndim not in (2, 3) or (color.ndim == 3 and color.shape[2] != 3):
+                raise ValueError("color must be (H, W) MONO8 or (H, W, 3) BGR8 of the frame's size")
+            rp.color = color.ctypes.data
+            rp.color_stride = color.strides[0]
+            rp.color_channels = 1 if color.ndim == 2 else 3
         disp = np.empty((H, W), np.int16)
         dmat = np.empty((H, W), np.float32)
         depth = np.empty((H, W), np.float32)
@@ -279,6 +289,17 @@ class Engine:
         self._check(self.lib.b200sgm_debug_read(self.h, lane, what.encode(), buf.ctypes.data_as(ctypes.c_void_p),
                                                 ctypes.c_size_t(buf.nbytes), None))
         return buf
+
+
+def reproject_from_camera(Kl, Pl, Pr, depth_min, depth_max) -> CReproject:
+    """b200sgm_reproject_from_camera: q and the disparity window formed exactly like the reference forms them."""
+    lib = load_library()
+    rp = CReproject()
+    k, pl, pr = (np.ascontiguousarray(a, np.float64) for a in (Kl, Pl, Pr))
+    lib.b200sgm_reproject_from_camera.restype = None
+    lib.b200sgm_reproject_from_camera(ctypes.byref(rp), k.ctypes.data_as(ctypes.c_void_p), pl.ctypes.data_as(ctypes.c_void_p),
+                                      pr.ctypes.data_as(ctypes.c_void_p), ctypes.c_double(depth_min), ctypes.c_double(depth_max))
+    return rp
 
 
 def alu_peak(device=0):

@@ -69,10 +69,22 @@ typedef struct b200sgm_point {
 /* Reprojection inputs: calc_q() of disparity_to_depth.cpp:62-85 cast to float as :136-140 does. */
 typedef struct b200sgm_reproject {
     float q03, q13, wz, q32, q33; /* -cx, -cy, fx, 1/T, -(cx-cxr)/T                                  */
-    float depth_min, depth_max;   /* cfg/i3DR_pointCloud.cfg; test of disparity_to_depth.cpp:174-175  */
-    float min_disparity;          /* T*f/depth_max  (generate_disparity.cpp:449)                      */
-    float max_disparity;          /* T*f/depth_min  (generate_disparity.cpp:450); +inf if depth_min=0 */
+    float min_disparity;          /* float(T*f/depth_max)  (generate_disparity.cpp:449)               */
+    float max_disparity;          /* float(T*f/depth_min)  (generate_disparity.cpp:450); +inf if depth_min=0 */
+    double depth_min, depth_max;  /* cfg/i3DR_pointCloud.cfg as the DOUBLES the reference compares the float Z with
+                                     (disparity_to_depth.cpp:50-51, :174-175)                         */
+    /* colour source of the cloud (disparity_to_depth.cpp:111-125, :176-188): a host image of the frame's size, MONO8
+     * (color_channels 1) or BGR8 (color_channels 3); NULL = the left image handed to the matcher (MONO8) */
+    const uint8_t *color;
+    size_t color_stride;
+    int color_channels;
 } b200sgm_reproject;
+/* Fills q03..q33 and the disparity window exactly as the reference does: calc_q() on (K_l, P_r, P_l) in double then cast to
+ * float (disparity_to_depth.cpp:62-85, :136-140); f = P_l[0][0] and T = -P_r[0][3] / P_r[0][0] (image_geometry baseline) stored
+ * as float32 message fields, min/max_disparity = float(double(f32(T * f)) / depth) (generate_disparity.cpp:441-450).
+ * K: 3x3, P_l / P_r: 3x4, row-major.  Leaves `color` NULL. */
+void b200sgm_reproject_from_camera(b200sgm_reproject *rp, const double *K_l, const double *P_l, const double *P_r,
+                                   double depth_min, double depth_max);
 
 /* ---- lifetime ------------------------------------------------------------------------------------------- */
 

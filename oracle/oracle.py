@@ -108,16 +108,80 @@ def calc_q(fx: float, cx: float, cxr: float, cy: float, p14: float) -> np.ndarra
     return np.array([-cx, -cy, fx, 1.0 / T, q33], np.float64).astype(np.float32)
 
 
-def reproject(dmat: np.ndarray, gray, q: np.ndarray, depth_min: float, depth_max: float):
+def reproject(dmat: np.ndarray, color, q: np.ndarray, depth_min: float, depth_max: float):
+    """Row R.  `color`: (H, W) MONO8 or (H, W, 3) BGR8 (disparity_to_depth.cpp:111-125, :176-188), or None."""
     d = np.ascontiguousarray(dmat, np.float32)
     H, W = d.shape
     depth = np.empty((H, W), np.float32)
     pts = np.zeros((H * W, 4), np.float32)
-    g = np.ascontiguousarray(gray, np.uint8) if gray is not None else None
+    g = np.ascontiguousarray(color, np.uint8) if color is not None else None
+    ch = 0 if g is None else (1 if g.ndim == 2 else 3)
     qq = np.ascontiguousarray(q, np.float32)
     n = lib().sgbm_oracle_reproject(d.ctypes.data_as(ctypes.c_void_p),
-                                    g.ctypes.data_as(ctypes.c_void_p) if g is not None else None,
+                                    g.ctypes.data_as(ctypes.c_void_p) if g is not None else None, ctypes.c_int(ch),
                                     ctypes.c_int(W), ctypes.c_int(H), qq.ctypes.data_as(ctypes.c_void_p),
-                                    ctypes.c_float(depth_min), ctypes.c_float(depth_max),
+                                    ctypes.c_double(depth_min), ctypes.c_double(depth_max),
                                     depth.ctypes.data_as(ctypes.c_void_p), pts.ctypes.data_as(ctypes.c_void_p))
+    return depth, pts[:n].copy()
+
+
+def disparity_window(fx: float, baseline: float, depth_min: float, depth_max: float):
+    """min_disparity / max_disparity exactly as generate_disparity.cpp:441-450 forms them: f and T are float32 message fields,
+    their product is a float32, the division by the double depth bound happens in double and the result is stored as float32
+    (depth_min == 0 gives +inf)."""
+    f, T = np.float32(fx), np.float32(baseline)
+    tf = np.float32(T * f)
+    with np.errstate(divide="ignore"):
+        lo = np.float32(np.float64(tf) / np.float64(depth_max))
+        hi = np.float32(np.float64(tf) / np.float64(depth_min)) if depth_min != 0 else np.float32(np.inf)
+    return float(lo), float(hi)
+
+
+# ---- oracle/_ref: the reference's own reprojection statements compiled against stand-in types (oracle/build_ref.py) ----
+_ref = None
+
+
+def ref_lib():
+    """libref_reproject.so, or None when it can be neither built (no /root/reference) nor found prebuilt."""
+    global _ref
+    if _ref is None:
+        from . import build_ref
+        path = build_ref.build()
+        if path is None:
+            return None
+        _ref = ctypes.CDLL(path)
+        _ref.ref_reproject.restype = ctypes.c_uint
+    return _ref
+
+
+def ref_calc_q(Kl, Pr, Pl) -> np.ndarray:
+    k, pr, pl = (np.ascontiguousarray(a, np.float64) for a in (Kl, Pr, Pl))
+    q = np.zeros(16, np.float64)
+    ref_lib().ref_calc_q(k.ctypes.data_as(ctypes.c_void_p), pr.ctypes.data_as(ctypes.c_void_p), pl.ctypes.data_as(ctypes.c_void_p),
+                         q.ctypes.data_as(ctypes.c_void_p))
+    return q.reshape(4, 4)
+
+
+def ref_process_disparity(disp32: np.ndarray, fx: float, baseline: float, depth_min: float, depth_max: float):
+    a = np.ascontiguousarray(disp32, np.float32)
+    out = np.empty_like(a)
+    mm = np.zeros(2, np.float32)
+    ref_lib().ref_process_disparity(a.ctypes.data_as(ctypes.c_void_p), ctypes.c_int(a.shape[0]), ctypes.c_int(a.shape[1]),
+                                    ctypes.c_double(fx), ctypes.c_double(baseline), ctypes.c_double(depth_min), ctypes.c_double(depth_max),
+                                    out.ctypes.data_as(ctypes.c_void_p), mm.ctypes.data_as(ctypes.c_void_p))
+    return out, float(mm[0]), float(mm[1])
+
+
+def ref_reproject(dmat: np.ndarray, color: np.ndarray, Kl, Pr, Pl, depth_min: float, depth_max: float):
+    d = np.ascontiguousarray(dmat, np.float32)
+    H, W = d.shape
+    g = np.ascontiguousarray(color, np.uint8)
+    ch = 1 if g.ndim == 2 else 3
+    k, pr, pl = (np.ascontiguousarray(a, np.float64) for a in (Kl, Pr, Pl))
+    depth = np.empty((H, W), np.float32)
+    pts = np.zeros((H * W, 4), np.float32)
+    n = ref_lib().ref_reproject(d.ctypes.data_as(ctypes.c_void_p), ctypes.c_int(H), ctypes.c_int(W), g.ctypes.data_as(ctypes.c_void_p),
+                                ctypes.c_int(ch), k.ctypes.data_as(ctypes.c_void_p), pr.ctypes.data_as(ctypes.c_void_p),
+                                pl.ctypes.data_as(ctypes.c_void_p), ctypes.c_double(depth_min), ctypes.c_double(depth_max),
+                                ctypes.c_float(0), ctypes.c_float(0), depth.ctypes.data_as(ctypes.c_void_p), pts.ctypes.data_as(ctypes.c_void_p))
     return depth, pts[:n].copy()

@@ -411,12 +411,13 @@ void sgbm_oracle_process_disparity(const int16_t *disp16, float *dmat, size_t n,
 }
 
 /* ---- R: disparity_to_depth.cpp:136-205.  q = {q03, q13, wz, q32, q33} as float32.             */
-/* depth: H*W float (0 where rejected); xyz: up to H*W records of 4 floats {X,Y,Z,rgb-packed};  */
-/* returns number of points (row-major scan order).                                             */
+/* color: MONO8 (channels 1) or BGR8 (channels 3), tight rows; depth window as the doubles the  */
+/* reference compares the float Z with (:175).  depth: H*W float (0 where rejected); xyz: up to */
+/* H*W records of 4 floats {X,Y,Z,rgb-packed}; returns number of points (row-major scan order). */
 typedef struct { float x, y, z; uint32_t rgb; } sgbm_oracle_point;
 
-uint32_t sgbm_oracle_reproject(const float *dmat, const uint8_t *gray, int W, int H, const float q[5],
-                               float depth_min, float depth_max, float *depth, sgbm_oracle_point *pts)
+uint32_t sgbm_oracle_reproject(const float *dmat, const uint8_t *color, int channels, int W, int H, const float q[5],
+                               double depth_min, double depth_max, float *depth, sgbm_oracle_point *pts)
 {
     const float q03 = q[0], q13 = q[1], wz = q[2], q32 = q[3], q33 = q[4];
     uint32_t n = 0;
@@ -429,11 +430,13 @@ uint32_t sgbm_oracle_reproject(const float *dmat, const uint8_t *gray, int W, in
                 volatile float w = d * q32;   /* volatile: forbid fused multiply-add */
                 w = w + q33;
                 float X = ((float)j + q03) / w, Y = ((float)i + q13) / w, Z = wz / w;
-                if (w > 0 && Z > 0 && Z <= depth_max && Z >= depth_min) {
+                if (w > 0 && Z > 0 && (double)Z <= depth_max && (double)Z >= depth_min) {
                     if (depth) depth[p] = Z;
                     if (pts) {
-                        uint32_t g = gray ? gray[p] : 0;
-                        pts[n].x = X; pts[n].y = Y; pts[n].z = Z; pts[n].rgb = (g << 16) | (g << 8) | g;
+                        uint32_t b = 0, g = 0, r = 0;
+                        if (color && channels == 1) b = g = r = color[p];
+                        else if (color && channels == 3) { b = color[3 * p]; g = color[3 * p + 1]; r = color[3 * p + 2]; }
+                        pts[n].x = X; pts[n].y = Y; pts[n].z = Z; pts[n].rgb = (r << 16) | (g << 8) | b;
                     }
                     n++;
                 }

@@ -305,6 +305,21 @@ def test_reprojection_c5_style():
     assert n == wpts.shape[0] and n > 1000
     assert np.array_equal(depth, wdepth)
     assert np.array_equal(pts.view(np.uint32), wpts.view(np.uint32))
+    # BGR8 colour source (disparity_to_depth.cpp:117-125, :185-188) and a depth window whose bounds are not float32 values
+    bgr = np.random.default_rng(2).integers(0, 256, (H, W, 3)).astype(np.uint8)
+    lo, hi = oracle.disparity_window(cam["fx"], 0.3, 0.35, 41.3)
+    disp, dmat, depth, pts, n = eng.compute_xyz(L, R, q, 0.35, 41.3, lo, hi, color=bgr)
+    wdm = oracle.process_disparity(want, lo, hi)
+    wdepth, wpts = oracle.reproject(wdm, bgr, q, 0.35, 41.3)
+    assert np.array_equal(dmat, wdm) and np.array_equal(depth, wdepth)
+    assert n == wpts.shape[0] and np.array_equal(pts.view(np.uint32), wpts.view(np.uint32))
+    # the C helper that forms q and the window like the reference does, against the oracle's statement of the same rules
+    Kl = np.array([[cam["fx"], 0, W / 2.0], [0, cam["fx"], H / 2.0], [0, 0, 1.0]])
+    Pl = np.array([[cam["fx"], 0, W / 2.0, 0], [0, cam["fx"], H / 2.0, 0], [0, 0, 1.0, 0]])
+    Pr = Pl.copy(); Pr[0, 3] = cam["p14"]
+    rp = b200sgm.reproject_from_camera(Kl, Pl, Pr, 0.35, 41.3)
+    assert np.array_equal(np.array([rp.q03, rp.q13, rp.wz, rp.q32, rp.q33], np.float32), q)
+    assert (rp.min_disparity, rp.max_disparity) == (np.float32(lo), np.float32(hi))
     eng.close()
 
 

@@ -96,3 +96,44 @@ def test_reprojection_restatement_matches_numpy():
     assert np.array_equal(depth, np.where(keep, Z, 0).astype(np.float32))
     assert pts.shape[0] == keep.sum()
     assert np.array_equal(pts[:, 0], X[keep]) and np.array_equal(pts[:, 1], Y[keep]) and np.array_equal(pts[:, 2], Z[keep])
+
+
+def _camera(rng):
+    fx = float(rng.uniform(600, 3000)); fy = fx * float(rng.uniform(0.99, 1.01))
+    cx, cy = float(rng.uniform(200, 1300)), float(rng.uniform(150, 1100))
+    cxr = cx + float(rng.choice([0.0, 0.0, 3.25, -7.5]))
+    fp = fx * float(rng.uniform(0.95, 1.05))          # P's focal length differs from K's after rectification
+    base = float(rng.uniform(0.05, 0.6))
+    Kl = np.array([[fx, 0, cx], [0, fy, cy], [0, 0, 1.0]])
+    Pl = np.array([[fp, 0, cx, 0], [0, fp, cy, 0], [0, 0, 1.0, 0]])
+    Pr = np.array([[fp, 0, cxr, -fp * base], [0, fp, cy, 0], [0, 0, 1.0, 0]])
+    return Kl, Pl, Pr, fp, base
+
+
+@pytest.mark.skipif(oracle.ref_lib() is None, reason="oracle/_ref not built (needs /root/reference or a prebuilt library)")
+def test_reprojection_pinned_to_the_reference_code():
+    """Rows a11 and R: the oracle's restatement against the REFERENCE'S OWN statements (oracle/_ref: calc_q and the per-pixel loop of
+    disparity_to_depth.cpp, the float conversion and depth window of generate_disparity.cpp:436-452, extracted from /root/reference
+    at build time and compiled against stand-in cv::Mat / pcl types).  Bit-for-bit, MONO8 and BGR8, several cameras and windows."""
+    rng = np.random.default_rng(17)
+    for case in range(12):
+        H, W = int(rng.integers(20, 70)), int(rng.integers(30, 100))
+        Kl, Pl, Pr, fp, base = _camera(rng)
+        depth_min = float(rng.choice([0.0, 0.3, 1.0])); depth_max = float(rng.choice([10.0, 2.5, 100.0, 0.7]))
+        disp16 = (rng.integers(-1, 200, (H, W)) * 16 + rng.integers(0, 16, (H, W))).astype(np.int16)
+        disp16[rng.random((H, W)) < 0.15] = -16
+        disp16[rng.random((H, W)) < 0.05] = 0
+        # a10 + a11: what stereo_match() hands to processDisparity is CV_32F holding the x16 value
+        want_dmat, lo, hi = oracle.ref_process_disparity(oracle.to_float(disp16), fp, base, depth_min, depth_max)
+        assert (lo, hi) == oracle.disparity_window(fp, base, depth_min, depth_max)
+        got_dmat = oracle.process_disparity(disp16, lo, hi)
+        assert np.array_equal(got_dmat.view(np.uint32), want_dmat.view(np.uint32))
+        # calc_q in double, cast to float as disparity_to_depth.cpp:136-140 does
+        Q = oracle.ref_calc_q(Kl, Pr, Pl)
+        q = oracle.calc_q(Kl[0, 0], Pl[0, 2], Pr[0, 2], Pl[1, 2], Pr[0, 3])
+        assert np.array_equal(q, np.array([Q[0, 3], Q[1, 3], Q[2, 3], Q[3, 2], Q[3, 3]]).astype(np.float32))
+        for color in (rng.integers(0, 256, (H, W)).astype(np.uint8), rng.integers(0, 256, (H, W, 3)).astype(np.uint8)):
+            wd, wp = oracle.ref_reproject(want_dmat, color, Kl, Pr, Pl, depth_min, depth_max)
+            gd, gp = oracle.reproject(got_dmat, color, q, depth_min, depth_max)
+            assert np.array_equal(gd.view(np.uint32), wd.view(np.uint32))
+            assert gp.shape == wp.shape and np.array_equal(gp.view(np.uint32), wp.view(np.uint32))
