@@ -1,11 +1,10 @@
-// Host launchers of the aggregation stages (k_horiz + cooperative k_sweep, or the generic per-direction kernels),
+// Host launchers of the aggregation stages (k_horiz + cooperative k_vert, or the generic per-direction kernels),
 // templated on N; instantiated once per N in agg_n*.cu so that the instantiations compile in parallel.
 #pragma once
 #include "engine_internal.h"
 #include "k_path.cuh"
 #include "k_wta.cuh"
 #include "k_fused.cuh"
-#include "k_sweep.cuh"
 
 template <int N>
 int launch_paths_generic(b200sgm_engine* h, Lane& ln, const Eff& e, cudaStream_t st)
@@ -33,48 +32,44 @@ int launch_paths_generic(b200sgm_engine* h, Lane& ln, const Eff& e, cudaStream_t
     return B200SGM_OK;
 }
 
-// ---- fused path: k_horiz + cooperative k_sweep --------------------------------------------------------
-struct SweepPlan { bool ok; int nstrips, twmax; size_t smem; };
+// ---- fused path: k_horiz + cooperative k_vert ---------------------------------------------------------
+struct VertPlan { bool ok; int nstrips, twmax; size_t smem; };
 
-template <int N> struct SweepCfg { static constexpr int RING = N >= 8 ? 4 : 8, MAXT = sweep_max_threads(N); };
+// Ring depth and thread budget per register count: up to 256 disparities 8 rows of C / S_h in flight and 64 registers per
+// thread; beyond that a row is at least twice the bytes, so half the depth hides the same DRAM latency, and fewer, fatter
+// threads keep the N = 8 row loop out of local memory.
+template <int N> struct VertCfg { static constexpr int RING = N >= 8 ? 4 : 8, MAXT = vert_max_threads(N); };
 
 template <int N>
-inline SweepPlan plan_sweep(const b200sgm_engine* h, const Eff& e, bool wta)
+inline VertPlan plan_vert(const b200sgm_engine* h, const Eff& e)
 {
-    SweepPlan p{false, 0, 0, 0};
-    if (e.W1 < 4) return p;
+    VertPlan p{false, 0, 0, 0};
+    if (e.W1 < 2) return p;
     int n = std::min(h->num_sms, e.W1 / 2);
     n = std::min(n, kMaxStrips);
-    const int tw = (e.W1 + n - 1) / n;
+    int tw = (e.W1 + n - 1) / n;
     // wider than one co-resident wave of strips (or than a CTA has warps): use the hybrid path
-    if (tw > kSweepMaxTW || 32 * (2 * tw + 1) > SweepCfg<N>::MAXT) return p;
+    if (tw > kVertMaxWarps || 64 * tw > VertCfg<N>::MAXT) return p;
     p.nstrips = n; p.twmax = tw;
-    p.smem = sweep_smem_bytes(tw, e.Dp, SweepCfg<N>::RING, wta);
+    p.smem = vert_smem_bytes(tw, e.Dp, VertCfg<N>::RING);
     p.ok = p.smem <= size_t(h->max_smem_optin);
     return p;
 }
 
 template <int N, bool UP, bool DO_WTA, bool FULL, bool CLAMP_EACH>
-int launch_sweep_t(b200sgm_engine* h, Lane& ln, const Eff& e, const SweepPlan& vp, cudaStream_t st)
+int launch_vert_t(b200sgm_engine* h, Lane& ln, const Eff& e, const VertPlan& vp, cudaStream_t st)
 {
-    SweepGeom g;
+    VertGeom g;
     g.w = WtaGeom{e.W, e.H, e.W1, e.minX1, e.minD, e.D, e.Dp, e.uniq, e.d12, e.INVALID};
     g.nstrips = vp.nstrips; g.twmax = vp.twmax;
     g.P1 = e.P1; g.P2 = e.P2;
     g.spin_limit = (long long)h->clock_khz * 500;   // ~0.5 s of SM clock ticks
     { static const int dbg = [] { const char* v = getenv("B200SGM_DEBUG_VERT"); return v ? atoi(v) : 0; }(); g.debug_flags = dbg; }
-    g.trace = nullptr; g.trace_strip = 0; g.trace_row0 = 0;
-    {
-        static const char* tr = getenv("B200SGM_TRACE");     // "strip,row0": development only
-        if (tr && DO_WTA) {
-            if (!h->trace) { CUDA_TRY(h, cudaMalloc(&h->trace, kTraceBytes)); }
-            CUDA_TRY(h, cudaMemsetAsync(h->trace, 0, kTraceBytes, st));
-            g.trace = h->trace;
-            sscanf(tr, "%d,%d", &g.trace_strip, &g.trace_row0);
-        }
-    }
-    const int nthreads = 32 * ((DO_WTA ? 2 : 1) * vp.twmax + 1);
-    auto kern = k_sweep<N, SweepCfg<N>::RING, UP, DO_WTA, FULL, CLAMP_EACH>;
+    // two agent warps per CTA when they fit next to the column warps (1024 threads per CTA)
+    int nthreads = (DO_WTA ? 64 : 32) * vp.twmax;
+    { static const bool no_agents = getenv("B200SGM_NO_AGENTS") != nullptr; g.agents = (!no_agents && nthreads + 64 <= VertCfg<N>::MAXT) ? 1 : 0; }
+    if (g.agents) nthreads += 64;
+    auto kern = k_vert<N, VertCfg<N>::RING, UP, DO_WTA, FULL, CLAMP_EACH>;
     {
         static std::atomic<unsigned long long> attr_done{0};   // per instantiation and device: raise the dynamic shared-memory limit once
         const unsigned long long bit = 1ull << (h->device & 63);
@@ -83,7 +78,7 @@ int launch_sweep_t(b200sgm_engine* h, Lane& ln, const Eff& e, const SweepPlan& v
             attr_done.fetch_or(bit);
         }
     }
-    CUDA_TRY(h, cudaMemsetAsync(ln.xbuf, 0, sweep_xbuf_bytes(vp.nstrips, e.Dp), st));
+    CUDA_TRY(h, cudaMemsetAsync(ln.xbuf, 0, size_t(2) * vp.nstrips * kXbufGen * (e.Dp / 2) * sizeof(uint2), st));
     const uint16_t* Cp = ln.C; uint16_t* Sp = ln.S; int16_t* dp = ln.disp_wta; uint32_t* kp = ln.disp2key;
     uint2* xb = ln.xbuf; int* er = ln.d_err;
     void* args[] = {(void*)&Cp, (void*)&Sp, (void*)&g, (void*)&dp, (void*)&kp, (void*)&xb, (void*)&er};
@@ -105,7 +100,7 @@ int launch_sweep_t(b200sgm_engine* h, Lane& ln, const Eff& e, const SweepPlan& v
 }
 
 template <int N, bool UP, bool DO_WTA>
-int launch_sweep(b200sgm_engine* h, Lane& ln, const Eff& e, const SweepPlan& vp, cudaStream_t st)
+int launch_vert(b200sgm_engine* h, Lane& ln, const Eff& e, const VertPlan& vp, cudaStream_t st)
 {
     const bool full = e.Dp == e.D && e.D == 64 * N;
     // worst-case cost of a cell: bs^2 * (2*ftzero + 63) (A.5 value bounds); one final clamp is enough when
@@ -115,10 +110,10 @@ int launch_sweep(b200sgm_engine* h, Lane& ln, const Eff& e, const SweepPlan& vp,
     // S_h arrives unclamped (<= 2*cmax) in MODE_SGBM / first sweep, clamped (<= kMaxCost) in the second sweep of MODE_HH
     const bool clamp_each = kMaxCost + 3 * cmax > 65535 || 5 * cmax > 65535;
     if (full) {
-        if (clamp_each) return launch_sweep_t<N, UP, DO_WTA, true, true>(h, ln, e, vp, st);
-        return launch_sweep_t<N, UP, DO_WTA, true, false>(h, ln, e, vp, st);
+        if (clamp_each) return launch_vert_t<N, UP, DO_WTA, true, true>(h, ln, e, vp, st);
+        return launch_vert_t<N, UP, DO_WTA, true, false>(h, ln, e, vp, st);
     }
-    return launch_sweep_t<N, UP, DO_WTA, false, true>(h, ln, e, vp, st);
+    return launch_vert_t<N, UP, DO_WTA, false, true>(h, ln, e, vp, st);
 }
 
 template <int N>
@@ -145,7 +140,7 @@ int launch_fused(b200sgm_engine* h, Lane& ln, const Eff& e, cudaStream_t st, boo
         LAUNCH_CHECK(h);
     }
     prof_mark(h, ln, 3, st);
-    const SweepPlan vp = plan_sweep<N>(h, e, true);
+    const VertPlan vp = plan_vert<N>(h, e);
     if (hybrid || !vp.ok) {
         static const int dirs_sgbm[3][2] = {{1, 1}, {0, 1}, {-1, 1}};
         static const int dirs_hh[6][2] = {{1, 1}, {0, 1}, {-1, 1}, {-1, -1}, {0, -1}, {1, -1}};
@@ -168,11 +163,11 @@ int launch_fused(b200sgm_engine* h, Lane& ln, const Eff& e, cudaStream_t st, boo
     }
     int rc;
     if (e.mode == B200SGM_MODE_HH) {
-        rc = launch_sweep<N, false, false>(h, ln, e, vp, st);
+        rc = launch_vert<N, false, false>(h, ln, e, vp, st);
         if (rc) return rc;
-        rc = launch_sweep<N, true, true>(h, ln, e, vp, st);
+        rc = launch_vert<N, true, true>(h, ln, e, vp, st);
     } else {
-        rc = launch_sweep<N, false, true>(h, ln, e, vp, st);
+        rc = launch_vert<N, false, true>(h, ln, e, vp, st);
     }
     return rc;
 }

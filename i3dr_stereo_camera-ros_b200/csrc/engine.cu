@@ -4,7 +4,6 @@
 // No CPU fallback exists: every result is produced by the kernels below.
 #include "engine_internal.h"
 #include "k_fused.cuh"   // geometry helpers only; the kernels are instantiated in agg_n*.cu
-#include "k_sweep.cuh"
 #include "k_post.cuh"
 
 CoopGate& coop_gate(int device)
@@ -230,7 +229,7 @@ int b200sgm_create(int device, int max_width, int max_height, int max_disparitie
         ok = ok && cudaMalloc(&ln.points, npix * sizeof(float4)) == cudaSuccess;
         ok = ok && cudaMalloc(&ln.block_count, ((npix + 255) / 256 + 1) * 4) == cudaSuccess && cudaMalloc(&ln.total, 4) == cudaSuccess;
         ok = ok && cudaMallocHost(&ln.h_total, 4) == cudaSuccess;
-        ok = ok && cudaMalloc(&ln.xbuf, sweep_xbuf_bytes(kMaxStrips, int(Dp))) == cudaSuccess;
+        ok = ok && cudaMalloc(&ln.xbuf, size_t(2) * kMaxStrips * kXbufGen * (Dp / 2) * sizeof(uint2)) == cudaSuccess;
         ok = ok && cudaMalloc(&ln.d_err, kStatusWords * sizeof(int)) == cudaSuccess && cudaMemset(ln.d_err, 0, kStatusWords * sizeof(int)) == cudaSuccess;
         ok = ok && cudaMallocHost(&ln.h_err, kStatusWords * sizeof(int)) == cudaSuccess;
         if (ok) memset(ln.h_err, 0, kStatusWords * sizeof(int));
@@ -252,7 +251,7 @@ int b200sgm_destroy(b200sgm_handle h)
     cudaSetDevice(h->device);
     for (Lane& ln : h->lanes) { if (ln.stream) cudaStreamSynchronize(ln.stream); free_lane(ln); }
     for (auto& r : h->rect) { cudaFree(r.ent); cudaFree(r.map1); cudaFree(r.map2); }
-    cudaFree(h->d_wtab); cudaFree(h->rect_src); cudaFree(h->rect_dst); cudaFree(h->trace);
+    cudaFree(h->d_wtab); cudaFree(h->rect_src); cudaFree(h->rect_dst);
     delete h;
     return B200SGM_OK;
 }
@@ -670,7 +669,6 @@ int b200sgm_debug_read(b200sgm_handle h, int lane, const char* what, void* host,
     else if (!strcmp(what, "wta")) src = ln.disp_wta;
     else if (!strcmp(what, "median")) src = ln.disp_med;
     else if (!strcmp(what, "stats")) src = ln.d_err;     // {error flag, late exchange records, poll iterations, max cost}
-    else if (!strcmp(what, "trace")) src = h->trace;      // k_sweep time stamps (B200SGM_TRACE), kTraceBytes
     else return fail(h, B200SGM_EINVAL, "unknown debug buffer");
     if (!src) return fail(h, B200SGM_ESTATE, "debug buffer not allocated");
     if (dp) {

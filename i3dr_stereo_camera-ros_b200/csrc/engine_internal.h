@@ -34,7 +34,7 @@ struct Lane {
     uint32_t *block_count = nullptr, *total = nullptr;
     uint32_t* h_total = nullptr;                    // pinned
     uint8_t* color = nullptr;                       // colour image of the point cloud (BGR8 / MONO8), allocated on first use
-    uint2* xbuf = nullptr;                          // k_sweep inter-strip records (LL protocol) and progress words
+    uint2* xbuf = nullptr;                          // k_vert exchange records (LL protocol)
     // device status words of the frame in flight: [0] inter-strip wait timed out, [1] late exchange records (debug),
     // [2] poll iterations (debug), [3] largest cost-volume cell seen by k_horiz (overflow guard)
     int* d_err = nullptr;
@@ -52,7 +52,6 @@ constexpr int kStages = 7;    // prefilter, cost, horizontal, vertical+wta, lrch
 constexpr int kProfRing = 256;
 constexpr int kMaxStrips = 320;
 constexpr int kStatusWords = 4;
-constexpr size_t kTraceBytes = (32 * 32 * 4 + 2 * kMaxStrips) * sizeof(long long);
 
 // Cooperative sweeps of ALL engines of a process on one device are serialised: one sweep fills every SM, and two
 // partially resident sweeps would spin on CTAs that can never be scheduled.  Process-wide, keyed by device; the events
@@ -81,7 +80,6 @@ struct b200sgm_engine {
     cudaEvent_t prof_ref = nullptr;   // time origin of the stage timeline
     int num_sms = 148;
     int max_smem_optin = 227 * 1024;
-    long long* trace = nullptr;                   // development: k_sweep time stamps (B200SGM_TRACE)
     int clock_khz = 1965000;
     std::mutex mu;
     // rectification (row N2): per camera (0 left, 1 right) the model and the cached fixed-point maps

@@ -401,9 +401,10 @@ struct VertGeom {
 // The consumer issues its record load at the TOP of the row and only inspects the tags right before it needs
 // the data, so in the common case (the neighbour is not late) the L2 round trip is off the critical path.
 constexpr int kXbufGen = 4;
-constexpr int kVRing = 8;     // rows of C in flight per column (cp.async ring in shared memory): DRAM latency x row rate
-constexpr int kSRing = 8;     // rows of S_h in flight: same depth as C -- cp.async groups retire in order, so a shallower
-                              // S_h ring would make its wait drain the younger C requests as well
+// RING (template parameter of k_vert) = rows of C and of S_h in flight per column (cp.async rings in shared memory): DRAM latency x
+// row rate.  The two rings have the same depth -- cp.async groups retire in order, so a shallower S_h ring would make its wait
+// drain the younger C requests as well.  8 up to 256 disparities, 4 beyond (a row is then at least twice the bytes).
+constexpr int vert_max_threads(int n) { return n <= 4 ? 1024 : 896; }   // 64 registers per thread, 72 for the N >= 8 instantiations
 constexpr int kRowUnroll = 4; // the row loop is unrolled by this: record generation, stage slot, parity are immediates
 __device__ __forceinline__ uint2* xrec(uint2* xbuf, int nstrips, int Dp, int side, int strip, int row)
 {
@@ -425,11 +426,11 @@ static_assert(kStage == kRowUnroll && kXbufGen == kRowUnroll && kStage % kWB == 
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
 __device__ __forceinline__ void named_bar_arrive(int id, int nthreads) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
 
-// dynamic smem: Ld[2 parity][2 dir][twmax+2][Dp] | Cring[kVRing][twmax][Dp] | Sring[kSRing][twmax][Dp] | stage[kStage][twmax][Dp]
+// dynamic smem: Ld[2 parity][2 dir][twmax+2][Dp] | Cring[twmax][RING][Dp] | Sring[twmax][RING][Dp] | stage[kStage][twmax][Dp]
 //               | xring[2 sides][kXbufGen][Dp]   (uint16)
-inline size_t vert_smem_bytes(int twmax, int Dp)
+inline size_t vert_smem_bytes(int twmax, int Dp, int ring)
 {
-    return (size_t(4) * (twmax + 2) + size_t(kVRing + kSRing + kStage) * twmax + 2 * kXbufGen) * Dp * sizeof(uint16_t);   // 190 KB at c3
+    return (size_t(4) * (twmax + 2) + size_t(2 * ring + kStage) * twmax + 2 * kXbufGen) * Dp * sizeof(uint16_t);   // 190 KB at c3
 }
 
 // Warp-specialised vertical sweep.  Launch: 32 * twmax threads when !DO_WTA, else 64 * twmax:
@@ -446,8 +447,8 @@ inline size_t vert_smem_bytes(int twmax, int Dp)
 // pairs an agent with its edge warp once per row.
 // FULL      : Dp == D == 64*N (no padded cells, every lane active)
 // CLAMP_EACH: saturate after every addition of the sum (needed when the 16-bit sum of the terms could wrap)
-template <int N, bool UP, bool DO_WTA, bool FULL, bool CLAMP_EACH>
-__global__ void __launch_bounds__(1024, 1) k_vert(const uint16_t* __restrict__ Cvol, uint16_t* __restrict__ Svol, VertGeom g,
+template <int N, int RING, bool UP, bool DO_WTA, bool FULL, bool CLAMP_EACH>
+__global__ void __launch_bounds__(vert_max_threads(N), 1) k_vert(const uint16_t* __restrict__ Cvol, uint16_t* __restrict__ Svol, VertGeom g,
                                                   int16_t* __restrict__ disp, uint32_t* __restrict__ disp2key,
                                                   uint2* __restrict__ xbuf, int* __restrict__ err)
 {
@@ -461,8 +462,8 @@ __global__ void __launch_bounds__(1024, 1) k_vert(const uint16_t* __restrict__ C
     // Ld holds the NORMALISED diagonal states; zero = "predecessor outside the image" (first row, border columns)
     uint16_t* Ld = smem_v;
     uint16_t* ringbase = Ld + size_t(4) * slots * Dp;
-    uint16_t* sringbase = ringbase + size_t(kVRing) * g.twmax * Dp;
-    uint16_t* stagebase = sringbase + size_t(kSRing) * g.twmax * Dp;
+    uint16_t* sringbase = ringbase + size_t(RING) * g.twmax * Dp;
+    uint16_t* stagebase = sringbase + size_t(RING) * g.twmax * Dp;
     uint16_t* xringbase = stagebase + size_t(kStage) * g.twmax * Dp;
     {
         uint32_t* z = reinterpret_cast<uint32_t*>(smem_v);
@@ -492,7 +493,7 @@ __global__ void __launch_bounds__(1024, 1) k_vert(const uint16_t* __restrict__ C
             const int nrow_a = 32 * (TW + nag), nfe_a = 64 * TW + 32 * nag;
             const int je = side == 0 ? 0 : TW - 1;
             uint16_t* wr = Ld + side * (slots * Dp) + (je + 1) * Dp + lane * 2 * N;          // + parity * 2*slots*Dp
-            const uint16_t* cring = ringbase + size_t(je) * kVRing * Dp + lane * 2 * N;
+            const uint16_t* cring = ringbase + size_t(je) * RING * Dp + lane * 2 * N;
             uint16_t* sB = dst;                                                              // stageB[side][kStage][Dp] aliases the xring
             asm volatile("bar.sync 1, %0;" ::"r"(nrow_a) : "memory");                          // C(0) is visible
             for (int r = 0; r < H; r++) {
@@ -520,7 +521,7 @@ __global__ void __launch_bounds__(1024, 1) k_vert(const uint16_t* __restrict__ C
                     }
                 }
                 dead = __any_sync(kFullMask, dead);
-                if (active) ld_regs<N>(cring + (r & (kVRing - 1)) * Dp, Cc);
+                if (active) ld_regs<N>(cring + (r & (RING - 1)) * Dp, Cc);
                 else {
 #pragma unroll
                     for (int q = 0; q < N; q++) Cc[q] = kMaxCostX2;
@@ -685,23 +686,23 @@ __global__ void __launch_bounds__(1024, 1) k_vert(const uint16_t* __restrict__ C
     uint16_t* gSout = Svol + (size_t(ystart) * W1 + x) * Dp + lo;          // row being computed (first pass of MODE_HH)
     const int Dh = Dp >> 1;
     // cp.async rings: [warp][slot][Dp], slot = row & (ring - 1).  Group G_r (committed at the top of row r) carries C
-    // of row r+kVRing-1 and S_h of row r+kSRing-1; the prologue commits C rows 0..kVRing-2 and S_h rows 0..kSRing-2.
-    uint16_t* ring = ringbase + size_t(j) * kVRing * Dp + lo;
-    uint16_t* sring = sringbase + size_t(j) * kSRing * Dp + lo;
+    // of row r+RING-1 and S_h of row r+RING-1; the prologue commits C rows 0..RING-2 and S_h rows 0..RING-2.
+    uint16_t* ring = ringbase + size_t(j) * RING * Dp + lo;
+    uint16_t* sring = sringbase + size_t(j) * RING * Dp + lo;
     auto issue_c = [&](int row_) {
-        if (row_ < H && active) cp_async_lane<N>(ring + (row_ & (kVRing - 1)) * Dp, gC);
+        if (row_ < H && active) cp_async_lane<N>(ring + (row_ & (RING - 1)) * Dp, gC);
         gC += rowStride;
     };
     auto issue_s = [&](int row_) {
-        if (row_ < H && active) cp_async_lane<N>(sring + (row_ & (kSRing - 1)) * Dp, gSin);
+        if (row_ < H && active) cp_async_lane<N>(sring + (row_ & (RING - 1)) * Dp, gSin);
         gSin += rowStride;
     };
 #pragma unroll
-    for (int i = 0; i < kSRing - 1; i++) issue_s(i);
+    for (int i = 0; i < RING - 1; i++) issue_s(i);
 #pragma unroll
-    for (int i = 0; i < kVRing - 1; i++) { issue_c(i); cp_async_commit(); }
+    for (int i = 0; i < RING - 1; i++) { issue_c(i); cp_async_commit(); }
     if (nag3) {            // agents read this column's C ring: make row 0 visible to them
-        cp_async_wait<kVRing - 2>();
+        cp_async_wait<RING - 2>();
         named_bar_sync(BAR_ROW, nrow);
     }
 
@@ -718,7 +719,7 @@ __global__ void __launch_bounds__(1024, 1) k_vert(const uint16_t* __restrict__ C
         constexpr bool EDGE = EMODE != 0;
         constexpr bool NO_B = EMODE == 3;      // the agent owns the incoming-diagonal step
         constexpr int PAR = Q & 1;
-        issue_c(r + kVRing - 1); issue_s(r + kSRing - 1); cp_async_commit();
+        issue_c(r + RING - 1); issue_s(r + RING - 1); cp_async_commit();
         uint32_t Cc[N], Sc[N], LtA[N], LtB[N], LnA[N], LnV[N], LnB[N];
         // incoming diagonal of the previous row: fire the loads now, inspect the tags right before step B
         const bool consume = EDGE && r > 0;
@@ -729,9 +730,9 @@ __global__ void __launch_bounds__(1024, 1) k_vert(const uint16_t* __restrict__ C
                 for (int q = 0; q < N; q++) pre[q] = ld_volatile_v2(rec + q);
             }
         }
-        cp_async_wait<kVRing - 1>();     // this thread's copies of row r have landed (each lane reads only its own bytes)
+        cp_async_wait<RING - 1>();     // this thread's copies of row r have landed (each lane reads only its own bytes)
         if (active) {
-            ld_regs<N>(ring + (r & (kVRing - 1)) * Dp, Cc); ld_regs<N>(rdA[PAR ^ 1], LtA);
+            ld_regs<N>(ring + (r & (RING - 1)) * Dp, Cc); ld_regs<N>(rdA[PAR ^ 1], LtA);
             if (!EDGE) ld_regs<N>(rdB[PAR ^ 1], LtB);
         } else {
 #pragma unroll
@@ -806,8 +807,7 @@ __global__ void __launch_bounds__(1024, 1) k_vert(const uint16_t* __restrict__ C
             for (int q = 0; q < N; q++) LnB[q] = 0;
         }
         // ---- S = sat(S_h + L_v + L_A + L_B)
-        static_assert(kSRing == kVRing, "S_h of row r travels in the same group as C of row r");
-        if (active) ld_regs<N>(sring + (r & (kSRing - 1)) * Dp, Sc);
+        if (active) ld_regs<N>(sring + (r & (RING - 1)) * Dp, Sc);
         else {
 #pragma unroll
             for (int q = 0; q < N; q++) Sc[q] = 0;
@@ -839,7 +839,7 @@ __global__ void __launch_bounds__(1024, 1) k_vert(const uint16_t* __restrict__ C
             if (active) st_regs<N>(gSout, S);
             gSout += rowStride;
         }
-        if (DO_WTA) cp_async_wait<kVRing - 2>();   // C of the NEXT row is complete before the barrier: the agents read it
+        if (DO_WTA) cp_async_wait<RING - 2>();   // C of the NEXT row is complete before the barrier: the agents read it
         named_bar_sync(BAR_ROW, nrow);
     };
 
