@@ -89,7 +89,24 @@ def build_host(force: bool = False) -> str:
     return HARNESS
 
 
+STREAM_BENCH = os.path.join(HOST, "stream_bench")
+
+
+def build_stream(force: bool = False) -> str:
+    """Builds the C++ frame-stream driver (host/stream_driver.cpp) with its single-process multi-GPU bench (host/stream_bench.cpp)."""
+    srcs = [os.path.join(HOST, "stream_bench.cpp"), os.path.join(HOST, "stream_driver.cpp")]
+    deps = srcs + [os.path.join(HOST, "stream_driver.h"), LIB]
+    if not force and os.path.exists(STREAM_BENCH) and all(os.path.getmtime(d) <= os.path.getmtime(STREAM_BENCH) for d in deps):
+        return STREAM_BENCH
+    cmd = ["g++", "-std=c++17", "-O2", "-pthread", "-I" + os.path.join(HERE, "..", "include"), "-I" + HOST, "-o", STREAM_BENCH] + srcs + \
+          ["-L" + HERE, "-lb200sgm", "-Wl,-rpath,$ORIGIN/.."]
+    print("[b200sgm] " + " ".join(cmd), file=sys.stderr)
+    subprocess.check_call(cmd)
+    return STREAM_BENCH
+
+
 if __name__ == "__main__":
     build(force="--force" in sys.argv, verbose="-v" in sys.argv)
     build_host(force="--force" in sys.argv)
+    build_stream(force="--force" in sys.argv)
     print(LIB)

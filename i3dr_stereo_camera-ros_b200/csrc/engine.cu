@@ -24,6 +24,7 @@ int nreg_for(int D)
 // A.1 parameter normalisation + geometry.  Returns 0 or B200SGM_EINVAL with h->err set.
 int make_eff(b200sgm_engine* h, int W, int H, Eff& e)
 {
+    if (h->bm_only) return fail(h, B200SGM_ESTATE, "this engine was created with b200sgm_create_bm: block matcher and rectification only");
     b200sgm_params p;
     {
         std::lock_guard<std::mutex> lk(h->mu);     // set_params may run on another thread
@@ -195,7 +196,7 @@ extern "C" {
 
 const char* b200sgm_version(void) { return "b200sgm 0.1 (sm_100a)"; }
 
-int b200sgm_create(int device, int max_width, int max_height, int max_disparities, int lanes, b200sgm_handle* out)
+static int create_engine(int device, int max_width, int max_height, int max_disparities, int lanes, bool bm_only, b200sgm_handle* out)
 {
     if (!out) return B200SGM_EINVAL;
     *out = nullptr;
@@ -204,7 +205,7 @@ int b200sgm_create(int device, int max_width, int max_height, int max_disparitie
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev) return B200SGM_ECUDA;
     if (cudaSetDevice(device) != cudaSuccess) return B200SGM_ECUDA;
     b200sgm_engine* h = new b200sgm_engine();
-    h->device = device; h->maxW = max_width; h->maxH = max_height; h->maxD = max_disparities;
+    h->device = device; h->maxW = max_width; h->maxH = max_height; h->maxD = max_disparities; h->bm_only = bm_only;
     cudaDeviceGetAttribute(&h->num_sms, cudaDevAttrMultiProcessorCount, device);
     cudaDeviceGetAttribute(&h->clock_khz, cudaDevAttrClockRate, device);
     cudaDeviceGetAttribute(&h->max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
@@ -219,8 +220,12 @@ int b200sgm_create(int device, int max_width, int max_height, int max_disparitie
         ok = ok && cudaEventCreateWithFlags(&ln.done, cudaEventDisableTiming) == cudaSuccess;
         ok = ok && cudaMalloc(&ln.left, npix) == cudaSuccess && cudaMalloc(&ln.right, npix) == cudaSuccess;
         ok = ok && cudaMalloc(&ln.feat_l, npix * sizeof(Feat)) == cudaSuccess && cudaMalloc(&ln.feat_r, npix * sizeof(Feat)) == cudaSuccess;
-        ok = ok && cudaMalloc(&ln.C, vol) == cudaSuccess && cudaMalloc(&ln.S, vol) == cudaSuccess;
-        ok = ok && cudaMalloc(&ln.ckpt, horiz_ckpt_elems(max_width, max_height, int(Dp)) * sizeof(uint16_t)) == cudaSuccess;
+        ok = ok && cudaMalloc(&ln.C, vol) == cudaSuccess;
+        if (!bm_only) {
+            ok = ok && cudaMalloc(&ln.S, vol) == cudaSuccess;
+            ok = ok && cudaMalloc(&ln.ckpt, horiz_ckpt_elems(max_width, max_height, int(Dp)) * sizeof(uint16_t)) == cudaSuccess;
+            ok = ok && cudaMalloc(&ln.xbuf, size_t(2) * kMaxStrips * kXbufGen * (Dp / 2) * sizeof(uint2)) == cudaSuccess;
+        }
         ok = ok && cudaMalloc(&ln.disp2key, npix * 4) == cudaSuccess;
         ok = ok && cudaMalloc(&ln.disp_wta, npix * 2 + 16) == cudaSuccess && cudaMalloc(&ln.disp_med, npix * 2) == cudaSuccess && cudaMalloc(&ln.disp_out, npix * 2) == cudaSuccess;
         ok = ok && cudaMalloc(&ln.label, npix * 4) == cudaSuccess && cudaMalloc(&ln.csize, npix * 4) == cudaSuccess;
@@ -229,7 +234,6 @@ int b200sgm_create(int device, int max_width, int max_height, int max_disparitie
         ok = ok && cudaMalloc(&ln.points, npix * sizeof(float4)) == cudaSuccess;
         ok = ok && cudaMalloc(&ln.block_count, ((npix + 255) / 256 + 1) * 4) == cudaSuccess && cudaMalloc(&ln.total, 4) == cudaSuccess;
         ok = ok && cudaMallocHost(&ln.h_total, 4) == cudaSuccess;
-        ok = ok && cudaMalloc(&ln.xbuf, size_t(2) * kMaxStrips * kXbufGen * (Dp / 2) * sizeof(uint2)) == cudaSuccess;
         ok = ok && cudaMalloc(&ln.d_err, kStatusWords * sizeof(int)) == cudaSuccess && cudaMemset(ln.d_err, 0, kStatusWords * sizeof(int)) == cudaSuccess;
         ok = ok && cudaMallocHost(&ln.h_err, kStatusWords * sizeof(int)) == cudaSuccess;
         if (ok) memset(ln.h_err, 0, kStatusWords * sizeof(int));
@@ -243,6 +247,29 @@ int b200sgm_create(int device, int max_width, int max_height, int max_disparitie
     }
     *out = h;
     return B200SGM_OK;
+}
+
+int b200sgm_create(int device, int max_width, int max_height, int max_disparities, int lanes, b200sgm_handle* out)
+{
+    return create_engine(device, max_width, max_height, max_disparities, lanes, false, out);
+}
+
+int b200sgm_create_bm(int device, int max_width, int max_height, int max_disparities, int lanes, b200sgm_handle* out)
+{
+    return create_engine(device, max_width, max_height, max_disparities, lanes, true, out);
+}
+
+int b200sgm_host_alloc(size_t bytes, void** ptr)
+{
+    if (!ptr || bytes == 0) return B200SGM_EINVAL;
+    *ptr = nullptr;
+    return cudaMallocHost(ptr, bytes) == cudaSuccess ? B200SGM_OK : B200SGM_ECUDA;
+}
+
+int b200sgm_host_free(void* ptr)
+{
+    if (!ptr) return B200SGM_OK;
+    return cudaFreeHost(ptr) == cudaSuccess ? B200SGM_OK : B200SGM_ECUDA;
 }
 
 int b200sgm_destroy(b200sgm_handle h)
@@ -546,6 +573,8 @@ int bm_run(b200sgm_engine* h, Lane& ln, const b200sgm_bm_params* bp, const uint8
     if (bp->blockSize < 5 || bp->blockSize > 255 || bp->blockSize % 2 == 0 || bp->blockSize >= std::min(width, height))
         return fail(h, B200SGM_EINVAL, "blockSize must be odd, within 5..255 and smaller than the image width and height");
     if (bp->preFilterCap < 1 || bp->preFilterCap > 63) return fail(h, B200SGM_EINVAL, "preFilterCap must be within 1..63");
+    if (bp->preFilterSize != 0 && (bp->preFilterSize < 5 || bp->preFilterSize > 255 || bp->preFilterSize % 2 == 0))
+        return fail(h, B200SGM_EINVAL, "preFilterSize must be odd and be within 5..255");
     if (bp->textureThreshold < 0 || bp->uniquenessRatio < 0) return fail(h, B200SGM_EINVAL, "textureThreshold and uniquenessRatio must be non-negative");
     if (bp->disp12MaxDiff >= 0) return fail(h, B200SGM_EINVAL, "disp12MaxDiff >= 0 is not supported by the block matcher (the reference never sets it)");
     if ((bp->minDisparity + bp->numDisparities) * 16 >= 32768 || (bp->minDisparity - 1) * 16 < -32768) return fail(h, B200SGM_EINVAL, "disparity range does not fit CV_16S x16");
@@ -577,6 +606,28 @@ int b200sgm_bm_compute(b200sgm_handle h, const b200sgm_bm_params* bp, const uint
     CUDA_TRY(h, cudaMemcpy2DAsync(ln.right, width, right, right_stride, width, height, cudaMemcpyHostToDevice, st));
     if (int rc = bm_run(h, ln, bp, ln.left, width, ln.right, width, width, height, st)) return rc;
     CUDA_TRY(h, cudaMemcpy2DAsync(disp, disp_stride, ln.disp_out, size_t(width) * 2, size_t(width) * 2, height, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(h, cudaStreamSynchronize(st));
+    return B200SGM_OK;
+}
+
+int b200sgm_bm_compute_f32(b200sgm_handle h, const b200sgm_bm_params* bp, const uint8_t* left, size_t left_stride, const uint8_t* right,
+                           size_t right_stride, int width, int height, float* disp32, size_t disp_stride)
+{
+    if (!h || !bp || !left || !right || !disp32) return B200SGM_EINVAL;
+    if (width <= 0 || height <= 0) return fail(h, B200SGM_EINVAL, "empty image");
+    if (width > h->maxW || height > h->maxH) return fail(h, B200SGM_ESIZE, "image exceeds the engine's max size");
+    if (left_stride < size_t(width) || right_stride < size_t(width) || disp_stride < size_t(width) * 4) return fail(h, B200SGM_EINVAL, "stride smaller than a row");
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    Lane& ln = h->lanes[0];
+    if (ln.busy) return fail(h, B200SGM_ESTATE, "lane 0 is busy: call b200sgm_wait first");
+    cudaStream_t st = ln.stream;
+    CUDA_TRY(h, cudaMemcpy2DAsync(ln.left, width, left, left_stride, width, height, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(h, cudaMemcpy2DAsync(ln.right, width, right, right_stride, width, height, cudaMemcpyHostToDevice, st));
+    if (int rc = bm_run(h, ln, bp, ln.left, width, ln.right, width, width, height, st)) return rc;
+    const int npix = width * height;
+    k_to_f32<<<(npix + 255) / 256, 256, 0, st>>>(ln.disp_out, ln.f32a, npix);
+    LAUNCH_CHECK(h);
+    CUDA_TRY(h, cudaMemcpy2DAsync(disp32, disp_stride, ln.f32a, size_t(width) * 4, size_t(width) * 4, height, cudaMemcpyDeviceToHost, st));
     CUDA_TRY(h, cudaStreamSynchronize(st));
     return B200SGM_OK;
 }

@@ -70,6 +70,7 @@ constexpr int kVertMaxWarps = 16;
 struct b200sgm_engine {
     int device = 0;
     int maxW = 0, maxH = 0, maxD = 0;
+    bool bm_only = false;                         // created by b200sgm_create_bm: no S / checkpoint / exchange buffers
     std::vector<Lane> lanes;
     b200sgm_params raw{};
     bool have_params = false;

@@ -23,6 +23,7 @@ SYMBOLS = (
     "b200sgm_debug_set_path", "b200sgm_profile", "b200sgm_stage_times", "b200sgm_alu_peak", "b200sgm_stage_timeline",
     "b200sgm_set_camera", "b200sgm_rectify", "b200sgm_rectify_device", "b200sgm_rectify_maps", "b200sgm_bm_compute",
     "b200sgm_bm_compute_device", "b200sgm_lane_status", "b200sgm_reproject_from_camera",
+    "b200sgm_create_bm", "b200sgm_host_alloc", "b200sgm_host_free", "b200sgm_bm_compute_f32",
 )
 
 STAGES = ("prefilter", "cost", "horizontal", "vertical_wta", "lrcheck", "median", "speckle")
@@ -70,10 +71,12 @@ def _u8(a):
 class Engine:
     """One engine per GPU. `lanes` = frames that may be in flight (each lane owns its scratch volumes)."""
 
-    def __init__(self, device=0, max_width=640, max_height=480, max_disparities=64, lanes=1, params: SGBMParams | None = None):
+    def __init__(self, device=0, max_width=640, max_height=480, max_disparities=64, lanes=1, params: SGBMParams | None = None,
+                 bm_only=False):
         self.lib = load_library()
         self.h = ctypes.c_void_p()
-        rc = self.lib.b200sgm_create(int(device), int(max_width), int(max_height), int(max_disparities), int(lanes), ctypes.byref(self.h))
+        create = self.lib.b200sgm_create_bm if bm_only else self.lib.b200sgm_create
+        rc = create(int(device), int(max_width), int(max_height), int(max_disparities), int(lanes), ctypes.byref(self.h))
         if rc != 0:
             raise B200SGMError(rc, "b200sgm_create failed (no usable CUDA device or out of memory)")
         self.device = device
@@ -196,23 +199,24 @@ class Engine:
 
     # ---- StereoBM (row N4): cv::StereoBM::compute of matcherOpenCVBlock.cpp:13-20 ----
     def bm_compute(self, left, right, numDisparities=64, blockSize=9, minDisparity=0, preFilterCap=31, textureThreshold=10,
-                   uniquenessRatio=15, speckleWindowSize=0, speckleRange=0, disp12MaxDiff=-1) -> np.ndarray:
+                   uniquenessRatio=15, speckleWindowSize=0, speckleRange=0, disp12MaxDiff=-1, preFilterSize=0, f32=False) -> np.ndarray:
         L, R = _u8(left), _u8(right)
         if L.shape != R.shape:
             raise ValueError("Images MUST be the same resolution")
         H, W = L.shape
-        bp = (ctypes.c_int * 9)(minDisparity, numDisparities, blockSize, preFilterCap, textureThreshold, uniquenessRatio,
-                                speckleWindowSize, speckleRange, disp12MaxDiff)
-        out = np.empty((H, W), np.int16)
-        self._check(self.lib.b200sgm_bm_compute(self.h, bp, L.ctypes.data_as(ctypes.c_void_p), ctypes.c_size_t(L.strides[0]),
-                                                R.ctypes.data_as(ctypes.c_void_p), ctypes.c_size_t(R.strides[0]), W, H,
-                                                out.ctypes.data_as(ctypes.c_void_p), ctypes.c_size_t(W * 2)))
+        bp = (ctypes.c_int * 10)(minDisparity, numDisparities, blockSize, preFilterCap, textureThreshold, uniquenessRatio,
+                                 speckleWindowSize, speckleRange, disp12MaxDiff, preFilterSize)
+        out = np.empty((H, W), np.float32 if f32 else np.int16)
+        fn = self.lib.b200sgm_bm_compute_f32 if f32 else self.lib.b200sgm_bm_compute
+        self._check(fn(self.h, bp, L.ctypes.data_as(ctypes.c_void_p), ctypes.c_size_t(L.strides[0]),
+                       R.ctypes.data_as(ctypes.c_void_p), ctypes.c_size_t(R.strides[0]), W, H,
+                       out.ctypes.data_as(ctypes.c_void_p), ctypes.c_size_t(out.strides[0])))
         return out
 
     def bm_compute_device(self, lane, lptr, lstride, rptr, rstride, W, H, dptr, dstride, stream=0, numDisparities=64, blockSize=9,
                           minDisparity=0, preFilterCap=31, textureThreshold=10, uniquenessRatio=15, speckleWindowSize=0, speckleRange=0):
-        bp = (ctypes.c_int * 9)(minDisparity, numDisparities, blockSize, preFilterCap, textureThreshold, uniquenessRatio,
-                                speckleWindowSize, speckleRange, -1)
+        bp = (ctypes.c_int * 10)(minDisparity, numDisparities, blockSize, preFilterCap, textureThreshold, uniquenessRatio,
+                                 speckleWindowSize, speckleRange, -1, 0)
         self._check(self.lib.b200sgm_bm_compute_device(self.h, int(lane), bp, ctypes.c_void_p(lptr), ctypes.c_size_t(lstride),
                                                        ctypes.c_void_p(rptr), ctypes.c_size_t(rstride), int(W), int(H),
                                                        ctypes.c_void_p(dptr), ctypes.c_size_t(dstride), ctypes.c_void_p(stream)))

@@ -41,6 +41,11 @@ public:
     Mat(Size s, int type) { create(s.height, s.width, type); }
     Mat(Size s, int type, Scalar fill) { create(s.height, s.width, type); setTo(fill.v); }
     Mat(int r, int c, int type) { create(r, c, type); }
+    // header over caller-owned data, like cv::Mat(rows, cols, type, data, step)
+    Mat(int r, int c, int type, void* ext, size_t stp = 0) : rows(r), cols(c), data(static_cast<uint8_t*>(ext)), type_(type)
+    {
+        step = stp ? stp : size_t(c) * elem_size(type);
+    }
 
     static size_t elem_size(int type) { return type == CV_8UC1 ? 1 : (type == CV_16S ? 2 : 4); }
     void create(int r, int c, int type)
@@ -73,6 +78,10 @@ public:
     }
     void convertTo(Mat& dst, int rtype, double alpha = 1.0) const
     {
+        if (rtype == type_ && alpha == 1.0) {   // OpenCV: same depth, no scale -> copyTo, which returns at once when dst is this matrix
+            if (dst.data != data) copyTo(dst);
+            return;
+        }
         Mat out(rows, cols, rtype);
         for (int y = 0; y < rows; y++)
             for (int x = 0; x < cols; x++) {

@@ -6,12 +6,19 @@
 //           [algorithm: 0 = B200 SGM (default), 1 = B200 block matcher] [textureThreshold] [--bench N]
 // --bench N: after the first match, times N more stereo_match() calls on the same pair (the per-frame cost the node pays:
 // setImages copy + match + getDisparity copy) and prints "bench_ms_per_frame <ms>" on stderr.
+// --back out.f32: also backwardMatch() + getBackDisparity() (the right-view disparity of matcherOpenCVSGBM.cpp:46-51).
+// --cloud prefix fx cx cxr cy p14 depth_min depth_max [color.raw channels]: MatcherB200SGM::matchToCloud with the CameraInfo
+//   K_l = [fx 0 cx; 0 fx cy; 0 0 1], P_l = [K_l | 0], P_r = P_l with cx -> cxr and P_r[0][3] = p14; writes prefix.dmat.f32,
+//   prefix.depth.f32 and prefix.cloud.bin (uint32 count, then count x {x, y, z, rgb}); --bench then times matchToCloud too
+//   ("bench_cloud_ms_per_frame").
+// --bad-prefilter-size N: pushes setPreFilterSize(N) before matching (cv::StereoBM rejects even or out-of-range sizes).
 #include <chrono>
 #include <cstdio>
 #include <cstring>
 #include <cstdlib>
 #include <fstream>
 #include <iostream>
+#include <string>
 #include <vector>
 
 #include "matcherB200SGM.h"
@@ -97,8 +104,19 @@ int main(int argc, char **argv)
   _stereo_algorithm = argc > 16 ? atoi(argv[16]) : 0;
   if (argc > 17) _texture_threshold = atoi(argv[17]);
   int bench_frames = 0;
-  for (int i = 15; i + 1 < argc; i++)
-    if (!strcmp(argv[i], "--bench")) bench_frames = atoi(argv[i + 1]);
+  const char *back_path = nullptr, *cloud_prefix = nullptr, *color_path = nullptr;
+  int color_channels = 0;
+  double cam[7] = {0, 0, 0, 0, 0, 0, 0};   // fx cx cxr cy p14 depth_min depth_max
+  for (int i = 15; i < argc; i++) {
+    if (!strcmp(argv[i], "--bench") && i + 1 < argc) bench_frames = atoi(argv[++i]);
+    else if (!strcmp(argv[i], "--back") && i + 1 < argc) back_path = argv[++i];
+    else if (!strcmp(argv[i], "--bad-prefilter-size") && i + 1 < argc) _preFilterSize = atoi(argv[++i]);
+    else if (!strcmp(argv[i], "--cloud") && i + 8 < argc) {
+      cloud_prefix = argv[++i];
+      for (int k = 0; k < 7; k++) cam[k] = atof(argv[++i]);
+      if (i + 2 < argc && argv[i + 1][0] != '-') { color_path = argv[++i]; color_channels = atoi(argv[++i]); }
+    }
+  }
 
   // warm-up exactly like init_stereo_matchers.cpp:41-56: a 10x10 zero pair through setImages/match/getDisparity
   {
@@ -123,6 +141,53 @@ int main(int argc, char **argv)
   }
   std::ofstream o(argv[5], std::ios::binary);
   for (int y = 0; y < disp.rows; y++) o.write(reinterpret_cast<const char *>(disp.data + y * disp.step), size_t(disp.cols) * 4);
+  if (back_path && _stereo_algorithm == 0) {
+    if (matcher->backwardMatch() != 0) return 1;
+    cv::Mat back;
+    matcher->getBackDisparity(back);
+    std::ofstream ob(back_path, std::ios::binary);
+    for (int y = 0; y < back.rows; y++) ob.write(reinterpret_cast<const char *>(back.data + y * back.step), size_t(back.cols) * 4);
+  }
+  if (cloud_prefix && _stereo_algorithm == 0) {
+    B200StereoCamera c;
+    const double K[9] = {cam[0], 0, cam[1], 0, cam[0], cam[3], 0, 0, 1};
+    const double Pl[12] = {cam[0], 0, cam[1], 0, 0, cam[0], cam[3], 0, 0, 0, 1, 0};
+    const double Pr[12] = {cam[0], 0, cam[2], cam[4], 0, cam[0], cam[3], 0, 0, 0, 1, 0};
+    memcpy(c.K_l, K, sizeof K); memcpy(c.P_l, Pl, sizeof Pl); memcpy(c.P_r, Pr, sizeof Pr);
+    std::vector<unsigned char> color;
+    if (color_path) {
+      color.resize(size_t(W) * H * color_channels);
+      std::ifstream fc(color_path, std::ios::binary);
+      fc.read(reinterpret_cast<char *>(color.data()), color.size());
+      if (!fc) { std::cerr << "cannot read the colour image" << std::endl; return 2; }
+    }
+    cv::Mat dmat, depth;
+    std::vector<b200sgm_point> cloud;
+    matcher->setImages(&left, &right);
+    auto once = [&] {
+      return b200sgm_matcher->matchToCloud(c, cam[5], cam[6], color_path ? color.data() : nullptr, size_t(W) * color_channels, color_channels,
+                                           dmat, depth, cloud);
+    };
+    if (once() != 0) return 1;
+    const std::string pre(cloud_prefix);
+    std::ofstream o1(pre + ".dmat.f32", std::ios::binary), o2(pre + ".depth.f32", std::ios::binary), o3(pre + ".cloud.bin", std::ios::binary);
+    for (int y = 0; y < H; y++) {
+      o1.write(reinterpret_cast<const char *>(dmat.data + y * dmat.step), size_t(W) * 4);
+      o2.write(reinterpret_cast<const char *>(depth.data + y * depth.step), size_t(W) * 4);
+    }
+    const uint32_t n = uint32_t(cloud.size());
+    o3.write(reinterpret_cast<const char *>(&n), 4);
+    o3.write(reinterpret_cast<const char *>(cloud.data()), size_t(n) * sizeof(b200sgm_point));
+    if (bench_frames > 0) {
+      const auto t0 = std::chrono::steady_clock::now();
+      for (int i = 0; i < bench_frames; i++) {
+        matcher->setImages(&left, &right);
+        if (once() != 0) return 1;
+      }
+      const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count() / bench_frames;
+      std::cerr << "bench_cloud_ms_per_frame " << ms << std::endl;
+    }
+  }
   // mismatched sizes must leave the previous images untouched and still succeed (abstractStereoMatcher.cpp:21-24)
   cv::Mat small(cv::Size(W / 2, H), CV_8UC1);
   matcher->setImages(&left, &small);

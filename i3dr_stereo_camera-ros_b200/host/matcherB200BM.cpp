@@ -22,10 +22,13 @@ void MatcherB200BM::init(void)
   params_.speckleWindowSize = 0;
   params_.speckleRange = 0;
   params_.disp12MaxDiff = -1;
+  params_.preFilterSize = 0;   // StereoBM::create's default (9)
 }
 
 MatcherB200BM::~MatcherB200BM()
 {
+  disparity_lr = cv::Mat();
+  b200sgm_host_free(lr_buf_);
   if (engine_) b200sgm_destroy(engine_);
 }
 
@@ -37,7 +40,7 @@ int MatcherB200BM::ensureEngine(int width, int height)
   cap_w_ = std::max(width, cap_w_);
   cap_h_ = std::max(height, cap_h_);
   cap_d_ = std::max((d + 63) / 64 * 64, cap_d_);
-  const int rc = b200sgm_create(device_, cap_w_, cap_h_, cap_d_, 1, &engine_);
+  const int rc = b200sgm_create_bm(device_, cap_w_, cap_h_, cap_d_, 1, &engine_);
   if (rc != B200SGM_OK) {
     engine_ = nullptr;
     cap_w_ = cap_h_ = cap_d_ = 0;
@@ -59,19 +62,19 @@ int MatcherB200BM::forwardMatch()
   }
   const int w = left->cols, h = left->rows;
   int rc = ensureEngine(w, h);
+  if (rc == 0 && lr_cap_ < size_t(w) * h) {
+    b200sgm_host_free(lr_buf_);
+    lr_buf_ = nullptr; lr_cap_ = 0;
+    void *p = nullptr;
+    if (b200sgm_host_alloc(size_t(w) * h * sizeof(float), &p) == B200SGM_OK) { lr_buf_ = static_cast<float *>(p); lr_cap_ = size_t(w) * h; }
+    else { error_ = "page-locked host allocation failed"; rc = B200SGM_ECUDA; }
+  }
   if (rc == 0) {
-    std::vector<int16_t> d16(size_t(w) * h);
-    rc = b200sgm_bm_compute(engine_, &params_, left->data, left->step, right->data, right->step, w, h, d16.data(), size_t(w) * 2);
+    // disparity_lr.convertTo(disparity_lr, CV_32FC1): same numeric value, still x16 (matcherOpenCVBlock.cpp:34) -- done on the device
+    if (disparity_lr.data != reinterpret_cast<unsigned char *>(lr_buf_) || disparity_lr.rows != h || disparity_lr.cols != w)
+      disparity_lr = cv::Mat(h, w, CV_32FC1, lr_buf_);
+    rc = b200sgm_bm_compute_f32(engine_, &params_, left->data, left->step, right->data, right->step, w, h, lr_buf_, size_t(w) * sizeof(float));
     if (rc != 0) error_ = b200sgm_last_error(engine_);
-    else {
-      // disparity_lr.convertTo(disparity_lr, CV_32FC1): same numeric value, still x16 (matcherOpenCVBlock.cpp:34)
-      if (disparity_lr.rows != h || disparity_lr.cols != w || disparity_lr.type() != CV_32FC1)
-        disparity_lr = cv::Mat(cv::Size(w, h), CV_32FC1);
-      for (int y = 0; y < h; y++) {
-        float *o = reinterpret_cast<float *>(disparity_lr.data + size_t(y) * disparity_lr.step);
-        for (int x = 0; x < w; x++) o[x] = float(d16[size_t(y) * w + x]);
-      }
-    }
   }
   if (rc != 0) {
     std::cerr << "Error in OpenCV StereoBM parameters" << std::endl;   // the reference's wording (matcherOpenCVBlock.cpp:40)
@@ -113,3 +116,4 @@ void MatcherB200BM::setSpeckleFilterRange(int range) { params_.speckleRange = ra
 void MatcherB200BM::setDisp12MaxDiff(int diff) { params_.disp12MaxDiff = diff; }
 void MatcherB200BM::setInterpolation(bool enable) { this->interpolate = enable; }
 void MatcherB200BM::setPreFilterCap(int cap) { params_.preFilterCap = cap; }
+void MatcherB200BM::setPreFilterSize(int size) { params_.preFilterSize = size; }

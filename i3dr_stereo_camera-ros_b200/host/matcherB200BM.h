@@ -36,7 +36,7 @@ public:
   void setDisp12MaxDiff(int diff);
   void setInterpolation(bool enable);
   void setPreFilterCap(int cap);
-  void setPreFilterSize(int size) {}   // only read by PREFILTER_NORMALIZED_RESPONSE; StereoBM::create leaves XSOBEL
+  void setPreFilterSize(int size);     // PREFILTER_XSOBEL never reads it, but cv::StereoBM::compute validates it all the same
   // not used by the block matcher, same as matcherOpenCVBlock.h
   void setP1(float p1) {}
   void setP2(float p2) {}
@@ -50,6 +50,8 @@ private:
   b200sgm_bm_params params_;
   int device_ = 0;
   int cap_w_ = 0, cap_h_ = 0, cap_d_ = 0;
+  float *lr_buf_ = nullptr;     // page-locked; disparity_lr is a header over it
+  size_t lr_cap_ = 0;
   std::string error_;
 };
 

@@ -93,7 +93,14 @@ void b200sgm_reproject_from_camera(b200sgm_reproject *rp, const double *K_l, con
  * Allocates all device memory for images up to max_width x max_height and max_disparities up front so
  * that later calls do not allocate.  `lanes` >= 1 is the number of frames that may be in flight. */
 int b200sgm_create(int device, int max_width, int max_height, int max_disparities, int lanes, b200sgm_handle *out);
+/* Same for an engine that only ever runs the block matcher (b200sgm_bm_*) and rectification: no aggregated-cost volume,
+ * checkpoints or exchange records (about half the memory).  The SGBM entry points fail with B200SGM_ESTATE on it. */
+int b200sgm_create_bm(int device, int max_width, int max_height, int max_disparities, int lanes, b200sgm_handle *out);
 int b200sgm_destroy(b200sgm_handle h);
+/* Page-locked host memory for the buffers a caller hands to the host-pointer entry points (what makes b200sgm_enqueue
+ * asynchronous and the synchronous calls copy at full PCIe rate); a matcher keeps its result Mat in such a buffer. */
+int b200sgm_host_alloc(size_t bytes, void **ptr);
+int b200sgm_host_free(void *ptr);
 
 /* Replaces the 12 setters pushed by updateMatcher() (generate_disparity.cpp:241-261). Cheap, lazy: only
  * stores and validates; takes effect on the next compute/enqueue. */
@@ -170,6 +177,10 @@ int b200sgm_rectify_maps(b200sgm_handle h, int cam, int width, int height, float
 typedef struct b200sgm_bm_params {
     int minDisparity, numDisparities, blockSize, preFilterCap, textureThreshold, uniquenessRatio, speckleWindowSize,
         speckleRange, disp12MaxDiff;
+    /* setPreFilterSize (matcherOpenCVBlock.cpp; pushed by generate_disparity.cpp:255).  PREFILTER_XSOBEL never reads it, but
+     * cv::StereoBM::compute rejects values outside 5..255 or even ones all the same, and so does this engine; 0 = OpenCV's
+     * default (9). */
+    int preFilterSize;
 } b200sgm_bm_params;
 
 /* matcher->compute(*left, *right, disparity_lr) of MatcherOpenCVBlock::forwardMatch (matcherOpenCVBlock.cpp:20): CV_8UC1 host
@@ -179,6 +190,12 @@ typedef struct b200sgm_bm_params {
 int b200sgm_bm_compute(b200sgm_handle h, const b200sgm_bm_params *p, const uint8_t *left, size_t left_stride,
                        const uint8_t *right, size_t right_stride, int width, int height, int16_t *disp,
                        size_t disp_stride);
+
+/* Same, but the result is what MatcherOpenCVBlock::forwardMatch leaves in disparity_lr: CV_32FC1 holding the same x16 value
+ * (disparity_lr.convertTo(disparity_lr, CV_32FC1), matcherOpenCVBlock.cpp:34), converted on the device. */
+int b200sgm_bm_compute_f32(b200sgm_handle h, const b200sgm_bm_params *p, const uint8_t *left, size_t left_stride,
+                           const uint8_t *right, size_t right_stride, int width, int height, float *disp32,
+                           size_t disp_stride);
 
 /* Device-resident variant, enqueued on `cuda_stream` (or the stream of lane `lane` when NULL), not synchronised. */
 int b200sgm_bm_compute_device(b200sgm_handle h, int lane, const b200sgm_bm_params *p, const uint8_t *d_left,
