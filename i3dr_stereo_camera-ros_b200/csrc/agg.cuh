@@ -39,25 +39,43 @@ struct VertPlan { bool ok; int nstrips, twmax; size_t smem; };
 // thread; beyond that a row is at least twice the bytes, so half the depth hides the same DRAM latency, and fewer, fatter
 // threads keep the N = 8 row loop out of local memory.
 template <int N> struct VertCfg { static constexpr int RING = N >= 8 ? 4 : 8, MAXT = vert_max_threads(N); };
+// development switch: B200SGM_VERT_RING=4 halves the ring depth of the N <= 4 instantiations
+inline int vert_ring(int n_regs)
+{
+    static const int env = [] { const char* v = getenv("B200SGM_VERT_RING"); return v ? atoi(v) : 0; }();
+    return n_regs >= 8 ? 4 : (env == 4 ? 4 : 8);
+}
+// threads of a sweep with `tw` columns per strip: one path warp per column, one WTA warp per kWC columns
+inline int vert_threads(int tw, bool do_wta) { return 32 * (tw + (do_wta ? (tw + kWC - 1) / kWC : 0)); }
 
 template <int N>
 inline VertPlan plan_vert(const b200sgm_engine* h, const Eff& e)
 {
     VertPlan p{false, 0, 0, 0};
     if (e.W1 < 2) return p;
-    int n = std::min(h->num_sms, e.W1 / 2);
-    n = std::min(n, kMaxStrips);
+    // widest strip a CTA can take: threads (a path warp per column, a WTA warp per kWC columns, two agents) and shared memory
+    int twcap = kVertMaxWarps;
+    while (twcap > 1 && (vert_threads(twcap, true) + 64 > VertCfg<N>::MAXT || vert_smem_bytes(twcap, e.Dp, vert_ring(N)) > size_t(h->max_smem_optin))) twcap--;
+    // K = sweeps of this geometry that fit the GPU side by side; each gets num_sms / K strips (K = 1: one strip per SM)
+    const int nmin = (e.W1 + twcap - 1) / twcap;
+    // (an engine with a single lane never has two frames in flight: it spreads every sweep over all SMs, which is 10 % faster
+    // for a frame on its own; B200SGM_VERT_ALL_SMS forces that for measurements)
+    static const bool wide_env = getenv("B200SGM_VERT_ALL_SMS") != nullptr;
+    const bool wide = wide_env || h->lanes.size() < 2;
+    const int K = wide ? 1 : std::max(1, h->num_sms / std::max(1, nmin));
+    int n = std::min(h->num_sms / K, e.W1 / 2);
+    n = std::max(1, std::min(n, kMaxStrips));
     int tw = (e.W1 + n - 1) / n;
     // wider than one co-resident wave of strips (or than a CTA has warps): use the hybrid path
-    if (tw > kVertMaxWarps || 64 * tw > VertCfg<N>::MAXT) return p;
+    if (tw > kVertMaxWarps || vert_threads(tw, true) > VertCfg<N>::MAXT) return p;
     p.nstrips = n; p.twmax = tw;
-    p.smem = vert_smem_bytes(tw, e.Dp, VertCfg<N>::RING);
+    p.smem = vert_smem_bytes(tw, e.Dp, vert_ring(N));
     p.ok = p.smem <= size_t(h->max_smem_optin);
     return p;
 }
 
-template <int N, bool UP, bool DO_WTA, bool FULL, bool CLAMP_EACH>
-int launch_vert_t(b200sgm_engine* h, Lane& ln, const Eff& e, const VertPlan& vp, cudaStream_t st)
+template <int N, int RING, bool UP, bool DO_WTA, bool FULL, bool CLAMP_EACH>
+int launch_vert_r(b200sgm_engine* h, Lane& ln, const Eff& e, const VertPlan& vp, cudaStream_t st)
 {
     VertGeom g;
     g.w = WtaGeom{e.W, e.H, e.W1, e.minX1, e.minD, e.D, e.Dp, e.uniq, e.d12, e.INVALID};
@@ -66,15 +84,17 @@ int launch_vert_t(b200sgm_engine* h, Lane& ln, const Eff& e, const VertPlan& vp,
     g.spin_limit = (long long)h->clock_khz * 500;   // ~0.5 s of SM clock ticks
     { static const int dbg = [] { const char* v = getenv("B200SGM_DEBUG_VERT"); return v ? atoi(v) : 0; }(); g.debug_flags = dbg; }
     // two agent warps per CTA when they fit next to the column warps (1024 threads per CTA)
-    int nthreads = (DO_WTA ? 64 : 32) * vp.twmax;
+    int nthreads = vert_threads(vp.twmax, DO_WTA);
     { static const bool no_agents = getenv("B200SGM_NO_AGENTS") != nullptr; g.agents = (!no_agents && nthreads + 64 <= VertCfg<N>::MAXT) ? 1 : 0; }
     if (g.agents) nthreads += 64;
-    auto kern = k_vert<N, VertCfg<N>::RING, UP, DO_WTA, FULL, CLAMP_EACH>;
+    auto kern = k_vert<N, RING, UP, DO_WTA, FULL, CLAMP_EACH>;
     {
         static std::atomic<unsigned long long> attr_done{0};   // per instantiation and device: raise the dynamic shared-memory limit once
         const unsigned long long bit = 1ull << (h->device & 63);
         if (!(attr_done.load() & bit)) {
             CUDA_TRY(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_smem_optin));
+            // largest shared-memory carve-out, so that what this sweep leaves free can hold CTAs of another frame's kernels
+            CUDA_TRY(h, cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
             attr_done.fetch_or(bit);
         }
     }
@@ -85,18 +105,41 @@ int launch_vert_t(b200sgm_engine* h, Lane& ln, const Eff& e, const VertPlan& vp,
     {
         CoopGate& gate = coop_gate(h->device);
         std::lock_guard<std::mutex> lk(gate.mu);
-        if (!gate.ev[0]) {
-            CUDA_TRY(h, cudaEventCreateWithFlags(&gate.ev[0], cudaEventDisableTiming));
-            CUDA_TRY(h, cudaEventCreateWithFlags(&gate.ev[1], cudaEventDisableTiming));
+        if (!gate.ev[0])
+            for (auto& ev : gate.ev) CUDA_TRY(h, cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+        static const int kmax = [] { const char* v = getenv("B200SGM_VERT_CONCURRENT"); return v ? std::max(1, atoi(v)) : CoopGate::kRing - 1; }();
+        const int K = std::max(1, std::min(std::min(h->num_sms / vp.nstrips, CoopGate::kRing - 1), kmax));
+        const unsigned long long i = gate.count;
+        if (vp.nstrips != gate.last_n) {
+            for (unsigned long long q = i > CoopGate::kRing ? i - CoopGate::kRing : 0; q < i; q++)
+                CUDA_TRY(h, cudaStreamWaitEvent(st, gate.ev[q % CoopGate::kRing], 0));
+        } else if (i >= (unsigned long long)K) {
+            CUDA_TRY(h, cudaStreamWaitEvent(st, gate.ev[(i - K) % CoopGate::kRing], 0));
         }
-        if (gate.any) CUDA_TRY(h, cudaStreamWaitEvent(st, gate.ev[gate.idx], 0));
-        CUDA_TRY(h, cudaLaunchCooperativeKernel((void*)kern, dim3(vp.nstrips), dim3(nthreads), args, vp.smem, st));
+        // The sweep only needs its strips co-resident (no grid-wide barrier).  A plain launch gets that as well -- the gate bounds
+        // the sweeps in flight and no other kernel of the engine waits on anything.
+        static const bool plain = [] { const char* v = getenv("B200SGM_VERT_PLAIN"); return v && atoi(v) != 0; }();
+        if (plain) {
+            kern<<<dim3(vp.nstrips), dim3(nthreads), vp.smem, st>>>(Cp, Sp, g, dp, kp, xb, er);
+            CUDA_TRY(h, cudaGetLastError());
+        } else {
+            CUDA_TRY(h, cudaLaunchCooperativeKernel((void*)kern, dim3(vp.nstrips), dim3(nthreads), args, vp.smem, st));
+        }
         h->launches++;
-        gate.idx ^= 1;
-        CUDA_TRY(h, cudaEventRecord(gate.ev[gate.idx], st));
-        gate.any = true;
+        CUDA_TRY(h, cudaEventRecord(gate.ev[i % CoopGate::kRing], st));
+        gate.count = i + 1;
+        gate.last_n = vp.nstrips;
     }
     return B200SGM_OK;
+}
+
+template <int N, bool UP, bool DO_WTA, bool FULL, bool CLAMP_EACH>
+int launch_vert_t(b200sgm_engine* h, Lane& ln, const Eff& e, const VertPlan& vp, cudaStream_t st)
+{
+    if constexpr (N <= 4) {
+        if (vert_ring(N) == 4) return launch_vert_r<N, 4, UP, DO_WTA, FULL, CLAMP_EACH>(h, ln, e, vp, st);
+    }
+    return launch_vert_r<N, VertCfg<N>::RING, UP, DO_WTA, FULL, CLAMP_EACH>(h, ln, e, vp, st);
 }
 
 template <int N, bool UP, bool DO_WTA>
@@ -116,14 +159,15 @@ int launch_vert(b200sgm_engine* h, Lane& ln, const Eff& e, const VertPlan& vp, c
     return launch_vert_t<N, UP, DO_WTA, false, true>(h, ln, e, vp, st);
 }
 
+// part: 0 = horizontal pair + vertical sweep(s) (a frame), 1 = horizontal pair only, 2 = vertical sweep(s) only
 template <int N>
-int launch_fused(b200sgm_engine* h, Lane& ln, const Eff& e, cudaStream_t st, bool hybrid)
+int launch_fused(b200sgm_engine* h, Lane& ln, const Eff& e, cudaStream_t st, bool hybrid, int part)
 {
     int wpb = 2;
     while (wpb > 1 && size_t(wpb) * horiz_smem_per_warp(e.Dp) > 200 * 1024) wpb /= 2;
     const size_t hsmem = size_t(wpb) * horiz_smem_per_warp(e.Dp);
     if (hsmem > 200 * 1024) return fail(h, B200SGM_EINVAL, "numDisparities too large for the horizontal kernel");
-    {
+    if (part != 2) {
         const bool full = e.Dp == 64 * N;
         const long long bs = 2 * e.SW2 + 1;
         const bool clamp = !full || 2 * (bs * bs * (2 * e.ftzero + 63) + e.P2) > 65535;
@@ -133,13 +177,15 @@ int launch_fused(b200sgm_engine* h, Lane& ln, const Eff& e, cudaStream_t st, boo
         const unsigned long long bit = 1ull << (h->device & 63);
         if (!(attr_done[ki].load() & bit)) {
             CUDA_TRY(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+            CUDA_TRY(h, cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
             attr_done[ki].fetch_or(bit);
         }
         kern<<<(e.H + wpb - 1) / wpb, 32 * wpb, hsmem, st>>>(ln.C, ln.S, ln.ckpt, e.W1, e.H, e.Dp, e.D, e.P1, e.P2,
                                                               reinterpret_cast<unsigned*>(ln.d_err) + 3);
         LAUNCH_CHECK(h);
     }
-    prof_mark(h, ln, 3, st);
+    if (part == 0) prof_mark(h, ln, 3, st);
+    if (part == 1) return B200SGM_OK;
     const VertPlan vp = plan_vert<N>(h, e);
     if (hybrid || !vp.ok) {
         static const int dirs_sgbm[3][2] = {{1, 1}, {0, 1}, {-1, 1}};
@@ -173,9 +219,9 @@ int launch_fused(b200sgm_engine* h, Lane& ln, const Eff& e, cudaStream_t st, boo
 }
 
 template <int N>
-int launch_agg_n(b200sgm_engine* h, Lane& ln, const Eff& e, cudaStream_t st)
+int launch_agg_n(b200sgm_engine* h, Lane& ln, const Eff& e, cudaStream_t st, int part)
 {
     if (h->path == 1) { prof_mark(h, ln, 3, st); return launch_paths_generic<N>(h, ln, e, st); }
-    return launch_fused<N>(h, ln, e, st, h->path == 2);
+    return launch_fused<N>(h, ln, e, st, h->path == 2, part);
 }
 

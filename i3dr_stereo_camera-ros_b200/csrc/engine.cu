@@ -62,15 +62,15 @@ int make_eff(b200sgm_engine* h, int W, int H, Eff& e)
     return B200SGM_OK;
 }
 
-int launch_aggregation(b200sgm_engine* h, Lane& ln, const Eff& e, cudaStream_t st)
+int launch_aggregation(b200sgm_engine* h, Lane& ln, const Eff& e, cudaStream_t st, int part = 0)
 {
     switch (e.nreg) {
-        case 1: return launch_agg_n<1>(h, ln, e, st);
-        case 2: return launch_agg_n<2>(h, ln, e, st);
-        case 4: return launch_agg_n<4>(h, ln, e, st);
-        case 8: return launch_agg_n<8>(h, ln, e, st);
-        case 16: return launch_agg_n<16>(h, ln, e, st);
-        case 32: return launch_agg_n<32>(h, ln, e, st);
+        case 1: return launch_agg_n<1>(h, ln, e, st, part);
+        case 2: return launch_agg_n<2>(h, ln, e, st, part);
+        case 4: return launch_agg_n<4>(h, ln, e, st, part);
+        case 8: return launch_agg_n<8>(h, ln, e, st, part);
+        case 16: return launch_agg_n<16>(h, ln, e, st, part);
+        case 32: return launch_agg_n<32>(h, ln, e, st, part);
     }
     return fail(h, B200SGM_EINVAL, "bad nreg");
 }
@@ -740,6 +740,56 @@ int b200sgm_debug_read(b200sgm_handle h, int lane, const char* what, void* host,
             }
         }
     }
+    return B200SGM_OK;
+}
+
+// Development probe: how long do stages of two different frames take when they share the GPU?  Lanes 0 and 1 must each have
+// processed a frame of this size (their volumes are reused as they are; results are not meaningful).  `mask_a` runs on
+// lane 0's stream, `mask_b` on lane 1's, concurrently; bit 0 = cost, bit 1 = horizontal pair, bit 2 = vertical sweep + WTA.
+// Returns the mean milliseconds from the common start to the completion of both.
+int b200sgm_debug_overlap(b200sgm_handle h, int width, int height, int mask_a, int mask_b, int iters, float* ms_out)
+{
+    if (!h || !ms_out || h->lanes.size() < 2 || iters <= 0) return B200SGM_EINVAL;
+    Eff e;
+    int rc = make_eff(h, width, height, e);
+    if (rc) return rc;
+    if (e.W1 <= 0) return B200SGM_EINVAL;
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    cudaEvent_t e0, e1, e2, ea;
+    CUDA_TRY(h, cudaEventCreate(&e0)); CUDA_TRY(h, cudaEventCreate(&e1)); CUDA_TRY(h, cudaEventCreate(&e2)); CUDA_TRY(h, cudaEventCreate(&ea));
+    double ta = 0, tb = 0;
+    auto run = [&](Lane& ln, int mask) -> int {
+        if (mask & 1) {
+            const char* msg = nullptr; int nl = 0;
+            if (launch_cost(ln.feat_l, ln.feat_r, ln.C, e, false, h->num_sms, ln.stream, &nl, &msg) != cudaSuccess || msg) return B200SGM_ECUDA;
+        }
+        if (mask & 2) { int r2 = launch_aggregation(h, ln, e, ln.stream, 1); if (r2) return r2; }
+        if (mask & 4) { int r2 = launch_aggregation(h, ln, e, ln.stream, 2); if (r2) return r2; }
+        return B200SGM_OK;
+    };
+    Lane &a = h->lanes[0], &b = h->lanes[1];
+    double total = 0;
+    for (int i = 0; i < iters + 1; i++) {
+        CUDA_TRY(h, cudaEventRecord(e0, a.stream));
+        CUDA_TRY(h, cudaStreamWaitEvent(b.stream, e0, 0));
+        if ((rc = run(a, mask_a))) return rc;
+        CUDA_TRY(h, cudaEventRecord(ea, a.stream));
+        if ((rc = run(b, mask_b))) return rc;
+        CUDA_TRY(h, cudaEventRecord(e1, b.stream));
+        CUDA_TRY(h, cudaStreamWaitEvent(a.stream, e1, 0));
+        CUDA_TRY(h, cudaEventRecord(e2, a.stream));
+        CUDA_TRY(h, cudaStreamSynchronize(a.stream));
+        float ms = 0;
+        CUDA_TRY(h, cudaEventElapsedTime(&ms, e0, e2));
+        if (i > 0) total += ms;     // first round is a warm-up
+        float fa = 0, fb = 0;
+        cudaEventElapsedTime(&fa, e0, ea); cudaEventElapsedTime(&fb, e0, e1);
+        if (i > 0) { ta += fa; tb += fb; }
+    }
+    if (getenv("B200SGM_DEBUG_OVERLAP")) fprintf(stderr, "overlap: lane 0 done at %.3f ms, lane 1 done at %.3f ms\n", ta / iters, tb / iters);
+    cudaEventDestroy(ea);
+    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaEventDestroy(e2);
+    *ms_out = float(total / iters);
     return B200SGM_OK;
 }
 

@@ -53,15 +53,19 @@ constexpr int kProfRing = 256;
 constexpr int kMaxStrips = 320;
 constexpr int kStatusWords = 4;
 
-// Cooperative sweeps of ALL engines of a process on one device are serialised: one sweep fills every SM, and two
-// partially resident sweeps would spin on CTAs that can never be scheduled.  Process-wide, keyed by device; the events
-// are never destroyed (they outlive any engine).  coop_serialise() makes `st` wait for the previous sweep on `device`;
-// coop_published() records the sweep just launched on `st`.  Hold the returned lock across both calls.
+// Vertical sweeps of ALL engines of a process on one device share the SMs under this gate: the CTAs of a sweep spin on
+// their neighbours, so every sweep in flight must be fully resident.  A sweep of n strips takes n SMs (one CTA fills an
+// SM's register file); sweeps of narrow images use a fraction of the SMs, and floor(num_sms / n) of them -- of different
+// frames -- may run side by side.  Sweep i waits for sweep i - K (hence for every older one of its residue class, and by
+// induction at most K are ever running); a sweep whose n differs from its predecessor's waits for all of them.
+// Process-wide, keyed by device; the events are never destroyed (they outlive any engine).  Hold `mu` across the wait,
+// the launch and the record.
 struct CoopGate {
+    static constexpr int kRing = 16;
     std::mutex mu;
-    cudaEvent_t ev[2] = {nullptr, nullptr};
-    int idx = 0;
-    bool any = false;
+    cudaEvent_t ev[kRing] = {};
+    unsigned long long count = 0;     // sweeps launched so far; sweep i records ev[i % kRing]
+    int last_n = 0;
 };
 CoopGate& coop_gate(int device);
 constexpr int kVertMaxWarps = 16;
@@ -131,4 +135,4 @@ inline int fail(b200sgm_engine* h, int code, const std::string& msg)
 
 // Aggregation + WTA stages for N packed registers per lane (D <= 64 * N); one explicit instantiation per agg_n*.cu.
 template <int N>
-int launch_agg_n(b200sgm_engine* h, Lane& ln, const Eff& e, cudaStream_t st);
+int launch_agg_n(b200sgm_engine* h, Lane& ln, const Eff& e, cudaStream_t st, int part);

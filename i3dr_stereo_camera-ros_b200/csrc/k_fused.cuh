@@ -233,6 +233,7 @@ __global__ void __launch_bounds__(64) k_horiz(const uint16_t* __restrict__ Cvol,
 // each stalling the warp for its full latency.  Staged vectors must hold 0xFFFF in cells >= D.
 // ------------------------------------------------------------------------------------------------
 constexpr int kWB = 2;
+constexpr int kWC = 2;        // columns per WTA warp of the vertical sweep (its path warps own one column each)
 struct WtaCtx {
     uint32_t kk0;        // (lane*N) | (lane*N + Dh) << 16 : disparity indices of this lane's first word
     uint32_t umagic;     // floor(2^32 / f) + 1 with f = 100 - uniq > 0
@@ -404,7 +405,13 @@ constexpr int kXbufGen = 4;
 // RING (template parameter of k_vert) = rows of C and of S_h in flight per column (cp.async rings in shared memory): DRAM latency x
 // row rate.  The two rings have the same depth -- cp.async groups retire in order, so a shallower S_h ring would make its wait
 // drain the younger C requests as well.  8 up to 256 disparities, 4 beyond (a row is then at least twice the bytes).
-constexpr int vert_max_threads(int n) { return n <= 4 ? 1024 : 896; }   // 64 registers per thread, 72 for the N >= 8 instantiations
+// 64 registers per thread up to 256 disparities, 72 for the N >= 8 instantiations.  (A sweep never has more than 16 + 8 + 2
+// warps; bounding the N <= 4 kernels by those 832 threads lets ptxas use 72 registers and removes the last spills, but the
+// row loop gets slower: 1.62 instead of 1.55 ms at c3 -- measured, kept at 64.)
+#ifndef B200SGM_VERT_MAXT
+#define B200SGM_VERT_MAXT 1024
+#endif
+constexpr int vert_max_threads(int n) { return n <= 4 ? B200SGM_VERT_MAXT : 896; }
 constexpr int kRowUnroll = 4; // the row loop is unrolled by this: record generation, stage slot, parity are immediates
 __device__ __forceinline__ uint2* xrec(uint2* xbuf, int nstrips, int Dp, int side, int strip, int row)
 {
@@ -471,7 +478,9 @@ __global__ void __launch_bounds__(vert_max_threads(N), 1) k_vert(const uint16_t*
         for (int i = threadIdx.x; i < nz; i += blockDim.x) z[i] = 0;
     }
     __syncthreads();
-    const int agent_base = DO_WTA ? 2 * g.twmax : g.twmax;
+    const int wta_warps = DO_WTA ? (g.twmax + kWC - 1) / kWC : 0;      // launched; (TW + kWC - 1) / kWC of them have columns
+    const int agent_base = g.twmax + wta_warps;
+    const int TWW = DO_WTA ? (TW + kWC - 1) / kWC : 0;
     const bool exchange_on = !(g.debug_flags & 1);
     const LaneCtx lc = make_lane_ctx<N>(lane, Dp, g.P1, g.P2);
     const bool active = FULL || lc.active;
@@ -490,7 +499,7 @@ __global__ void __launch_bounds__(vert_max_threads(N), 1) k_vert(const uint16_t*
             // the inner neighbour column (Ld) and L for the sum (stageB, added by the column's WTA warp).  The edge path
             // warp is left with two independent steps, so the exchange latency is off every column warp's critical path.
             const int nag = (b > 0 ? 1 : 0) + (b < n - 1 ? 1 : 0);
-            const int nrow_a = 32 * (TW + nag), nfe_a = 64 * TW + 32 * nag;
+            const int nrow_a = 32 * (TW + nag), nfe_a = 32 * (TW + TWW + nag);
             const int je = side == 0 ? 0 : TW - 1;
             uint16_t* wr = Ld + side * (slots * Dp) + (je + 1) * Dp + lane * 2 * N;          // + parity * 2*slots*Dp
             const uint16_t* cring = ringbase + size_t(je) * RING * Dp + lane * 2 * N;
@@ -567,11 +576,11 @@ __global__ void __launch_bounds__(vert_max_threads(N), 1) k_vert(const uint16_t*
         return;
     }
     const bool wta_role = DO_WTA && w >= g.twmax;
-    const int j = wta_role ? w - g.twmax : w;
-    if (j >= TW) return;                 // the barriers below only count the TW column warps of each role
+    const int j = wta_role ? kWC * (w - g.twmax) : w;      // (first) column of this warp
+    if (j >= TW) return;                 // the barriers below only count the warps that own columns
     // agents of a WTA sweep take part in the row barrier and in the stage-ring hand-over
     const int nag3 = (DO_WTA && g.agents && exchange_on) ? (b > 0 ? 1 : 0) + (b < n - 1 ? 1 : 0) : 0;
-    const int nrow = 32 * (TW + nag3), nboth = 64 * TW + 32 * nag3;
+    const int nrow = 32 * (TW + nag3), nboth = 32 * (TW + TWW + nag3);
     const int x = x0 + j;
     const int lo = lane * 2 * N;
     const int ringSlot = g.twmax * Dp;                 // slot stride of the stage ring [slot][warp][Dp]
@@ -590,53 +599,72 @@ __global__ void __launch_bounds__(vert_max_threads(N), 1) k_vert(const uint16_t*
         wc.kk0 = uint32_t(lane * N) | (uint32_t(lane * N + wc.Dh) << 16);
         wc.f = 100 - g.w.uniq;
         wc.umagic = wc.f > 0 ? uint32_t((1ull << 32) / uint32_t(wc.f)) + 1u : 0u;
-        WtaAcc acc{0xFFFFFFFFu, 0u, 0, 0};
+        // this warp resolves columns j .. j + ncol - 1 (ncol <= kWC) of every parked row
+        const int ncol = min(kWC, TW - j);
+        WtaAcc acc[kWC];
+        int edge_side[kWC];
+#pragma unroll
+        for (int c = 0; c < kWC; c++) {
+            acc[c] = WtaAcc{0xFFFFFFFFu, 0u, 0, 0};
+            const int jc = j + c;
+            edge_side[c] = nag3 == 0 ? -1 : ((jc == 0 && b > 0) ? 0 : ((jc == TW - 1 && jc != 0 && b < n - 1) ? 1 : -1));
+        }
         int pending = 0;                    // rows parked in acc
-        const int edge_side = nag3 == 0 ? -1 : ((j == 0 && b > 0) ? 0 : ((j == TW - 1 && j != 0 && b < n - 1) ? 1 : -1));
         // one batch of kWB (= 2) parked rows starting at row r; Q0 = r & 3 is an immediate so that the barrier ids are
         auto batch = [&](auto q0_tag, int r, int cnt) {
             constexpr int Q0 = decltype(q0_tag)::value;
             named_bar_sync(BAR_FULL + Q0, nboth);
             if (cnt > 1) named_bar_sync(BAR_FULL + Q0 + 1, nboth);
-            uint16_t* sc = stage + Q0 * ringSlot;
-            if (edge_side >= 0) {
-                // edge column: the agent computed the incoming-diagonal path; add its L to the parked partial sum
-                const uint16_t* sB = xringbase + size_t(edge_side) * kStage * Dp + lane * 2 * N;
 #pragma unroll
-                for (int q = 0; q < kWB; q++) {
-                    if (q < cnt && active) {
-                        uint32_t P[N], B[N];
-                        ld_regs<N>(sc + q * ringSlot + lane * 2 * N, P);
-                        ld_regs<N>(sB + (Q0 + q) * Dp, B);
+            for (int c = 0; c < kWC; c++) {
+                if (c >= ncol) break;
+                uint16_t* sc = stage + c * Dp + Q0 * ringSlot;
+                if (edge_side[c] >= 0) {
+                    // edge column: the agent computed the incoming-diagonal path; add its L to the parked partial sum
+                    const uint16_t* sB = xringbase + size_t(edge_side[c]) * kStage * Dp + lane * 2 * N;
 #pragma unroll
-                        for (int i = 0; i < N; i++) {
-                            P[i] = __vminu2(P[i] + B[i], kMaxCostX2);
-                            if (!FULL) {
-                                const int k = lane * N + i;
-                                if (k >= g.w.D) P[i] = 0xFFFFFFFFu;
-                                else if (k + wc.Dh >= g.w.D) P[i] |= 0xFFFF0000u;
+                    for (int q = 0; q < kWB; q++) {
+                        if (q < cnt && active) {
+                            uint32_t P[N], B[N];
+                            ld_regs<N>(sc + q * ringSlot + lane * 2 * N, P);
+                            ld_regs<N>(sB + (Q0 + q) * Dp, B);
+#pragma unroll
+                            for (int i = 0; i < N; i++) {
+                                P[i] = __vminu2(P[i] + B[i], kMaxCostX2);
+                                if (!FULL) {
+                                    const int k = lane * N + i;
+                                    if (k >= g.w.D) P[i] = 0xFFFFFFFFu;
+                                    else if (k + wc.Dh >= g.w.D) P[i] |= 0xFFFF0000u;
+                                }
                             }
+                            st_regs<N>(sc + q * ringSlot + lane * 2 * N, P);
                         }
-                        st_regs<N>(sc + q * ringSlot + lane * 2 * N, P);
+                    }
+                }
+                if (wta_on) {
+                    if (wc.f > 0) {
+                        wta_vec<N>(sc, ringSlot, r, g.w, wc, lane, active, acc[c]);   // a row past the end lands in a lane >= cnt of the flush
+                    } else {
+                        __syncwarp();
+                        for (int q = 0; q < cnt; q++) {
+                            const int d = wta_slow<N>(sc + q * ringSlot, g.w, wc, x + c, lane, active, kptr + q * dStride);
+                            if (lane == 0) dptr[q * dStride + c] = int16_t(d);
+                        }
+                        __syncwarp();
                     }
                 }
             }
             if (wta_on) {
                 if (wc.f > 0) {
-                    wta_vec<N>(sc, ringSlot, r, g.w, wc, lane, active, acc);   // a row past the end lands in a lane >= cnt of the flush
                     pending += cnt;
                     if (((r + kWB) & 31) == 0 || r + kWB >= H) {
-                        wta_flush32(acc, pending, g.w, wc, x, lane, dptr, kptr, dStride);
+#pragma unroll
+                        for (int c = 0; c < kWC; c++)
+                            if (c < ncol) wta_flush32(acc[c], pending, g.w, wc, x + c, lane, dptr + c, kptr, dStride);
                         dptr += pending * dStride; kptr += pending * dStride;
                         pending = 0;
                     }
                 } else {
-                    __syncwarp();
-                    for (int q = 0; q < cnt; q++) {
-                        const int d = wta_slow<N>(sc + q * ringSlot, g.w, wc, x, lane, active, kptr + q * dStride);
-                        if (lane == 0) dptr[q * dStride] = int16_t(d);
-                    }
-                    __syncwarp();
                     dptr += cnt * dStride; kptr += cnt * dStride;
                 }
             }

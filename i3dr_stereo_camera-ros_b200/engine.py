@@ -20,7 +20,7 @@ SYMBOLS = (
     "b200sgm_create", "b200sgm_destroy", "b200sgm_set_params", "b200sgm_get_effective_params", "b200sgm_compute",
     "b200sgm_compute_f32", "b200sgm_compute_device", "b200sgm_enqueue", "b200sgm_wait", "b200sgm_compute_xyz",
     "b200sgm_last_error", "b200sgm_version", "b200sgm_launch_count", "b200sgm_lane_stream", "b200sgm_debug_read",
-    "b200sgm_debug_set_path", "b200sgm_profile", "b200sgm_stage_times", "b200sgm_alu_peak", "b200sgm_stage_timeline",
+    "b200sgm_debug_set_path", "b200sgm_debug_overlap", "b200sgm_profile", "b200sgm_stage_times", "b200sgm_alu_peak", "b200sgm_stage_timeline",
     "b200sgm_set_camera", "b200sgm_rectify", "b200sgm_rectify_device", "b200sgm_rectify_maps", "b200sgm_bm_compute",
     "b200sgm_bm_compute_device", "b200sgm_lane_status", "b200sgm_reproject_from_camera",
     "b200sgm_create_bm", "b200sgm_host_alloc", "b200sgm_host_free", "b200sgm_bm_compute_f32",

@@ -230,6 +230,10 @@ int b200sgm_alu_peak(int device, double tera_ops[3]);
 int b200sgm_debug_read(b200sgm_handle h, int lane, const char *what, void *host, size_t bytes, int *dp);
 /* Selects the kernel path: 0 = default (fastest validated), 1 = generic per-direction chains. Tests only. */
 int b200sgm_debug_set_path(b200sgm_handle h, int path);
+/* Development probe (tools/overlap_probe.py): mean milliseconds for stage set `mask_a` on lane 0 and `mask_b` on lane 1
+ * (bit 0 cost, bit 1 horizontal pair, bit 2 vertical sweep + WTA) launched together on their two streams.  Both lanes
+ * must have processed a frame of this size; the volumes are reused as they are and the results are meaningless. */
+int b200sgm_debug_overlap(b200sgm_handle h, int width, int height, int mask_a, int mask_b, int iters, float *ms_out);
 
 #ifdef __cplusplus
 }
