@@ -140,7 +140,7 @@ class Engine:
                                                  W, H, out.ctypes.data_as(ctypes.c_void_p), ctypes.c_size_t(W * 4)))
         return out
 
-    def compute_xyz(self, left, right, q, depth_min, depth_max, min_disparity, max_disparity, want_points=True, color=None):
+    def compute_xyz(self, left, right, q, depth_min, depth_max, min_disparity, max_disparity, want_points=True, color=None, out=None):
         """Matching + processDisparity + reprojection.  `color`: None (the left image, MONO8), (H, W) uint8 or (H, W, 3) BGR8."""
         L, R = _u8(left), _u8(right)
         H, W = L.shape
@@ -153,10 +153,15 @@ class Engine:
             rp.color = color.ctypes.data
             rp.color_stride = color.strides[0]
             rp.color_channels = 1 if color.ndim == 2 else 3
-        disp = np.empty((H, W), np.int16)
-        dmat = np.empty((H, W), np.float32)
-        depth = np.empty((H, W), np.float32)
-        pts = np.empty((H * W, 4), np.float32) if want_points else None
+        if out is None:
+            disp = np.empty((H, W), np.int16)
+            dmat = np.empty((H, W), np.float32)
+            depth = np.empty((H, W), np.float32)
+            pts = np.empty((H * W, 4), np.float32) if want_points else None
+        else:
+            disp, dmat, depth, pts = out      # caller-owned (e.g. page-locked) arrays of exactly these shapes and dtypes
+            assert disp.dtype == np.int16 and dmat.dtype == np.float32 and depth.dtype == np.float32 and disp.shape == (H, W)
+            assert pts is None or (pts.dtype == np.float32 and pts.shape == (H * W, 4))
         cnt = ctypes.c_uint32(0)
         self._check(self.lib.b200sgm_compute_xyz(
             self.h, L.ctypes.data_as(ctypes.c_void_p), ctypes.c_size_t(L.strides[0]), R.ctypes.data_as(ctypes.c_void_p),
