@@ -11,7 +11,10 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-LIB = os.path.join(HERE, "libb200sgm.so")
+# development aid: B200SGM_VARIANT=<name> B200SGM_CFLAGS="-D..." builds libb200sgm_<name>.so beside the product library
+# (objects under csrc/_obj_<name>); B200SGM_LIB=<path> makes engine.py load it instead
+VARIANT = os.environ.get("B200SGM_VARIANT", "")
+LIB = os.path.join(HERE, "libb200sgm%s.so" % ("_" + VARIANT if VARIANT else ""))
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
          "-Xcompiler", "-fPIC", "-shared", "--use_fast_math"]
@@ -24,7 +27,7 @@ def sources():
     return [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC)) if f.endswith(".cu")]
 
 
-OBJ = os.path.join(CSRC, "_obj")
+OBJ = os.path.join(CSRC, "_obj" + ("_" + VARIANT if VARIANT else ""))
 
 
 def _stale(target: str, deps) -> bool:
@@ -50,7 +53,7 @@ def _deps(src: str, seen=None):
 def build(force: bool = False, verbose: bool = False) -> str:
     """Compiles every csrc/*.cu to its own object (in parallel, only the stale ones) and links libb200sgm.so."""
     os.makedirs(OBJ, exist_ok=True)
-    cflags = [f for f in FLAGS if f != "-shared"]
+    cflags = [f for f in FLAGS if f != "-shared"] + os.environ.get("B200SGM_CFLAGS", "").split()
     procs, objs = [], []
     for src in sources():
         obj = os.path.join(OBJ, os.path.basename(src)[:-3] + ".o")

@@ -53,24 +53,27 @@ inline VertPlan plan_vert(const b200sgm_engine* h, const Eff& e)
 {
     VertPlan p{false, 0, 0, 0};
     if (e.W1 < 2) return p;
+    if (kVertTma && e.Dp % 8 != 0) return p;      // bulk copies move multiples of 16 bytes: odd paddings take the hybrid path
     // widest strip a CTA can take: threads (a path warp per column, a WTA warp per kWC columns, two agents) and shared memory
     int twcap = kVertMaxWarps;
-    while (twcap > 1 && (vert_threads(twcap, true) + 64 > VertCfg<N>::MAXT || vert_smem_bytes(twcap, e.Dp, vert_ring(N)) > size_t(h->max_smem_optin))) twcap--;
+    const size_t smem_cap = kVertCps == 1 ? size_t(h->max_smem_optin) : (size_t(h->max_smem_sm) / kVertCps - 1024);
+    const int slots = h->num_sms * kVertCps;       // co-resident strips of the GPU
+    while (twcap > 1 && (vert_threads(twcap, true) + 64 > VertCfg<N>::MAXT || vert_smem_bytes(twcap, e.Dp, vert_ring(N)) > smem_cap)) twcap--;
     // K = sweeps of this geometry that fit the GPU side by side; each gets num_sms / K strips (K = 1: one strip per SM)
     const int nmin = (e.W1 + twcap - 1) / twcap;
     // (an engine with a single lane never has two frames in flight: it spreads every sweep over all SMs, which is 10 % faster
     // for a frame on its own; B200SGM_VERT_ALL_SMS forces that for measurements)
     static const bool wide_env = getenv("B200SGM_VERT_ALL_SMS") != nullptr;
     const bool wide = wide_env || h->lanes.size() < 2;
-    const int K = wide ? 1 : std::max(1, h->num_sms / std::max(1, nmin));
-    int n = std::min(h->num_sms / K, e.W1 / 2);
+    const int K = wide ? 1 : std::max(1, slots / std::max(1, nmin));
+    int n = std::min(slots / K, e.W1 / 2);
     n = std::max(1, std::min(n, kMaxStrips));
     int tw = (e.W1 + n - 1) / n;
     // wider than one co-resident wave of strips (or than a CTA has warps): use the hybrid path
     if (tw > kVertMaxWarps || vert_threads(tw, true) > VertCfg<N>::MAXT) return p;
     p.nstrips = n; p.twmax = tw;
     p.smem = vert_smem_bytes(tw, e.Dp, vert_ring(N));
-    p.ok = p.smem <= size_t(h->max_smem_optin);
+    p.ok = p.smem <= smem_cap;
     return p;
 }
 
@@ -108,7 +111,7 @@ int launch_vert_r(b200sgm_engine* h, Lane& ln, const Eff& e, const VertPlan& vp,
         if (!gate.ev[0])
             for (auto& ev : gate.ev) CUDA_TRY(h, cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
         static const int kmax = [] { const char* v = getenv("B200SGM_VERT_CONCURRENT"); return v ? std::max(1, atoi(v)) : CoopGate::kRing - 1; }();
-        const int K = std::max(1, std::min(std::min(h->num_sms / vp.nstrips, CoopGate::kRing - 1), kmax));
+        const int K = std::max(1, std::min(std::min(h->num_sms * kVertCps / vp.nstrips, CoopGate::kRing - 1), kmax));
         const unsigned long long i = gate.count;
         if (vp.nstrips != gate.last_n) {
             for (unsigned long long q = i > CoopGate::kRing ? i - CoopGate::kRing : 0; q < i; q++)

@@ -209,6 +209,7 @@ static int create_engine(int device, int max_width, int max_height, int max_disp
     cudaDeviceGetAttribute(&h->num_sms, cudaDevAttrMultiProcessorCount, device);
     cudaDeviceGetAttribute(&h->clock_khz, cudaDevAttrClockRate, device);
     cudaDeviceGetAttribute(&h->max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
+    cudaDeviceGetAttribute(&h->max_smem_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, device);
     const size_t npix = size_t(max_width) * max_height;
     const int nreg = nreg_for(max_disparities);
     const size_t Dp = size_t((max_disparities + 2 * nreg - 1) / (2 * nreg) * (2 * nreg));

@@ -85,6 +85,7 @@ struct b200sgm_engine {
     cudaEvent_t prof_ref = nullptr;   // time origin of the stage timeline
     int num_sms = 148;
     int max_smem_optin = 227 * 1024;
+    int max_smem_sm = 228 * 1024;                 // shared memory of an SM (all resident CTAs, incl. 1 KB reserved per CTA)
     int clock_khz = 1965000;
     std::mutex mu;
     // rectification (row N2): per camera (0 left, 1 right) the model and the cached fixed-point maps

@@ -44,6 +44,66 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int PENDING>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(PENDING) : "memory"); }
 
+// ---- TMA bulk copies (cp.async.bulk, completion counted in bytes on an mbarrier) ----------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return uint32_t(__cvta_generic_to_shared(p)); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_init_fence()
+{
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+// global -> shared, `bytes` a multiple of 16, both addresses 16-byte aligned
+__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try(uint64_t* bar, uint32_t parity)
+{
+    uint32_t ok;
+    asm volatile("{\n"
+                 ".reg .pred P1;\n"
+                 "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n"
+                 "selp.u32 %0, 1, 0, P1;\n"
+                 "}" : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    return ok != 0;
+}
+// Waits for the phase with the given parity to complete.  Bounded: a hand-over that never comes (a bug, or a sweep whose
+// neighbour died) raises the sweep's error word instead of hanging the GPU; every other wait then gives up within 256 tries.
+__device__ __forceinline__ void mbar_wait_b(uint64_t* bar, uint32_t parity, int* err)
+{
+    if (mbar_try(bar, parity)) return;
+    int spins = 0;
+    while (!mbar_try(bar, parity)) {
+        if ((++spins & 255) == 0 && (spins > (1 << 22) || *reinterpret_cast<volatile int*>(err))) {
+            atomicExch(err, 1);
+            break;
+        }
+    }
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
+{
+    asm volatile("{\n"
+                 ".reg .pred P1;\n"
+                 "LAB_WAIT:\n"
+                 "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+                 "@P1 bra DONE;\n"
+                 "bra LAB_WAIT;\n"
+                 "DONE:\n"
+                 "}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+
 // ------------------------------------------------------------------------------------------------
 // Horizontal pair.  Launch: one warp per row.
 // ------------------------------------------------------------------------------------------------
@@ -226,6 +286,20 @@ __global__ void __launch_bounds__(64) k_horiz(const uint16_t* __restrict__ Cvol,
     if (lane == 0 && cmx > 0) atomicMax(maxc, cmx);
 }
 
+// Per-register-count policies of the sweep, each picked by measurement on a B200 (2448x2048 unless noted; vertical stage, ms):
+//   MBAR             : the stage-ring hand-over between a WTA warp and the path warps (and agent) of ITS columns goes through one
+//                      mbarrier pair per WTA warp and slot instead of CTA-wide named barriers.  N = 8 (480 disparities): 5.27
+//                      against 6.15; N = 4 (256): 1.65 against 1.53 -- the extra try_wait / elect / arrive instructions
+//                      (+25 % on the path warps) cost more than the shorter barrier waits give back.
+//   AGENT_PREFETCH   : the agent requests the neighbour's record of row r at the END of its row r (instead of polling at the top
+//                      of row r + 1), so the L2 round trip overlaps the row barrier.  640x480x64: 0.237 against 0.261;
+//                      1280x720x128 MODE_HH: 1.130 against 1.166; N = 4: 1.556 against 1.531 (not taken there).
+//   WTA_INTERLEAVE   : both staged rows of a column go through each phase of the WTA together (N <= 4: 1.531 against 1.551);
+//                      for N >= 8 the second row's registers spill (6.15 against 5.52), so rows go one after the other.
+template <int N> struct VertPolicy {
+    static constexpr bool MBAR = N >= 8, AGENT_PREFETCH = N != 4, WTA_INTERLEAVE = N <= 4;
+};
+
 // ------------------------------------------------------------------------------------------------
 // Batched shared-memory WTA (A.6) used by the vertical sweep.  The column warp parks the summed cost of kWB
 // consecutive rows in its private staging area and then resolves the kWB pixels TOGETHER: the kWB dependency
@@ -233,6 +307,13 @@ __global__ void __launch_bounds__(64) k_horiz(const uint16_t* __restrict__ Cvol,
 // each stalling the warp for its full latency.  Staged vectors must hold 0xFFFF in cells >= D.
 // ------------------------------------------------------------------------------------------------
 constexpr int kWB = 2;
+// B200SGM_WTA_TOGETHER=1: the two columns of a WTA warp go through every phase of wta_vec together (four independent chains
+// instead of two).  Measured at c3: 1.585 ms against 1.551 ms one column after the other -- the WTA warps are not what the
+// path warps wait for (they wait for each other), and the extra live registers cost the N >= 8 instantiations spills.
+#ifndef B200SGM_WTA_TOGETHER
+#define B200SGM_WTA_TOGETHER 0
+#endif
+constexpr bool kWtaTogether = B200SGM_WTA_TOGETHER != 0;
 constexpr int kWC = 2;        // columns per WTA warp of the vertical sweep (its path warps own one column each)
 struct WtaCtx {
     uint32_t kk0;        // (lane*N) | (lane*N + Dh) << 16 : disparity indices of this lane's first word
@@ -251,59 +332,95 @@ struct WtaAcc {
     int sm, sp;      // S[best-1], S[best+1]
 };
 
-// Vector part for kWB staged rows of this column (`qs` uint16 apart); row0 = index of staged row 0 in the sweep.
-// Only the warp-wide reductions happen here; what is left per pixel is a handful of scalars, parked in lane
-// (row & 31) of `acc` and resolved for 32 rows at once by wta_flush32 (lane-parallel instead of warp-redundant).
-template <int N>
-__device__ __forceinline__ void wta_vec(uint16_t* __restrict__ scratch, int qs, int row0, const WtaGeom& g, const WtaCtx& w,
-                                        int lane, bool active, WtaAcc& acc)
+// Vector part for kWB staged rows of NC neighbouring columns (`qs` uint16 between rows, Dp between columns); row0 = index of
+// staged row 0 in the sweep.  Only the warp-wide reductions happen here; what is left per pixel is a handful of scalars, parked
+// in lane (row & 31) of `acc` and resolved for 32 rows at once by wta_flush32 (lane-parallel instead of warp-redundant).
+// The NC * kWB pixels go through every phase TOGETHER: their dependency chains (arg-min reduction -> neighbour cells ->
+// patched vector -> second reduction) are independent and each is latency bound, so the WTA warp -- the slowest stage of the
+// sweep's path-warp / WTA-warp pipeline when the columns were resolved one after the other -- overlaps them.
+// Columns >= ncol (the last warp of a strip with an odd column count) are computed on whatever the stage ring holds there and
+// dropped: their stores and their accumulators are predicated off.
+template <int N, int NC>
+__device__ __forceinline__ void wta_vec(uint16_t* __restrict__ scratch, int qs, int row0, int ncol, const WtaGeom& g, const WtaCtx& w,
+                                        int lane, bool active, WtaAcc (&acc)[NC])
 {
     const int Dp = g.Dp;
-    __syncwarp();
-    uint32_t key[kWB];
-#pragma unroll
-    for (int q = 0; q < kWB; q++) {
-        uint32_t S[N];
-        if (active) ld_regs<N>(scratch + q * qs + lane * 2 * N, S);
+    constexpr bool IL = VertPolicy<N>::WTA_INTERLEAVE;      // all reductions of a phase back to back (else one pixel at a time: fewer live registers)
+    auto load = [&](int c, int q, uint32_t (&S)[N]) {
+        if (active) ld_regs<N>(scratch + c * Dp + q * qs + lane * 2 * N, S);
         else {
 #pragma unroll
             for (int j = 0; j < N; j++) S[j] = 0xFFFFFFFFu;
         }
-        // key = S << 16 | k: the warp minimum is the smallest cost and, among equals, the FIRST disparity
-        uint32_t kq = 0xFFFFFFFFu;
+    };
+    __syncwarp();
+    uint32_t key[NC][kWB];
 #pragma unroll
-        for (int j = 0; j < N; j++) {
-            const uint32_t kk = w.kk0 + uint32_t(j) * 0x10001u;
-            kq = __vimin3_u32(kq, S[j] * 0x10000u + (kk & 0xFFFFu), __byte_perm(kk, S[j], 0x7632));
+    for (int c = 0; c < NC; c++) {
+#pragma unroll
+        for (int q = 0; q < kWB; q++) {
+            uint32_t S[N];
+            load(c, q, S);
+            // key = S << 16 | k: the warp minimum is the smallest cost and, among equals, the FIRST disparity
+            uint32_t kq = 0xFFFFFFFFu;
+#pragma unroll
+            for (int j = 0; j < N; j++) {
+                const uint32_t kk = w.kk0 + uint32_t(j) * 0x10001u;
+                kq = __vimin3_u32(kq, S[j] * 0x10000u + (kk & 0xFFFFu), __byte_perm(kk, S[j], 0x7632));
+            }
+            key[c][q] = IL ? kq : __reduce_min_sync(kFullMask, kq);
         }
-        key[q] = __reduce_min_sync(kFullMask, kq);
+    }
+    if constexpr (IL) {
+#pragma unroll
+        for (int c = 0; c < NC; c++) {
+#pragma unroll
+            for (int q = 0; q < kWB; q++) key[c][q] = __reduce_min_sync(kFullMask, key[c][q]);
+        }
     }
     // lanes 0,1,2 address cells best-1, best, best+1: lane 0 / 2 fetch the sub-pixel neighbours, then the three
     // lanes overwrite their cell with 0xFFFF (cells exempt from the uniqueness test)
     const int dl = min(lane, 2) - 1;
-    int val[kWB], cidx[kWB];
+    int val[NC][kWB], cidx[NC][kWB];
 #pragma unroll
-    for (int q = 0; q < kWB; q++) {
-        const int k = int(key[q] & 0xFFFFu) + dl;
-        cidx[q] = (k >= 0 && k < Dp) ? q * qs + cell_idx2(k, w.Dh, Dp) : -1;
-        val[q] = scratch[max(cidx[q], 0)];
+    for (int c = 0; c < NC; c++) {
+#pragma unroll
+        for (int q = 0; q < kWB; q++) {
+            const int k = int(key[c][q] & 0xFFFFu) + dl;
+            cidx[c][q] = (k >= 0 && k < Dp && c < ncol) ? c * Dp + q * qs + cell_idx2(k, w.Dh, Dp) : -1;
+            val[c][q] = scratch[max(cidx[c][q], 0)];
+        }
     }
     __syncwarp();
 #pragma unroll
-    for (int q = 0; q < kWB; q++)
-        if (lane < 3 && cidx[q] >= 0) scratch[cidx[q]] = 0xFFFFu;
+    for (int c = 0; c < NC; c++) {
+#pragma unroll
+        for (int q = 0; q < kWB; q++)
+            if (lane < 3 && cidx[c][q] >= 0) scratch[cidx[c][q]] = 0xFFFFu;
+    }
     __syncwarp();
+    uint32_t mm[NC][kWB];
 #pragma unroll
-    for (int q = 0; q < kWB; q++) {
-        uint32_t T[N];
-        if (active) ld_regs<N>(scratch + q * qs + lane * 2 * N, T);
-        else {
+    for (int c = 0; c < NC; c++) {
 #pragma unroll
-            for (int j = 0; j < N; j++) T[j] = 0xFFFFFFFFu;
+        for (int q = 0; q < kWB; q++) {
+            uint32_t T[N];
+            load(c, q, T);
+            uint32_t m = T[0];
+#pragma unroll
+            for (int j = 1; j < N; j++) m = __vminu2(m, T[j]);
+            m = __vminu2(m, __byte_perm(m, 0, 0x1032));
+            mm[c][q] = IL ? m : __reduce_min_sync(kFullMask, m);
         }
-        const uint32_t mm = warp_min16x2<N>(T);
-        const int smv = __shfl_sync(kFullMask, val[q], 0), spv = __shfl_sync(kFullMask, val[q], 2);
-        if (lane == ((row0 + q) & 31)) { acc.key = key[q]; acc.mm = mm; acc.sm = smv; acc.sp = spv; }
+    }
+#pragma unroll
+    for (int c = 0; c < NC; c++) {
+#pragma unroll
+        for (int q = 0; q < kWB; q++) {
+            const uint32_t m = IL ? __reduce_min_sync(kFullMask, mm[c][q]) : mm[c][q];
+            const int smv = __shfl_sync(kFullMask, val[c][q], 0), spv = __shfl_sync(kFullMask, val[c][q], 2);
+            if (lane == ((row0 + q) & 31) && c < ncol) { acc[c].key = key[c][q]; acc[c].mm = m; acc[c].sm = smv; acc[c].sp = spv; }
+        }
     }
 }
 
@@ -411,7 +528,15 @@ constexpr int kXbufGen = 4;
 #ifndef B200SGM_VERT_MAXT
 #define B200SGM_VERT_MAXT 1024
 #endif
-constexpr int vert_max_threads(int n) { return n <= 4 ? B200SGM_VERT_MAXT : 896; }
+// B200SGM_VERT_CPS = strips (CTAs) per SM: 2 halves the strip width, and the two lock-step groups of an SM fill each other's
+// barrier and latency gaps
+#ifndef B200SGM_VERT_CPS
+#define B200SGM_VERT_CPS 1
+#endif
+constexpr int kVertCps = B200SGM_VERT_CPS;
+// threads per CTA bound the registers per thread: beyond 256 disparities shared memory limits a strip to 13 / 6 / 3 columns, so
+// the bound follows and ptxas gets 88+ registers for the N >= 8 row loops (they spilled at 72)
+constexpr int vert_max_threads(int n) { return kVertCps == 2 ? 448 : (n <= 4 ? B200SGM_VERT_MAXT : (n == 8 ? 704 : (n == 16 ? 384 : 256))); }
 constexpr int kRowUnroll = 4; // the row loop is unrolled by this: record generation, stage slot, parity are immediates
 __device__ __forceinline__ uint2* xrec(uint2* xbuf, int nstrips, int Dp, int side, int strip, int row)
 {
@@ -428,6 +553,12 @@ __device__ __forceinline__ uint2 ld_volatile_v2(const uint2* p)
     return v;
 }
 
+// B200SGM_VERT_TMA: a row of a strip is one contiguous run of TW * Dp costs in C and in S_h, so one elected thread fetches it
+// with two bulk copies per row (rings [slot][column][Dp], one mbarrier per slot) instead of two cp.async per column warp.
+#ifndef B200SGM_VERT_TMA
+#define B200SGM_VERT_TMA 0
+#endif
+constexpr bool kVertTma = B200SGM_VERT_TMA != 0;
 constexpr int kStage = 4;     // rows of summed cost S parked for the WTA warps (ring, handed over with named barriers)
 static_assert(kStage == kRowUnroll && kXbufGen == kRowUnroll && kStage % kWB == 0, "stage slot = record generation = row & 3");
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
@@ -437,7 +568,9 @@ __device__ __forceinline__ void named_bar_arrive(int id, int nthreads) { asm vol
 //               | xring[2 sides][kXbufGen][Dp]   (uint16)
 inline size_t vert_smem_bytes(int twmax, int Dp, int ring)
 {
-    return (size_t(4) * (twmax + 2) + size_t(2 * ring + kStage) * twmax + 2 * kXbufGen) * Dp * sizeof(uint16_t);   // 190 KB at c3
+    return (size_t(4) * (twmax + 2) + size_t(2 * ring + kStage) * twmax + 2 * kXbufGen) * Dp * sizeof(uint16_t)   // 190 KB at c3
+           + (kVertTma ? size_t(ring) * sizeof(uint64_t) : 0)                                                        // + the ring's mbarriers
+           + size_t(2) * kStage * ((twmax + kWC - 1) / kWC) * sizeof(uint64_t);                                      // + full/empty per WTA warp and slot
 }
 
 // Warp-specialised vertical sweep.  Launch: 32 * twmax threads when !DO_WTA, else 64 * twmax:
@@ -455,11 +588,12 @@ inline size_t vert_smem_bytes(int twmax, int Dp, int ring)
 // FULL      : Dp == D == 64*N (no padded cells, every lane active)
 // CLAMP_EACH: saturate after every addition of the sum (needed when the 16-bit sum of the terms could wrap)
 template <int N, int RING, bool UP, bool DO_WTA, bool FULL, bool CLAMP_EACH>
-__global__ void __launch_bounds__(vert_max_threads(N), 1) k_vert(const uint16_t* __restrict__ Cvol, uint16_t* __restrict__ Svol, VertGeom g,
+__global__ void __launch_bounds__(vert_max_threads(N), kVertCps) k_vert(const uint16_t* __restrict__ Cvol, uint16_t* __restrict__ Svol, VertGeom g,
                                                   int16_t* __restrict__ disp, uint32_t* __restrict__ disp2key,
                                                   uint2* __restrict__ xbuf, int* __restrict__ err)
 {
     extern __shared__ __align__(16) uint16_t smem_v[];
+    constexpr bool kVertMbar = VertPolicy<N>::MBAR, kAgentPrefetch = VertPolicy<N>::AGENT_PREFETCH;
     const int W1 = g.w.W1, H = g.w.H, Dp = FULL ? 64 * N : g.w.Dp;
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int b = blockIdx.x, n = g.nstrips;
@@ -472,12 +606,38 @@ __global__ void __launch_bounds__(vert_max_threads(N), 1) k_vert(const uint16_t*
     uint16_t* sringbase = ringbase + size_t(RING) * g.twmax * Dp;
     uint16_t* stagebase = sringbase + size_t(RING) * g.twmax * Dp;
     uint16_t* xringbase = stagebase + size_t(kStage) * g.twmax * Dp;
+    uint64_t* ringbar = reinterpret_cast<uint64_t*>(xringbase + size_t(2) * kXbufGen * Dp);     // [RING], kVertTma only
     {
         uint32_t* z = reinterpret_cast<uint32_t*>(smem_v);
         const int nz = 2 * slots * Dp;
         for (int i = threadIdx.x; i < nz; i += blockDim.x) z[i] = 0;
     }
+    // hand-over barriers of the stage ring: fullbar[wta warp][slot] (arrivals: the path warps of its columns, plus the agent
+    // of an edge column), emptybar[wta warp][slot] (one arrival: the WTA warp)
+    const int nwta = (g.twmax + kWC - 1) / kWC;
+    uint64_t* fullbar = ringbar + (kVertTma ? RING : 0);
+    uint64_t* emptybar = fullbar + nwta * kStage;
+    if (kVertTma && threadIdx.x == 0) {
+#pragma unroll
+        for (int i = 0; i < RING; i++) mbar_init(ringbar + i, 1);
+    }
+    if (kVertMbar && DO_WTA && threadIdx.x < nwta) {
+        const int i = threadIdx.x;
+        const bool ag = g.agents && !(g.debug_flags & 1);
+        const int cols = min(kWC, TW - kWC * i);
+        const int prod = cols + ((ag && b > 0 && i == 0) ? 1 : 0) + ((ag && b < n - 1 && TW > 1 && (TW - 1) / kWC == i) ? 1 : 0);
+        for (int q = 0; q < kStage; q++) {
+            mbar_init(fullbar + i * kStage + q, max(prod, 1));
+            mbar_init(emptybar + i * kStage + q, 1);
+        }
+    }
+    if ((kVertTma || kVertMbar) && threadIdx.x < 32) mbar_init_fence();
     __syncthreads();
+    // ring geometry: cp.async [column][slot][Dp], bulk copies [slot][column][Dp]
+    const int ringColStride = kVertTma ? Dp : RING * Dp;
+    const int ringSlotStride = kVertTma ? g.twmax * Dp : Dp;
+    constexpr int kRingShift = RING == 8 ? 3 : 2;
+    static_assert(RING == 8 || RING == 4, "ring depth");
     const int wta_warps = DO_WTA ? (g.twmax + kWC - 1) / kWC : 0;      // launched; (TW + kWC - 1) / kWC of them have columns
     const int agent_base = g.twmax + wta_warps;
     const int TWW = DO_WTA ? (TW + kWC - 1) / kWC : 0;
@@ -502,35 +662,48 @@ __global__ void __launch_bounds__(vert_max_threads(N), 1) k_vert(const uint16_t*
             const int nrow_a = 32 * (TW + nag), nfe_a = 32 * (TW + TWW + nag);
             const int je = side == 0 ? 0 : TW - 1;
             uint16_t* wr = Ld + side * (slots * Dp) + (je + 1) * Dp + lane * 2 * N;          // + parity * 2*slots*Dp
-            const uint16_t* cring = ringbase + size_t(je) * RING * Dp + lane * 2 * N;
+            const uint16_t* cring = ringbase + size_t(je) * ringColStride + lane * 2 * N;
             uint16_t* sB = dst;                                                              // stageB[side][kStage][Dp] aliases the xring
-            asm volatile("bar.sync 1, %0;" ::"r"(nrow_a) : "memory");                          // C(0) is visible
+            if (!kVertTma) asm volatile("bar.sync 1, %0;" ::"r"(nrow_a) : "memory");           // C(0) is visible
+            // the record of row r - 1 is requested at the END of row r - 1 (the neighbour published it early in its own row
+            // r - 1), so that its L2 round trip overlaps the row barrier instead of heading this warp's row
+            uint2 pre[N];
+#pragma unroll
+            for (int q = 0; q < N; q++) pre[q] = make_uint2(0u, 0u);
+            uint64_t* fb = fullbar + (je / kWC) * kStage;
+            uint64_t* eb = emptybar + (je / kWC) * kStage;
             for (int r = 0; r < H; r++) {
                 uint32_t Cc[N], Lt[N], Ln[N];
 #pragma unroll
                 for (int q = 0; q < N; q++) Lt[q] = 0;
                 if (r > 0 && active && !dead) {
-                    const uint2* rec = rec0 + ((r - 1) & (kXbufGen - 1)) * gen_stride;
-                    const long long t0 = clock64();
-                    int spins = 0;
-                    while (true) {
-                        bool ok = true;
+                    bool ok = true;
 #pragma unroll
-                        for (int q = 0; q < N; q++) {
-                            uint2 v = ld_volatile_v2(rec + q);
-                            Lt[q] = v.x;
-                            ok = ok && v.y == uint32_t(r);
-                        }
-                        if (ok || (g.debug_flags & 8)) break;     // 8: timing experiment, take whatever is there
-                        if ((++spins & 255) == 0 && (clock64() - t0 > g.spin_limit || *reinterpret_cast<volatile int*>(err))) {
-                            atomicExch(err, 1);
-                            dead = true;
-                            break;
+                    for (int q = 0; q < N; q++) { Lt[q] = pre[q].x; ok = ok && pre[q].y == uint32_t(r); }
+                    if (!ok && !(g.debug_flags & 8)) {            // 8: timing experiment, take whatever is there
+                        const uint2* rec = rec0 + ((r - 1) & (kXbufGen - 1)) * gen_stride;
+                        const long long t0 = clock64();
+                        int spins = 0;
+                        while (true) {
+                            ok = true;
+#pragma unroll
+                            for (int q = 0; q < N; q++) {
+                                uint2 v = ld_volatile_v2(rec + q);
+                                Lt[q] = v.x;
+                                ok = ok && v.y == uint32_t(r);
+                            }
+                            if (ok) break;
+                            if ((++spins & 255) == 0 && (clock64() - t0 > g.spin_limit || *reinterpret_cast<volatile int*>(err))) {
+                                atomicExch(err, 1);
+                                dead = true;
+                                break;
+                            }
                         }
                     }
                 }
                 dead = __any_sync(kFullMask, dead);
-                if (active) ld_regs<N>(cring + (r & (RING - 1)) * Dp, Cc);
+                if (kVertTma) mbar_wait(ringbar + (r & (RING - 1)), (r >> kRingShift) & 1);
+                if (active) ld_regs<N>(cring + (r & (RING - 1)) * ringSlotStride, Cc);
                 else {
 #pragma unroll
                     for (int q = 0; q < N; q++) Cc[q] = kMaxCostX2;
@@ -538,9 +711,21 @@ __global__ void __launch_bounds__(vert_max_threads(N), 1) k_vert(const uint16_t*
                 path_step<N>(Cc, Lt, Ln, lc);
                 if (active) st_regs<N>(wr + (r & 1) * (2 * slots * Dp), Lt);
                 const int q4 = r & (kStage - 1);
-                if (r >= kStage) named_bar_sync(BAR_EMPTY + q4, nfe_a);
-                if (active) st_regs<N>(sB + q4 * Dp, Ln);
-                named_bar_arrive(BAR_FULL + q4, nfe_a);
+                if (kVertMbar) {
+                    if (r >= kStage) mbar_wait_b(eb + q4, ((r >> 2) + 1) & 1, err);
+                    if (active) st_regs<N>(sB + q4 * Dp, Ln);
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(fb + q4);
+                } else {
+                    if (r >= kStage) named_bar_sync(BAR_EMPTY + q4, nfe_a);
+                    if (active) st_regs<N>(sB + q4 * Dp, Ln);
+                    named_bar_arrive(BAR_FULL + q4, nfe_a);
+                }
+                if (kAgentPrefetch && r + 1 < H && active) {
+                    const uint2* rec = rec0 + (r & (kXbufGen - 1)) * gen_stride;
+#pragma unroll
+                    for (int q = 0; q < N; q++) pre[q] = ld_volatile_v2(rec + q);
+                }
                 asm volatile("bar.sync 1, %0;" ::"r"(nrow_a) : "memory");                      // BAR_ROW of row r
             }
             return;
@@ -610,11 +795,18 @@ __global__ void __launch_bounds__(vert_max_threads(N), 1) k_vert(const uint16_t*
             edge_side[c] = nag3 == 0 ? -1 : ((jc == 0 && b > 0) ? 0 : ((jc == TW - 1 && jc != 0 && b < n - 1) ? 1 : -1));
         }
         int pending = 0;                    // rows parked in acc
+        uint64_t* wfull = fullbar + (w - g.twmax) * kStage;
+        uint64_t* wempty = emptybar + (w - g.twmax) * kStage;
         // one batch of kWB (= 2) parked rows starting at row r; Q0 = r & 3 is an immediate so that the barrier ids are
         auto batch = [&](auto q0_tag, int r, int cnt) {
             constexpr int Q0 = decltype(q0_tag)::value;
-            named_bar_sync(BAR_FULL + Q0, nboth);
-            if (cnt > 1) named_bar_sync(BAR_FULL + Q0 + 1, nboth);
+            if (kVertMbar) {
+                mbar_wait_b(wfull + Q0, (r >> 2) & 1, err);
+                if (cnt > 1) mbar_wait_b(wfull + Q0 + 1, (r >> 2) & 1, err);
+            } else {
+                named_bar_sync(BAR_FULL + Q0, nboth);
+                if (cnt > 1) named_bar_sync(BAR_FULL + Q0 + 1, nboth);
+            }
 #pragma unroll
             for (int c = 0; c < kWC; c++) {
                 if (c >= ncol) break;
@@ -641,16 +833,24 @@ __global__ void __launch_bounds__(vert_max_threads(N), 1) k_vert(const uint16_t*
                         }
                     }
                 }
-                if (wta_on) {
-                    if (wc.f > 0) {
-                        wta_vec<N>(sc, ringSlot, r, g.w, wc, lane, active, acc[c]);   // a row past the end lands in a lane >= cnt of the flush
-                    } else {
-                        __syncwarp();
-                        for (int q = 0; q < cnt; q++) {
-                            const int d = wta_slow<N>(sc + q * ringSlot, g.w, wc, x + c, lane, active, kptr + q * dStride);
-                            if (lane == 0) dptr[q * dStride + c] = int16_t(d);
-                        }
-                        __syncwarp();
+                if (wta_on && wc.f <= 0) {
+                    __syncwarp();
+                    for (int q = 0; q < cnt; q++) {
+                        const int d = wta_slow<N>(sc + q * ringSlot, g.w, wc, x + c, lane, active, kptr + q * dStride);
+                        if (lane == 0) dptr[q * dStride + c] = int16_t(d);
+                    }
+                    __syncwarp();
+                }
+            }
+            // (a row past the end lands in a lane >= cnt of the flush)
+            if (wta_on && wc.f > 0) {
+                if constexpr (kWtaTogether) wta_vec<N, kWC>(stage + Q0 * ringSlot, ringSlot, r, ncol, g.w, wc, lane, active, acc);
+                else {
+#pragma unroll
+                    for (int c = 0; c < kWC; c++) {
+                        if (c >= ncol) break;
+                        WtaAcc (&a1)[1] = *reinterpret_cast<WtaAcc (*)[1]>(&acc[c]);
+                        wta_vec<N, 1>(stage + c * Dp + Q0 * ringSlot, ringSlot, r, 1, g.w, wc, lane, active, a1);
                     }
                 }
             }
@@ -668,8 +868,16 @@ __global__ void __launch_bounds__(vert_max_threads(N), 1) k_vert(const uint16_t*
                     dptr += cnt * dStride; kptr += cnt * dStride;
                 }
             }
-            if (r + kStage < H) named_bar_arrive(BAR_EMPTY + Q0, nboth);
-            if (cnt > 1 && r + 1 + kStage < H) named_bar_arrive(BAR_EMPTY + Q0 + 1, nboth);
+            if (kVertMbar) {
+                __syncwarp();
+                if (lane == 0) {
+                    if (r + kStage < H) mbar_arrive(wempty + Q0);
+                    if (cnt > 1 && r + 1 + kStage < H) mbar_arrive(wempty + Q0 + 1);
+                }
+            } else {
+                if (r + kStage < H) named_bar_arrive(BAR_EMPTY + Q0, nboth);
+                if (cnt > 1 && r + 1 + kStage < H) named_bar_arrive(BAR_EMPTY + Q0 + 1, nboth);
+            }
         };
         static_assert(kWB == 2 && kStage == 4, "two batches per stage-ring revolution");
         int r = 0;
@@ -715,8 +923,8 @@ __global__ void __launch_bounds__(vert_max_threads(N), 1) k_vert(const uint16_t*
     const int Dh = Dp >> 1;
     // cp.async rings: [warp][slot][Dp], slot = row & (ring - 1).  Group G_r (committed at the top of row r) carries C
     // of row r+RING-1 and S_h of row r+RING-1; the prologue commits C rows 0..RING-2 and S_h rows 0..RING-2.
-    uint16_t* ring = ringbase + size_t(j) * RING * Dp + lo;
-    uint16_t* sring = sringbase + size_t(j) * RING * Dp + lo;
+    uint16_t* ring = ringbase + size_t(j) * ringColStride + lo;
+    uint16_t* sring = sringbase + size_t(j) * ringColStride + lo;
     auto issue_c = [&](int row_) {
         if (row_ < H && active) cp_async_lane<N>(ring + (row_ & (RING - 1)) * Dp, gC);
         gC += rowStride;
@@ -725,15 +933,37 @@ __global__ void __launch_bounds__(vert_max_threads(N), 1) k_vert(const uint16_t*
         if (row_ < H && active) cp_async_lane<N>(sring + (row_ & (RING - 1)) * Dp, gSin);
         gSin += rowStride;
     };
+    // bulk-copy producer: one lane of a middle column's warp (the edge warps carry the exchange); it refills the slot of
+    // row r - 1 at the top of row r, i.e. after the row barrier every reader of that slot has passed
+    const bool producer = kVertTma && j == (TW >> 1) && lane == 0;
+    const uint16_t* gCs = Cvol + (size_t(ystart) * W1 + x0) * Dp;      // strip start of the next row to fetch
+    const uint16_t* gSs = Svol + (size_t(ystart) * W1 + x0) * Dp;
+    const uint32_t stripBytes = uint32_t(TW) * Dp * sizeof(uint16_t);
+    auto issue_bulk = [&](int row_) {
+        if (row_ < H) {
+            const int sl = row_ & (RING - 1);
+            mbar_expect_tx(ringbar + sl, 2 * stripBytes);
+            bulk_g2s(ringbase + size_t(sl) * ringSlotStride, gCs, stripBytes, ringbar + sl);
+            bulk_g2s(sringbase + size_t(sl) * ringSlotStride, gSs, stripBytes, ringbar + sl);
+        }
+        gCs += rowStride; gSs += rowStride;
+    };
+    if (kVertTma) {
+        if (producer)
+            for (int i = 0; i < RING - 1; i++) issue_bulk(i);
+    } else {
 #pragma unroll
-    for (int i = 0; i < RING - 1; i++) issue_s(i);
+        for (int i = 0; i < RING - 1; i++) issue_s(i);
 #pragma unroll
-    for (int i = 0; i < RING - 1; i++) { issue_c(i); cp_async_commit(); }
-    if (nag3) {            // agents read this column's C ring: make row 0 visible to them
-        cp_async_wait<RING - 2>();
-        named_bar_sync(BAR_ROW, nrow);
+        for (int i = 0; i < RING - 1; i++) { issue_c(i); cp_async_commit(); }
+        if (nag3) {            // agents read this column's C ring: make row 0 visible to them
+            cp_async_wait<RING - 2>();
+            named_bar_sync(BAR_ROW, nrow);
+        }
     }
 
+    uint64_t* pfull = fullbar + (j / kWC) * kStage;
+    uint64_t* pempty = emptybar + (j / kWC) * kStage;
     uint32_t LtV[N];
     uint2 pre[N];        // edge warps: the neighbour's record of the previous row, requested one row early
 #pragma unroll
@@ -747,7 +977,8 @@ __global__ void __launch_bounds__(vert_max_threads(N), 1) k_vert(const uint16_t*
         constexpr bool EDGE = EMODE != 0;
         constexpr bool NO_B = EMODE == 3;      // the agent owns the incoming-diagonal step
         constexpr int PAR = Q & 1;
-        issue_c(r + RING - 1); issue_s(r + RING - 1); cp_async_commit();
+        if (kVertTma) { if (producer) issue_bulk(r + RING - 1); }
+        else { issue_c(r + RING - 1); issue_s(r + RING - 1); cp_async_commit(); }
         uint32_t Cc[N], Sc[N], LtA[N], LtB[N], LnA[N], LnV[N], LnB[N];
         // incoming diagonal of the previous row: fire the loads now, inspect the tags right before step B
         const bool consume = EDGE && r > 0;
@@ -758,9 +989,10 @@ __global__ void __launch_bounds__(vert_max_threads(N), 1) k_vert(const uint16_t*
                 for (int q = 0; q < N; q++) pre[q] = ld_volatile_v2(rec + q);
             }
         }
-        cp_async_wait<RING - 1>();     // this thread's copies of row r have landed (each lane reads only its own bytes)
+        if (kVertTma) mbar_wait(ringbar + (r & (RING - 1)), (r >> kRingShift) & 1);     // both bulk copies of row r have landed
+        else cp_async_wait<RING - 1>();     // this thread's copies of row r have landed (each lane reads only its own bytes)
         if (active) {
-            ld_regs<N>(ring + (r & (RING - 1)) * Dp, Cc); ld_regs<N>(rdA[PAR ^ 1], LtA);
+            ld_regs<N>(ring + (r & (RING - 1)) * ringSlotStride, Cc); ld_regs<N>(rdA[PAR ^ 1], LtA);
             if (!EDGE) ld_regs<N>(rdB[PAR ^ 1], LtB);
         } else {
 #pragma unroll
@@ -835,7 +1067,7 @@ __global__ void __launch_bounds__(vert_max_threads(N), 1) k_vert(const uint16_t*
             for (int q = 0; q < N; q++) LnB[q] = 0;
         }
         // ---- S = sat(S_h + L_v + L_A + L_B)
-        if (active) ld_regs<N>(sring + (r & (RING - 1)) * Dp, Sc);
+        if (active) ld_regs<N>(sring + (r & (RING - 1)) * ringSlotStride, Sc);
         else {
 #pragma unroll
             for (int q = 0; q < N; q++) Sc[q] = 0;
@@ -860,14 +1092,21 @@ __global__ void __launch_bounds__(vert_max_threads(N), 1) k_vert(const uint16_t*
                     else if (k + Dh >= g.w.D) S[q] |= 0xFFFF0000u;
                 }
             }
-            if (r >= kStage) named_bar_sync(BAR_EMPTY + Q, nboth);    // the WTA warps have taken row r - kStage
-            if (active) st_regs<N>(stage + Q * ringSlot + lo, S);
-            named_bar_arrive(BAR_FULL + Q, nboth);
+            if (kVertMbar) {
+                if (r >= kStage) mbar_wait_b(pempty + Q, ((r >> 2) + 1) & 1, err);    // my WTA warp has taken row r - kStage
+                if (active) st_regs<N>(stage + Q * ringSlot + lo, S);
+                __syncwarp();
+                if (lane == 0) mbar_arrive(pfull + Q);
+            } else {
+                if (r >= kStage) named_bar_sync(BAR_EMPTY + Q, nboth);    // the WTA warps have taken row r - kStage
+                if (active) st_regs<N>(stage + Q * ringSlot + lo, S);
+                named_bar_arrive(BAR_FULL + Q, nboth);
+            }
         } else {
             if (active) st_regs<N>(gSout, S);
             gSout += rowStride;
         }
-        if (DO_WTA) cp_async_wait<RING - 2>();   // C of the NEXT row is complete before the barrier: the agents read it
+        if (DO_WTA && !kVertTma) cp_async_wait<RING - 2>();   // C of the NEXT row is complete before the barrier: the agents read it
         named_bar_sync(BAR_ROW, nrow);
     };
 

@@ -12,7 +12,7 @@ import numpy as np
 from .params import CParams, SGBMParams
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libb200sgm.so")
+LIB_PATH = os.environ.get("B200SGM_LIB") or os.path.join(_HERE, "libb200sgm.so")   # B200SGM_LIB: development builds (build.py variants)
 _lib = None
 
 # every symbol include/b200sgm.h declares
