@@ -48,6 +48,7 @@ cudaError_t launch_cost(const Feat* fl, const Feat* fr, uint16_t* C, const Eff& 
         void (*kern)(const Feat*, const Feat*, uint16_t*, CostFastGeom);
         if (e.SW2 == 4) kern = nopad ? k_cost_tile2<4, true> : k_cost_tile2<4, false>;
         else if (e.SW2 == 2) kern = nopad ? k_cost_tile2<2, true> : k_cost_tile2<2, false>;
+        else if (e.SW2 == 10) kern = nopad ? k_cost_tile2<10, true> : k_cost_tile2<10, false>;   // blockSize 21: the reference's launch default
         else kern = k_cost_tile2<0, false>;
         CUDA_TRY_(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
         kern<<<grid, 256, smem, st>>>(fl, fr, C, fg);

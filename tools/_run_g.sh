@@ -1,0 +1,3 @@
+mkdir -p gpurun_out
+timeout 120 python tools/stage_time.py cL 12 2>&1 | tail -1
+timeout 600 python -m pytest tests/test_gpu_parity.py -m gpu -x -q 2>&1 | tail -3
