@@ -12,6 +12,10 @@ namespace b200sgm {
 struct BmGeom {
     int W, H, ndisp, mindisp, wsz, cap, tex, uniq;
     int lofs, rofs, width1, FILTERED;
+    // cv::StereoBM walks width1 columns from lofs, i.e. minDisparity pixels past the end of every row when minDisparity > 0; what
+    // the LAST row of the valid ROI spills into the first pixels of the row below it survives OpenCV's ROI masking.  yspill is
+    // that row (-1: none): its virtual columns are stored at the same linear address OpenCV writes them to.
+    int yspill;
 };
 
 // prefilterXSobel; grid.z = 2 (left, right)
@@ -145,7 +149,7 @@ static __global__ void __launch_bounds__(128) k_bm_match(const uint16_t* __restr
             if (d == jp) vp = unsigned(sad[k]);
         }
         const int n = int(__reduce_max_sync(0xFFFFFFFFu, vn)), p = int(__reduce_max_sync(0xFFFFFFFFu, vp));
-        if (lane == 0 && in_row) {
+        if (lane == 0 && (in_row || y == g.yspill)) {
             int out = g.FILTERED;
             if (ok) {
                 const int den = p + n - 2 * int(minsad) + abs(p - n);
@@ -241,7 +245,7 @@ static __global__ void __launch_bounds__(128) k_bm_match_v(const uint16_t* __res
             if (k == jp % NPL) vp = sad[k];
         }
         const int n = __shfl_sync(0xFFFFFFFFu, vn, jm / NPL), p = __shfl_sync(0xFFFFFFFFu, vp, jp / NPL);
-        if (lane == 0 && in_row) {
+        if (lane == 0 && (in_row || y == g.yspill)) {
             int out = g.FILTERED;
             if (ok) {
                 const int den = p + n - 2 * minsad + abs(p - n);
@@ -347,7 +351,7 @@ static __global__ void __launch_bounds__(128) k_bm_match_p(const uint16_t* __res
         }
         wn = __shfl_sync(0xFFFFFFFFu, wn, jm / NPL); wp = __shfl_sync(0xFFFFFFFFu, wp, jp / NPL);
         const int n = int((jm & 1) ? (wn >> 16) : (wn & 0xFFFFu)), p = int((jp & 1) ? (wp >> 16) : (wp & 0xFFFFu));
-        if (lane == 0 && in_row) {
+        if (lane == 0 && (in_row || y == g.yspill)) {
             int out = g.FILTERED;
             if (ok) {
                 const int den = p + n - 2 * minsad + abs(p - n);
@@ -367,10 +371,12 @@ static __global__ void __launch_bounds__(128) k_bm_match_p(const uint16_t* __res
 }
 
 // getValidDisparityROI with full-image ROIs: everything outside [xmin, xmax) x [ymin, ymax) is FILTERED
-static __global__ void k_bm_mask(int16_t* __restrict__ disp, int W, int H, int xmin, int xmax, int ymin, int ymax, int FILTERED)
+// nspill: pixels at the start of row ymax that hold the spill of row ymax - 1 (BmGeom::yspill) and are left alone
+static __global__ void k_bm_mask(int16_t* __restrict__ disp, int W, int H, int xmin, int xmax, int ymin, int ymax, int FILTERED, int nspill)
 {
     const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
     if (x >= W) return;
+    if (y == ymax && x < nspill) return;
     if (x < xmin || x >= xmax || y < ymin || y >= ymax) disp[size_t(y) * W + x] = int16_t(FILTERED);
 }
 

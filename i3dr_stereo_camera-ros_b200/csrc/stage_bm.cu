@@ -18,6 +18,12 @@ cudaError_t launch_bm(const uint8_t* dL, size_t lp, const uint8_t* dR, size_t rp
     g.rofs = -std::min(g.ndisp - 1 + g.mindisp, 0);
     g.width1 = W - g.rofs - g.ndisp + 1;
     g.FILTERED = (g.mindisp - 1) * 16;
+    // valid-disparity ROI (getValidDisparityROI with full-image ROIs) and the row whose overflow OpenCV leaves behind
+    const int w2r = g.wsz / 2, maxDr = g.mindisp + g.ndisp - 1;
+    const int xmin = std::max(0, maxDr) + w2r, xmax = W - w2r, ymin = w2r, ymax = H - w2r;
+    const bool roi_ok = xmax > xmin && ymax > ymin;
+    const int nspill = (g.mindisp > 0 && roi_ok && w2r >= 1 && ymax >= 1 && ymax < H) ? std::min(g.width1 - (W - g.lofs), W) : 0;
+    g.yspill = nspill > 0 ? ymax - 1 : -1;
     const int npix = W * H;
     // everything starts FILTERED (left / right borders, rows the matcher does not reach)
     launch_fill16(disp, npix, int16_t(g.FILTERED), st);
@@ -64,9 +70,8 @@ cudaError_t launch_bm(const uint8_t* dL, size_t lp, const uint8_t* dR, size_t rp
             BM_LAUNCH_CHECK();
         }
         {
-            const int w2 = g.wsz / 2, maxD = g.mindisp + g.ndisp - 1;
             dim3 grid((W + 255) / 256, H);
-            k_bm_mask<<<grid, 256, 0, st>>>(disp, W, H, std::max(0, maxD) + w2, W - w2, w2, H - w2, g.FILTERED);
+            k_bm_mask<<<grid, 256, 0, st>>>(disp, W, H, xmin, xmax, ymin, ymax, g.FILTERED, std::max(nspill, 0));
             BM_LAUNCH_CHECK();
         }
     }

@@ -185,8 +185,9 @@ typedef struct b200sgm_bm_params {
 
 /* matcher->compute(*left, *right, disparity_lr) of MatcherOpenCVBlock::forwardMatch (matcherOpenCVBlock.cpp:20): CV_8UC1 host
  * images in, CV_16S disparity x16 out, filtered pixels = (minDisparity-1)*16.  Synchronous, lane 0.  Bit-exact with
- * cv::StereoBM 4.13 except the `minDisparity` pixels at the start of the first row below the valid ROI when minDisparity > 0,
- * where OpenCV leaves values it wrote past the end of the previous row (this engine returns filtered there). */
+ * cv::StereoBM 4.13, including the `minDisparity` pixels at the start of the first row below the valid ROI when
+ * minDisparity > 0, where OpenCV leaves the values it wrote past the end of the last ROI row (reproduced: the reference's
+ * launch default has minDisparity 147).  An empty valid ROI is outside the contract (OpenCV returns uninitialised memory). */
 int b200sgm_bm_compute(b200sgm_handle h, const b200sgm_bm_params *p, const uint8_t *left, size_t left_stride,
                        const uint8_t *right, size_t right_stride, int width, int height, int16_t *disp,
                        size_t disp_stride);

@@ -86,6 +86,14 @@ def compute(left: np.ndarray, right: np.ndarray, numDisparities: int = 64, block
     if xmax > xmin and ymax > ymin:
         mask[ymin:ymax, max(xmin, 0):xmax] = True
     disp[~mask] = FILTERED
+    # cv::StereoBM walks width1 columns starting at lofs, i.e. minDisparity pixels past the end of every row (minDisparity > 0):
+    # the spill of row y lands in the first pixels of row y + 1.  Inside the ROI rows the mask above wipes it; the spill of the
+    # LAST computed row (H - w2 - 1) stays in row H - w2.  Reproduced because the reference's launch default has minDisparity > 0.
+    ys = H - w2
+    if mindisp > 0 and w2 >= 1 and 1 <= ys < H and xmax > xmin and ymax > ymin:
+        k = min(width1 - (W - lofs), W)
+        if k > 0:
+            disp[ys, :k] = out[ys - 1, W - lofs:W - lofs + k]
     if speckleRange >= 0 and speckleWindowSize > 0:
         from oracle import oracle
         disp = oracle.filter_speckles(disp, FILTERED, speckleWindowSize, speckleRange)
@@ -94,7 +102,8 @@ def compute(left: np.ndarray, right: np.ndarray, numDisparities: int = 64, block
 
 def overflow_mask(shape, blockSize: int, minDisparity: int) -> np.ndarray:
     """Pixels where cv::StereoBM leaves values it wrote past the end of the previous row (minDisparity > 0): the first
-    minDisparity columns of the first row below the valid ROI.  Excluded from every comparison with cv2 (include/b200sgm.h)."""
+    minDisparity columns of the first row below the valid ROI.  compute() reproduces them since round 2; kept for tools that
+    compare against older fixtures."""
     m = np.zeros(shape, bool)
     if minDisparity > 0:
         y = shape[0] - blockSize // 2
