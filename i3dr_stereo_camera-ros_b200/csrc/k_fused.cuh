@@ -296,8 +296,15 @@ __global__ void __launch_bounds__(64) k_horiz(const uint16_t* __restrict__ Cvol,
 //                      1280x720x128 MODE_HH: 1.130 against 1.166; N = 4: 1.556 against 1.531 (not taken there).
 //   WTA_INTERLEAVE   : both staged rows of a column go through each phase of the WTA together (N <= 4: 1.531 against 1.551);
 //                      for N >= 8 the second row's registers spill (6.15 against 5.52), so rows go one after the other.
+//   SPLIT_ROW        : split-phase row barrier of a WTA sweep (an mbarrier): a path warp ARRIVES as soon as its two diagonal
+//                      states of the row are stored -- all its neighbours wait for -- then runs the down step, the sum and the
+//                      stage hand-over, and only WAITS at the top of the next row.  Needs the non-blocking (MBAR) stage hand-over.
+#ifndef B200SGM_VERT_SPLIT
+#define B200SGM_VERT_SPLIT 0
+#endif
 template <int N> struct VertPolicy {
-    static constexpr bool MBAR = N >= 8, AGENT_PREFETCH = N != 4, WTA_INTERLEAVE = N <= 4;
+    static constexpr bool SPLIT_ROW = B200SGM_VERT_SPLIT != 0;
+    static constexpr bool MBAR = N >= 8 || SPLIT_ROW, AGENT_PREFETCH = N != 4, WTA_INTERLEAVE = N <= 4;
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -570,7 +577,8 @@ inline size_t vert_smem_bytes(int twmax, int Dp, int ring)
 {
     return (size_t(4) * (twmax + 2) + size_t(2 * ring + kStage) * twmax + 2 * kXbufGen) * Dp * sizeof(uint16_t)   // 190 KB at c3
            + (kVertTma ? size_t(ring) * sizeof(uint64_t) : 0)                                                        // + the ring's mbarriers
-           + size_t(2) * kStage * ((twmax + kWC - 1) / kWC) * sizeof(uint64_t);                                      // + full/empty per WTA warp and slot
+           + size_t(2) * kStage * ((twmax + kWC - 1) / kWC) * sizeof(uint64_t)                                       // + full/empty per WTA warp and slot
+           + sizeof(uint64_t);                                                                                       // + the split-phase row barrier
 }
 
 // Warp-specialised vertical sweep.  Launch: 32 * twmax threads when !DO_WTA, else 64 * twmax:
@@ -594,6 +602,7 @@ __global__ void __launch_bounds__(vert_max_threads(N), kVertCps) k_vert(const ui
 {
     extern __shared__ __align__(16) uint16_t smem_v[];
     constexpr bool kVertMbar = VertPolicy<N>::MBAR, kAgentPrefetch = VertPolicy<N>::AGENT_PREFETCH;
+    constexpr bool SPLIT = DO_WTA && VertPolicy<N>::SPLIT_ROW;
     const int W1 = g.w.W1, H = g.w.H, Dp = FULL ? 64 * N : g.w.Dp;
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int b = blockIdx.x, n = g.nstrips;
@@ -617,6 +626,7 @@ __global__ void __launch_bounds__(vert_max_threads(N), kVertCps) k_vert(const ui
     const int nwta = (g.twmax + kWC - 1) / kWC;
     uint64_t* fullbar = ringbar + (kVertTma ? RING : 0);
     uint64_t* emptybar = fullbar + nwta * kStage;
+    uint64_t* rowbar = emptybar + nwta * kStage;          // SPLIT: one arrival per path warp and agent of the strip and row
     if (kVertTma && threadIdx.x == 0) {
 #pragma unroll
         for (int i = 0; i < RING; i++) mbar_init(ringbar + i, 1);
@@ -630,6 +640,10 @@ __global__ void __launch_bounds__(vert_max_threads(N), kVertCps) k_vert(const ui
             mbar_init(fullbar + i * kStage + q, max(prod, 1));
             mbar_init(emptybar + i * kStage + q, 1);
         }
+    }
+    if (SPLIT && threadIdx.x == 0) {
+        const bool ag = g.agents && !(g.debug_flags & 1);
+        mbar_init(rowbar, TW + (ag ? (b > 0 ? 1 : 0) + (b < n - 1 ? 1 : 0) : 0));
     }
     if ((kVertTma || kVertMbar) && threadIdx.x < 32) mbar_init_fence();
     __syncthreads();
@@ -676,6 +690,7 @@ __global__ void __launch_bounds__(vert_max_threads(N), kVertCps) k_vert(const ui
                 uint32_t Cc[N], Lt[N], Ln[N];
 #pragma unroll
                 for (int q = 0; q < N; q++) Lt[q] = 0;
+                if (SPLIT && r > 0) mbar_wait_b(rowbar, (r - 1) & 1, err);      // row r - 1 of the strip is complete
                 if (r > 0 && active && !dead) {
                     bool ok = true;
 #pragma unroll
@@ -710,6 +725,10 @@ __global__ void __launch_bounds__(vert_max_threads(N), kVertCps) k_vert(const ui
                 }
                 path_step<N>(Cc, Lt, Ln, lc);
                 if (active) st_regs<N>(wr + (r & 1) * (2 * slots * Dp), Lt);
+                if (SPLIT) {               // the state is all the strip's row waits for from this warp
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(rowbar);
+                }
                 const int q4 = r & (kStage - 1);
                 if (kVertMbar) {
                     if (r >= kStage) mbar_wait_b(eb + q4, ((r >> 2) + 1) & 1, err);
@@ -726,7 +745,7 @@ __global__ void __launch_bounds__(vert_max_threads(N), kVertCps) k_vert(const ui
 #pragma unroll
                     for (int q = 0; q < N; q++) pre[q] = ld_volatile_v2(rec + q);
                 }
-                asm volatile("bar.sync 1, %0;" ::"r"(nrow_a) : "memory");                      // BAR_ROW of row r
+                if (!SPLIT) asm volatile("bar.sync 1, %0;" ::"r"(nrow_a) : "memory");          // BAR_ROW of row r
             }
             return;
         }
@@ -977,6 +996,7 @@ __global__ void __launch_bounds__(vert_max_threads(N), kVertCps) k_vert(const ui
         constexpr bool EDGE = EMODE != 0;
         constexpr bool NO_B = EMODE == 3;      // the agent owns the incoming-diagonal step
         constexpr int PAR = Q & 1;
+        if (SPLIT && r > 0) mbar_wait_b(rowbar, (r - 1) & 1, err);      // every warp of the strip has stored its states of row r - 1
         if (kVertTma) { if (producer) issue_bulk(r + RING - 1); }
         else { issue_c(r + RING - 1); issue_s(r + RING - 1); cp_async_commit(); }
         uint32_t Cc[N], Sc[N], LtA[N], LtB[N], LnA[N], LnV[N], LnB[N];
@@ -1008,8 +1028,8 @@ __global__ void __launch_bounds__(vert_max_threads(N), kVertCps) k_vert(const ui
                 for (int q = 0; q < N; q++) st_volatile_v2(rec + q, LtA[q], uint32_t(r + 1));
             }
         }
-        // ---- vertical path: registers only
-        path_step<N>(Cc, LtV, LnV, lc);
+        // ---- vertical path: registers only (SPLIT: after the row's arrival, nobody waits for it)
+        if (!SPLIT) path_step<N>(Cc, LtV, LnV, lc);
         // ---- step B
         if (EDGE && !NO_B) {
             if (consume && EMODE == 2) {
@@ -1066,6 +1086,14 @@ __global__ void __launch_bounds__(vert_max_threads(N), kVertCps) k_vert(const ui
 #pragma unroll
             for (int q = 0; q < N; q++) LnB[q] = 0;
         }
+        if (SPLIT) {
+            // both diagonal states of the row are stored: that is all the neighbours (and, with C of the next row landed, the
+            // agents) wait for.  The rest of the row overlaps their waiting.
+            cp_async_wait<RING - 2>();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(rowbar);
+            path_step<N>(Cc, LtV, LnV, lc);
+        }
         // ---- S = sat(S_h + L_v + L_A + L_B)
         if (active) ld_regs<N>(sring + (r & (RING - 1)) * ringSlotStride, Sc);
         else {
@@ -1106,8 +1134,10 @@ __global__ void __launch_bounds__(vert_max_threads(N), kVertCps) k_vert(const ui
             if (active) st_regs<N>(gSout, S);
             gSout += rowStride;
         }
-        if (DO_WTA && !kVertTma) cp_async_wait<RING - 2>();   // C of the NEXT row is complete before the barrier: the agents read it
-        named_bar_sync(BAR_ROW, nrow);
+        if (!SPLIT) {
+            if (DO_WTA && !kVertTma) cp_async_wait<RING - 2>();   // C of the NEXT row is complete before the barrier: the agents read it
+            named_bar_sync(BAR_ROW, nrow);
+        }
     };
 
     auto sweep = [&](auto edge_tag) {
