@@ -302,8 +302,18 @@ __global__ void __launch_bounds__(64) k_horiz(const uint16_t* __restrict__ Cvol,
 #ifndef B200SGM_VERT_SPLIT
 #define B200SGM_VERT_SPLIT 0
 #endif
+//   FOLD_EMPTY       : (named-barrier hand-over) the WTA warps release a batch of two stage slots by ARRIVING at the row barrier
+//                      of the row after next instead of at empty[q] barriers the path warps (and agents) sync on: one blocking
+//                      CTA-wide barrier per row instead of two.  Odd rows use two alternating barrier ids for it.  The WTA
+//                      warps then have two rows instead of almost three to resolve a batch: 640x480x64 0.241 -> 0.216,
+//                      1280x1024x128 MODE_HH 1.153 -> 1.096, but N = 4 (busy WTA warps) 1.529 -> 1.606, also with both columns of
+//                      a WTA warp resolved together (1.595): N <= 2 only.
+#ifndef B200SGM_VERT_FOLD
+#define B200SGM_VERT_FOLD 1
+#endif
 template <int N> struct VertPolicy {
     static constexpr bool SPLIT_ROW = B200SGM_VERT_SPLIT != 0;
+    static constexpr bool FOLD_EMPTY = B200SGM_VERT_FOLD != 0 && N <= 2 && !SPLIT_ROW;
     static constexpr bool MBAR = N >= 8 || SPLIT_ROW, AGENT_PREFETCH = N != 4, WTA_INTERLEAVE = N <= 4;
 };
 
@@ -603,6 +613,7 @@ __global__ void __launch_bounds__(vert_max_threads(N), kVertCps) k_vert(const ui
     extern __shared__ __align__(16) uint16_t smem_v[];
     constexpr bool kVertMbar = VertPolicy<N>::MBAR, kAgentPrefetch = VertPolicy<N>::AGENT_PREFETCH;
     constexpr bool SPLIT = DO_WTA && VertPolicy<N>::SPLIT_ROW;
+    constexpr bool FOLD = DO_WTA && VertPolicy<N>::FOLD_EMPTY;      // (implies !kVertMbar)
     const int W1 = g.w.W1, H = g.w.H, Dp = FULL ? 64 * N : g.w.Dp;
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int b = blockIdx.x, n = g.nstrips;
@@ -659,6 +670,9 @@ __global__ void __launch_bounds__(vert_max_threads(N), kVertCps) k_vert(const ui
     const LaneCtx lc = make_lane_ctx<N>(lane, Dp, g.P1, g.P2);
     const bool active = FULL || lc.active;
     constexpr int BAR_ROW = 1, BAR_FULL = 2, BAR_EMPTY = 2 + kStage, BAR_HALO = 2 + 2 * kStage;
+    // FOLD: row barrier of odd rows = BAR_ROWX + ((r >> 1) & 1) (the ids of empty[0], empty[1]); from row 3 on it also counts the
+    // WTA warps, which arrive there once they have resolved rows r - 3 and r - 2 (whose slots are rewritten in rows r + 1, r + 2)
+    constexpr int BAR_ROWX = BAR_EMPTY;
     if (w >= agent_base) {
         // ================================ agent warps ================================
         const int side = w - agent_base;                     // 0: left neighbour (feeds warp 0), 1: right neighbour (feeds warp TW-1)
@@ -736,7 +750,7 @@ __global__ void __launch_bounds__(vert_max_threads(N), kVertCps) k_vert(const ui
                     __syncwarp();
                     if (lane == 0) mbar_arrive(fb + q4);
                 } else {
-                    if (r >= kStage) named_bar_sync(BAR_EMPTY + q4, nfe_a);
+                    if (!FOLD && r >= kStage) named_bar_sync(BAR_EMPTY + q4, nfe_a);
                     if (active) st_regs<N>(sB + q4 * Dp, Ln);
                     named_bar_arrive(BAR_FULL + q4, nfe_a);
                 }
@@ -745,7 +759,8 @@ __global__ void __launch_bounds__(vert_max_threads(N), kVertCps) k_vert(const ui
 #pragma unroll
                     for (int q = 0; q < N; q++) pre[q] = ld_volatile_v2(rec + q);
                 }
-                if (!SPLIT) asm volatile("bar.sync 1, %0;" ::"r"(nrow_a) : "memory");          // BAR_ROW of row r
+                if (FOLD && (r & 1)) named_bar_sync(BAR_ROWX + ((r >> 1) & 1), r >= 3 ? nfe_a : nrow_a);
+                else if (!SPLIT) asm volatile("bar.sync 1, %0;" ::"r"(nrow_a) : "memory");     // BAR_ROW of row r
             }
             return;
         }
@@ -894,8 +909,12 @@ __global__ void __launch_bounds__(vert_max_threads(N), kVertCps) k_vert(const ui
                     if (cnt > 1 && r + 1 + kStage < H) mbar_arrive(wempty + Q0 + 1);
                 }
             } else {
-                if (r + kStage < H) named_bar_arrive(BAR_EMPTY + Q0, nboth);
-                if (cnt > 1 && r + 1 + kStage < H) named_bar_arrive(BAR_EMPTY + Q0 + 1, nboth);
+                if (FOLD) {
+                    if (r + 3 < H) named_bar_arrive(BAR_ROWX + (Q0 == 0 ? 1 : 0), nboth);     // row r + 3 = 3 or 1 (mod 4)
+                } else {
+                    if (r + kStage < H) named_bar_arrive(BAR_EMPTY + Q0, nboth);
+                    if (cnt > 1 && r + 1 + kStage < H) named_bar_arrive(BAR_EMPTY + Q0 + 1, nboth);
+                }
             }
         };
         static_assert(kWB == 2 && kStage == 4, "two batches per stage-ring revolution");
@@ -1126,7 +1145,7 @@ __global__ void __launch_bounds__(vert_max_threads(N), kVertCps) k_vert(const ui
                 __syncwarp();
                 if (lane == 0) mbar_arrive(pfull + Q);
             } else {
-                if (r >= kStage) named_bar_sync(BAR_EMPTY + Q, nboth);    // the WTA warps have taken row r - kStage
+                if (!FOLD && r >= kStage) named_bar_sync(BAR_EMPTY + Q, nboth);    // the WTA warps have taken row r - kStage
                 if (active) st_regs<N>(stage + Q * ringSlot + lo, S);
                 named_bar_arrive(BAR_FULL + Q, nboth);
             }
@@ -1136,7 +1155,8 @@ __global__ void __launch_bounds__(vert_max_threads(N), kVertCps) k_vert(const ui
         }
         if (!SPLIT) {
             if (DO_WTA && !kVertTma) cp_async_wait<RING - 2>();   // C of the NEXT row is complete before the barrier: the agents read it
-            named_bar_sync(BAR_ROW, nrow);
+            if (FOLD && (Q & 1)) named_bar_sync(BAR_ROWX + (Q >> 1), r >= 3 ? nboth : nrow);
+            else named_bar_sync(BAR_ROW, nrow);
         }
     };
 
