@@ -499,7 +499,9 @@ def run_b200(args, cfg):
         side = {}
         for name in ("c1", "c2", "cL", "c5"):
             try:
-                side[name] = side_config(torch, dev, CONFIGS[name], alu[0] if roofline else None, hbm_peak if roofline else 6457.1)
+                # c1's sweeps take a quarter of the SMs each: 8 frames in flight keep 4 of them running side by side
+                side[name] = side_config(torch, dev, CONFIGS[name], alu[0] if roofline else None, hbm_peak if roofline else 6457.1,
+                                         frames=16 if name == "c1" else 8, lanes=8 if name == "c1" else 4)
             except Exception as e:  # pragma: no cover
                 side[name] = {"error": repr(e)}
         try:
@@ -550,7 +552,7 @@ def side_config(torch, dev, cfg, alu_peak, hbm_peak, frames=8, lanes=4, reps=4):
         dL, dR = hL.to(dev), hR.to(dev)
         dD = torch.empty((frames, H, W), dtype=torch.int16, device=dev)
         streams = [torch.cuda.Stream(device=dev) for _ in range(lanes)]
-        out = {"workload": workload(cfg, frames, lanes)["workload"]}
+        out = {"workload": workload(cfg, frames, lanes)["workload"], "lanes": lanes}
 
         def one_pass():
             for i in range(frames):
