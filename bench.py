@@ -661,16 +661,23 @@ def plugin_call(cfg, hostL, hostR, refs, n_unique, frames=8):
         r = subprocess.run([str(a) for a in args], capture_output=True, text=True, timeout=600)
         if r.returncode != 0:
             return {"error": r.stderr[-400:]}
-        ms = None
+        ms = match_ms = None
         for line in r.stderr.splitlines():
             if line.startswith("bench_ms_per_frame"):
                 ms = float(line.split()[1])
+            if line.startswith("bench_match_ms_per_frame"):
+                match_ms = float(line.split()[1])
         got = np.fromfile(op, np.float32).reshape(H, W)
         ok = bool(np.array_equal(got, refs[0].astype(np.float32)))
     return {"api": "MatcherB200SGM::setImages/match/getDisparity via host/harness (b200sgm_compute_f32, pageable buffers, 1 lane)",
-            "ms_per_frame": ms, "frames_per_s": 1e3 / ms if ms else None, "frames": frames, "matches_reference": ok,
+            "ms_per_frame": ms, "frames_per_s": 1e3 / ms if ms else None, "match_ms_per_frame": match_ms,
+            "frames": frames, "matches_reference": ok,
             "h2d_bytes_per_frame": 2 * W * H, "d2h_bytes_per_frame": 4 * W * H,
-            "note": "compare with the reference's stereo_match() on cv::StereoSGBM: cpu_baseline single-frame latency = cores / value"}
+            "note": "ms_per_frame = the node's whole stereo_match() (generate_disparity.cpp:334-368: a fresh CV_32F Mat, setImages' two "
+                    "cv::resize copies into new Mats, match, getDisparity's deep copy -- reference code around the plugin); "
+                    "match_ms_per_frame = MatcherB200SGM::match() alone (H2D of the pageable images, the engine, the float result "
+                    "into the adapter's page-locked buffer).  Compare with the reference's stereo_match() on cv::StereoSGBM: "
+                    "cpu_baseline single-frame latency = cores / value"}
 
 
 _REAL_STDOUT = None

@@ -61,6 +61,7 @@ static void init_matcher(cv::Size image_size)   // generate_disparity.cpp:263-33
   updateMatcher();
 }
 
+static double g_match_ms = 0;     // time inside matcher->match() (the adapter + engine), of the whole stereo_match() call
 static cv::Mat stereo_match(cv::Mat left_image, cv::Mat right_image)   // generate_disparity.cpp:334-368
 {
   cv::Mat disp;
@@ -72,7 +73,9 @@ static cv::Mat stereo_match(cv::Mat left_image, cv::Mat right_image)   // genera
   }
   matcher->setDownsampleScale(1);
   matcher->setImages(&left_image, &right_image);
+  const auto tm0 = std::chrono::steady_clock::now();
   int exitCode = matcher->match();
+  g_match_ms += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - tm0).count();
   if (exitCode == 0) {
     matcher->getDisparity(disp);
   } else {
@@ -131,6 +134,7 @@ int main(int argc, char **argv)
   if (disp.empty()) return 1;
   if (disp.type() != CV_32F) { std::cerr << "unexpected disparity type" << std::endl; return 1; }
   if (bench_frames > 0) {
+    g_match_ms = 0;
     const auto t0 = std::chrono::steady_clock::now();
     for (int i = 0; i < bench_frames; i++) {
       cv::Mat d = stereo_match(left, right);
@@ -138,6 +142,7 @@ int main(int argc, char **argv)
     }
     const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count() / bench_frames;
     std::cerr << "bench_ms_per_frame " << ms << std::endl;
+    std::cerr << "bench_match_ms_per_frame " << g_match_ms / bench_frames << std::endl;
   }
   std::ofstream o(argv[5], std::ios::binary);
   for (int y = 0; y < disp.rows; y++) o.write(reinterpret_cast<const char *>(disp.data + y * disp.step), size_t(disp.cols) * 4);
