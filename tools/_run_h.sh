@@ -1,5 +1,4 @@
 mkdir -p gpurun_out
-(timeout 500 python tools/fuzz_parity.py 250 77 2>&1 | tail -2
-timeout 300 python tools/fuzz_parity.py 60 78 wide 2>&1 | tail -2
-timeout 300 python tools/fuzz_parity.py 30 79 tall 2>&1 | tail -2
-timeout 300 python tools/fuzz_sequence.py 100 2>&1 | tail -2) | tee gpurun_out/r2_fuzz.txt
+(echo "fuzz_parity full (2448x2048, random parameter sets):"; timeout 900 python tools/fuzz_parity.py 8 101 full 2>&1 | tail -1
+echo "fuzz_parity default:"; timeout 600 python tools/fuzz_parity.py 400 102 2>&1 | tail -1
+echo "fuzz_bm:"; timeout 400 python tools/fuzz_bm.py 300 7 2>&1 | tail -1) | tee gpurun_out/r2_fuzz3.txt
