@@ -33,7 +33,7 @@ int launch_paths_generic(b200sgm_engine* h, Lane& ln, const Eff& e, cudaStream_t
 }
 
 // ---- fused path: k_horiz + cooperative k_vert ---------------------------------------------------------
-struct VertPlan { bool ok; int nstrips, twmax; size_t smem; };
+struct VertPlan { bool ok; int nstrips, twmax; size_t smem; int halo; };
 
 // Ring depth and thread budget per register count: up to 256 disparities 8 rows of C / S_h in flight and 64 registers per
 // thread; beyond that a row is at least twice the bytes, so half the depth hides the same DRAM latency, and fewer, fatter
@@ -51,7 +51,7 @@ inline int vert_threads(int tw, bool do_wta) { return 32 * (tw + (do_wta ? (tw +
 template <int N>
 inline VertPlan plan_vert(const b200sgm_engine* h, const Eff& e)
 {
-    VertPlan p{false, 0, 0, 0};
+    VertPlan p{false, 0, 0, 0, 1};
     if (e.W1 < 2) return p;
     if (kVertTma && e.Dp % 8 != 0) return p;      // bulk copies move multiples of 16 bytes: odd paddings take the hybrid path
     // widest strip a CTA can take: threads (a path warp per column, a WTA warp per kWC columns, two agents) and shared memory
@@ -74,10 +74,22 @@ inline VertPlan plan_vert(const b200sgm_engine* h, const Eff& e)
     p.nstrips = n; p.twmax = tw;
     p.smem = vert_smem_bytes(tw, e.Dp, vert_ring(N));
     p.ok = p.smem <= smem_cap;
+    // Narrow strips (up to 128 disparities) sweep a row faster than a record crosses the L2: their agents advance the incoming
+    // diagonals through a halo of kHaloMax - 1 columns, which gives the records kHaloMax - 1 rows to arrive (k_vert's HALO).
+    // Needs the agents, strips wider than the halo, and room for the halo rings.  Only for narrow strips (a single frame spread
+    // over all SMs): wide strips are bound by their own work, and the halo's extra steps and C reads then cost more than the
+    // hand-over (1280x1024x128 MODE_HH on one lane: 1.115 -> 1.019 ms; four lanes of 16-column strips: 1053 -> 1011 frames/s).
+    static const bool halo_env = [] { const char* v = getenv("B200SGM_VERT_HALO"); return !v || atoi(v) != 0; }();
+    static const bool plain_agents = getenv("B200SGM_NO_AGENTS") == nullptr && getenv("B200SGM_DEBUG_VERT") == nullptr;
+    if (p.ok && N <= 2 && halo_env && plain_agents && kVertCps == 1 && !kVertTma && vert_ring(N) == VertCfg<N>::RING && n > 1 &&
+        e.W1 / n > kHaloMax && tw <= 10 && vert_threads(tw, true) + 64 <= VertCfg<N>::MAXT && vert_smem_bytes(tw, e.Dp, vert_ring(N), kHaloMax) <= smem_cap) {
+        p.halo = kHaloMax;
+        p.smem = vert_smem_bytes(tw, e.Dp, vert_ring(N), kHaloMax);
+    }
     return p;
 }
 
-template <int N, int RING, bool UP, bool DO_WTA, bool FULL, bool CLAMP_EACH>
+template <int N, int RING, bool UP, bool DO_WTA, bool FULL, bool CLAMP_EACH, int HALO = 1>
 int launch_vert_r(b200sgm_engine* h, Lane& ln, const Eff& e, const VertPlan& vp, cudaStream_t st)
 {
     VertGeom g;
@@ -90,7 +102,8 @@ int launch_vert_r(b200sgm_engine* h, Lane& ln, const Eff& e, const VertPlan& vp,
     int nthreads = vert_threads(vp.twmax, DO_WTA);
     { static const bool no_agents = getenv("B200SGM_NO_AGENTS") != nullptr; g.agents = (!no_agents && nthreads + 64 <= VertCfg<N>::MAXT) ? 1 : 0; }
     if (g.agents) nthreads += 64;
-    auto kern = k_vert<N, RING, UP, DO_WTA, FULL, CLAMP_EACH>;
+    auto kern = k_vert<N, RING, UP, DO_WTA, FULL, CLAMP_EACH, HALO>;
+    if (HALO > 1 && !g.agents) return fail(h, B200SGM_ECUDA, "internal: halo sweep planned without agents");
     {
         static std::atomic<unsigned long long> attr_done{0};   // per instantiation and device: raise the dynamic shared-memory limit once
         const unsigned long long bit = 1ull << (h->device & 63);
@@ -101,7 +114,7 @@ int launch_vert_r(b200sgm_engine* h, Lane& ln, const Eff& e, const VertPlan& vp,
             attr_done.fetch_or(bit);
         }
     }
-    CUDA_TRY(h, cudaMemsetAsync(ln.xbuf, 0, size_t(2) * vp.nstrips * kXbufGen * (e.Dp / 2) * sizeof(uint2), st));
+    CUDA_TRY(h, cudaMemsetAsync(ln.xbuf, 0, size_t(2) * vp.nstrips * (HALO > 1 ? kHaloGen : kXbufGen) * (e.Dp / 2) * sizeof(uint2), st));
     const uint16_t* Cp = ln.C; uint16_t* Sp = ln.S; int16_t* dp = ln.disp_wta; uint32_t* kp = ln.disp2key;
     uint2* xb = ln.xbuf; int* er = ln.d_err;
     void* args[] = {(void*)&Cp, (void*)&Sp, (void*)&g, (void*)&dp, (void*)&kp, (void*)&xb, (void*)&er};
@@ -141,6 +154,9 @@ int launch_vert_t(b200sgm_engine* h, Lane& ln, const Eff& e, const VertPlan& vp,
 {
     if constexpr (N <= 4) {
         if (vert_ring(N) == 4) return launch_vert_r<N, 4, UP, DO_WTA, FULL, CLAMP_EACH>(h, ln, e, vp, st);
+    }
+    if constexpr (N <= 2) {
+        if (vp.halo == kHaloMax) return launch_vert_r<N, VertCfg<N>::RING, UP, DO_WTA, FULL, CLAMP_EACH, kHaloMax>(h, ln, e, vp, st);
     }
     return launch_vert_r<N, VertCfg<N>::RING, UP, DO_WTA, FULL, CLAMP_EACH>(h, ln, e, vp, st);
 }

@@ -225,7 +225,7 @@ static int create_engine(int device, int max_width, int max_height, int max_disp
         if (!bm_only) {
             ok = ok && cudaMalloc(&ln.S, vol) == cudaSuccess;
             ok = ok && cudaMalloc(&ln.ckpt, horiz_ckpt_elems(max_width, max_height, int(Dp)) * sizeof(uint16_t)) == cudaSuccess;
-            ok = ok && cudaMalloc(&ln.xbuf, size_t(2) * kMaxStrips * kXbufGen * (Dp / 2) * sizeof(uint2)) == cudaSuccess;
+            ok = ok && cudaMalloc(&ln.xbuf, size_t(2) * kMaxStrips * kHaloGen * (Dp / 2) * sizeof(uint2)) == cudaSuccess;
         }
         ok = ok && cudaMalloc(&ln.disp2key, npix * 4) == cudaSuccess;
         ok = ok && cudaMalloc(&ln.disp_wta, npix * 2 + 16) == cudaSuccess && cudaMalloc(&ln.disp_med, npix * 2) == cudaSuccess && cudaMalloc(&ln.disp_out, npix * 2) == cudaSuccess;

@@ -536,6 +536,12 @@ struct VertGeom {
 // The consumer issues its record load at the TOP of the row and only inspects the tags right before it needs
 // the data, so in the common case (the neighbour is not late) the L2 round trip is off the critical path.
 constexpr int kXbufGen = 4;
+constexpr int kHaloGen = 16;      // record generations of a HALO > 1 sweep: a strip may run HALO rows ahead of a neighbour whose agent still
+                                  // needs a record HALO rows behind its own row (the records come from inner warps, which publish before
+                                  // their strip's edge warp has met its agent), so 2 * HALO + 1 generations are live at worst
+constexpr int kHaloRows = 8;      // rows of the agents' halo C rings
+constexpr int kHaloPF = 4;        // ... requested this many rows ahead
+constexpr int kHaloMax = 4;
 // RING (template parameter of k_vert) = rows of C and of S_h in flight per column (cp.async rings in shared memory): DRAM latency x
 // row rate.  The two rings have the same depth -- cp.async groups retire in order, so a shallower S_h ring would make its wait
 // drain the younger C requests as well.  8 up to 256 disparities, 4 beyond (a row is then at least twice the bytes).
@@ -555,9 +561,9 @@ constexpr int kVertCps = B200SGM_VERT_CPS;
 // the bound follows and ptxas gets 88+ registers for the N >= 8 row loops (they spilled at 72)
 constexpr int vert_max_threads(int n) { return kVertCps == 2 ? 448 : (n <= 4 ? B200SGM_VERT_MAXT : (n == 8 ? 704 : (n == 16 ? 384 : 256))); }
 constexpr int kRowUnroll = 4; // the row loop is unrolled by this: record generation, stage slot, parity are immediates
-__device__ __forceinline__ uint2* xrec(uint2* xbuf, int nstrips, int Dp, int side, int strip, int row)
+__device__ __forceinline__ uint2* xrec(uint2* xbuf, int nstrips, int Dp, int side, int strip, int row, int gens = kXbufGen)
 {
-    return xbuf + (size_t((side * nstrips + strip) * kXbufGen + (row & (kXbufGen - 1)))) * (Dp / 2);
+    return xbuf + (size_t((side * nstrips + strip) * gens + (row & (gens - 1)))) * (Dp / 2);
 }
 __device__ __forceinline__ void st_volatile_v2(uint2* p, uint32_t a, uint32_t b)
 {
@@ -583,12 +589,13 @@ __device__ __forceinline__ void named_bar_arrive(int id, int nthreads) { asm vol
 
 // dynamic smem: Ld[2 parity][2 dir][twmax+2][Dp] | Cring[twmax][RING][Dp] | Sring[twmax][RING][Dp] | stage[kStage][twmax][Dp]
 //               | xring[2 sides][kXbufGen][Dp]   (uint16)
-inline size_t vert_smem_bytes(int twmax, int Dp, int ring)
+inline size_t vert_smem_bytes(int twmax, int Dp, int ring, int halo = 1)
 {
     return (size_t(4) * (twmax + 2) + size_t(2 * ring + kStage) * twmax + 2 * kXbufGen) * Dp * sizeof(uint16_t)   // 190 KB at c3
+           + (halo > 1 ? size_t(2) * kHaloRows * (halo - 1) * Dp * sizeof(uint16_t) : 0)                             // + the agents' halo C rings [side][row][column]
            + (kVertTma ? size_t(ring) * sizeof(uint64_t) : 0)                                                        // + the ring's mbarriers
            + size_t(2) * kStage * ((twmax + kWC - 1) / kWC) * sizeof(uint64_t)                                       // + full/empty per WTA warp and slot
-           + sizeof(uint64_t);                                                                                       // + the split-phase row barrier
+           + 2 * sizeof(uint64_t);                                                                                   // + the split-phase row barrier (padded to 16 bytes)
 }
 
 // Warp-specialised vertical sweep.  Launch: 32 * twmax threads when !DO_WTA, else 64 * twmax:
@@ -605,7 +612,12 @@ inline size_t vert_smem_bytes(int twmax, int Dp, int ring)
 // pairs an agent with its edge warp once per row.
 // FULL      : Dp == D == 64*N (no padded cells, every lane active)
 // CLAMP_EACH: saturate after every addition of the sum (needed when the 16-bit sum of the terms could wrap)
-template <int N, int RING, bool UP, bool DO_WTA, bool FULL, bool CLAMP_EACH>
+// HALO      : 1 = a strip's edge column takes its incoming diagonal state from the neighbour's record of the previous row (one L2
+//             hand-over per row: the floor of the row time of narrow strips).  HALO = h > 1: the neighbour publishes the state
+//             of the column h columns inside its edge, and the agent advances that diagonal chain through the h - 1 columns in
+//             between itself (their C read a second time, by the agent): the record is then needed h - 1 rows after it was
+//             written, and neighbouring strips may drift h - 1 rows apart.
+template <int N, int RING, bool UP, bool DO_WTA, bool FULL, bool CLAMP_EACH, int HALO = 1>
 __global__ void __launch_bounds__(vert_max_threads(N), kVertCps) k_vert(const uint16_t* __restrict__ Cvol, uint16_t* __restrict__ Svol, VertGeom g,
                                                   int16_t* __restrict__ disp, uint32_t* __restrict__ disp2key,
                                                   uint2* __restrict__ xbuf, int* __restrict__ err)
@@ -638,6 +650,9 @@ __global__ void __launch_bounds__(vert_max_threads(N), kVertCps) k_vert(const ui
     uint64_t* fullbar = ringbar + (kVertTma ? RING : 0);
     uint64_t* emptybar = fullbar + nwta * kStage;
     uint64_t* rowbar = emptybar + nwta * kStage;          // SPLIT: one arrival per path warp and agent of the strip and row
+    uint16_t* haloring = reinterpret_cast<uint16_t*>(rowbar + 2);       // HALO > 1: [side][kHaloRows][HALO - 1][Dp] (16-byte aligned)
+    constexpr int XG = HALO > 1 ? kHaloGen : kXbufGen;                  // record generations
+    static_assert(HALO >= 1 && HALO <= kHaloMax && kHaloRows >= kHaloPF + HALO, "halo ring depth");
     if (kVertTma && threadIdx.x == 0) {
 #pragma unroll
         for (int i = 0; i < RING; i++) mbar_init(ringbar + i, 1);
@@ -677,10 +692,92 @@ __global__ void __launch_bounds__(vert_max_threads(N), kVertCps) k_vert(const ui
         // ================================ agent warps ================================
         const int side = w - agent_base;                     // 0: left neighbour (feeds warp 0), 1: right neighbour (feeds warp TW-1)
         if (!g.agents || !exchange_on || (side == 0 ? b == 0 : b == n - 1)) return;
-        const uint2* rec0 = xrec(xbuf, n, Dp, side, side == 0 ? b - 1 : b + 1, 0) + lane * N;
+        const uint2* rec0 = xrec(xbuf, n, Dp, side, side == 0 ? b - 1 : b + 1, 0, XG) + lane * N;
         uint16_t* dst = xringbase + size_t(side) * kXbufGen * Dp + lane * 2 * N;
         const int gen_stride = Dp / 2;
         bool dead = false;
+        // ---- HALO > 1: the diagonal chain that enters the strip at row i + 1 is seeded with the neighbour's record of row
+        // i - HALO + 1 (state of the column HALO columns outside the edge column) and advanced here through the HALO - 1 columns
+        // in between; halo_V(i) = its state one column outside the edge column at row i = what the HALO = 1 record of row i holds.
+        const int xe = side == 0 ? x0 : x1e - 1;                               // edge column (of the volume)
+        const int hdir = side == 0 ? 1 : -1;                                   // the chain moves this way, one column per row
+        uint16_t* hring = haloring + size_t(side) * kHaloRows * (HALO - 1) * Dp + lane * 2 * N;
+        const uint16_t* gHalo = Cvol + (size_t(UP ? H - 1 : 0) * W1 + (xe - hdir * (HALO - 1))) * Dp + lane * 2 * N;   // halo column k = 1, next row to request
+        const ptrdiff_t hRowStride = (UP ? -1 : 1) * ptrdiff_t(W1) * Dp;
+        auto halo_issue = [&](int row_) {
+            if (HALO > 1) {
+                if (row_ < H && active) {
+#pragma unroll
+                    for (int k = 1; k < HALO; k++)
+                        cp_async_lane<N>(hring + ((row_ & (kHaloRows - 1)) * (HALO - 1) + (k - 1)) * Dp, gHalo + ptrdiff_t(hdir * (k - 1)) * Dp);
+                }
+                gHalo += hRowStride;
+                cp_async_commit();
+            }
+        };
+        // the seed of halo_V(i + 1) is requested at the end of halo_V(i): it was published two rows ago, its L2 round trip then
+        // overlaps the agent's other work instead of heading the next chain
+        uint2 hpre[N];
+#pragma unroll
+        for (int q = 0; q < N; q++) hpre[q] = make_uint2(0u, 0u);
+        auto halo_prefetch = [&](int i) {       // seed record of halo_V(i)
+            const int rho0 = i - (HALO - 1);
+            if (HALO > 1 && rho0 >= 0 && i + 1 < H && active) {
+                const uint2* rec = rec0 + (rho0 & (XG - 1)) * gen_stride;
+#pragma unroll
+                for (int q = 0; q < N; q++) hpre[q] = ld_volatile_v2(rec + q);
+            }
+        };
+        auto halo_V = [&](int i, uint32_t (&St)[N]) {
+#pragma unroll
+            for (int q = 0; q < N; q++) St[q] = 0;
+            const int rho0 = i - (HALO - 1);
+            int k0 = 1;
+            if (rho0 >= 0) {
+                if (active && !dead) {
+                    bool ok = true;
+#pragma unroll
+                    for (int q = 0; q < N; q++) { St[q] = hpre[q].x; ok = ok && hpre[q].y == uint32_t(rho0 + 1); }
+                    if (!ok) {
+                        const uint2* rec = rec0 + (rho0 & (XG - 1)) * gen_stride;
+                        const long long t0 = clock64();
+                        int spins = 0;
+                        while (true) {
+                            ok = true;
+#pragma unroll
+                            for (int q = 0; q < N; q++) {
+                                uint2 v = ld_volatile_v2(rec + q);
+                                St[q] = v.x;
+                                ok = ok && v.y == uint32_t(rho0 + 1);
+                            }
+                            if (ok) break;
+                            if ((++spins & 255) == 0 && (clock64() - t0 > g.spin_limit || *reinterpret_cast<volatile int*>(err))) {
+                                atomicExch(err, 1);
+                                dead = true;
+                                break;
+                            }
+                        }
+                    }
+                }
+                dead = __any_sync(kFullMask, dead);
+            } else {
+                k0 = -rho0;                   // the chain starts at the first row of the sweep, from "outside the image"
+            }
+            halo_prefetch(i + 1);
+            cp_async_wait<kHaloPF>();         // the halo rows up to row i have landed (each lane reads only its own bytes)
+#pragma unroll
+            for (int k = 1; k < HALO; k++) {
+                if (k >= k0) {
+                    uint32_t Ch[N], Lh[N];
+                    if (active) ld_regs<N>(hring + (((rho0 + k) & (kHaloRows - 1)) * (HALO - 1) + (k - 1)) * Dp, Ch);
+                    else {
+#pragma unroll
+                        for (int q = 0; q < N; q++) Ch[q] = kMaxCostX2;
+                    }
+                    path_step<N>(Ch, St, Lh, lc);
+                }
+            }
+        };
         if (DO_WTA) {
             // The agent OWNS the edge column's incoming-diagonal path (the one step of the row that depends on the
             // neighbour strip): record of row r-1 -> path update with C(r) from the column's cp.async ring -> new state for
@@ -693,6 +790,43 @@ __global__ void __launch_bounds__(vert_max_threads(N), kVertCps) k_vert(const ui
             const uint16_t* cring = ringbase + size_t(je) * ringColStride + lane * 2 * N;
             uint16_t* sB = dst;                                                              // stageB[side][kStage][Dp] aliases the xring
             if (!kVertTma) asm volatile("bar.sync 1, %0;" ::"r"(nrow_a) : "memory");           // C(0) is visible
+            if constexpr (HALO > 1) {
+                static_assert(!VertPolicy<N>::SPLIT_ROW && !kVertTma, "halo agents: named row barrier, cp.async rings");
+                uint32_t Vp[N];                     // state one column outside the edge column at row r - 1 (zero: outside the image)
+#pragma unroll
+                for (int q = 0; q < N; q++) Vp[q] = 0;
+#pragma unroll
+                for (int i = 0; i < kHaloPF; i++) halo_issue(i);
+                uint64_t* fbh = fullbar + (je / kWC) * kStage;
+                uint64_t* ebh = emptybar + (je / kWC) * kStage;
+                for (int r = 0; r < H; r++) {
+                    halo_issue(r + kHaloPF);
+                    uint32_t Cc[N], Ln[N];
+                    if (active) ld_regs<N>(cring + (r & (RING - 1)) * ringSlotStride, Cc);
+                    else {
+#pragma unroll
+                        for (int q = 0; q < N; q++) Cc[q] = kMaxCostX2;
+                    }
+                    path_step<N>(Cc, Vp, Ln, lc);                       // the edge column's incoming-diagonal step of row r
+                    if (active) st_regs<N>(wr + (r & 1) * (2 * slots * Dp), Vp);
+                    const int q4 = r & (kStage - 1);
+                    if (kVertMbar) {
+                        if (r >= kStage) mbar_wait_b(ebh + q4, ((r >> 2) + 1) & 1, err);
+                        if (active) st_regs<N>(sB + q4 * Dp, Ln);
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(fbh + q4);
+                    } else {
+                        if (!FOLD && r >= kStage) named_bar_sync(BAR_EMPTY + q4, nfe_a);
+                        if (active) st_regs<N>(sB + q4 * Dp, Ln);
+                        named_bar_arrive(BAR_FULL + q4, nfe_a);
+                    }
+                    if (r + 1 < H) halo_V(r, Vp);                      // for the next row: off the strip's critical path
+                    if (FOLD && (r & 1)) named_bar_sync(BAR_ROWX + ((r >> 1) & 1), r >= 3 ? nfe_a : nrow_a);
+                    else asm volatile("bar.sync 1, %0;" ::"r"(nrow_a) : "memory");             // BAR_ROW of row r
+                }
+                cp_async_wait<0>();
+                return;
+            }
             // the record of row r - 1 is requested at the END of row r - 1 (the neighbour published it early in its own row
             // r - 1), so that its L2 round trip overlaps the row barrier instead of heading this warp's row
             uint2 pre[N];
@@ -762,6 +896,19 @@ __global__ void __launch_bounds__(vert_max_threads(N), kVertCps) k_vert(const ui
                 if (FOLD && (r & 1)) named_bar_sync(BAR_ROWX + ((r >> 1) & 1), r >= 3 ? nfe_a : nrow_a);
                 else if (!SPLIT) asm volatile("bar.sync 1, %0;" ::"r"(nrow_a) : "memory");     // BAR_ROW of row r
             }
+            return;
+        }
+        if constexpr (HALO > 1) {
+#pragma unroll
+            for (int i = 0; i < kHaloPF; i++) halo_issue(i);
+            for (int i = 0; i + 1 < H; i++) {                // state for the edge warp's row i + 1
+                halo_issue(i + kHaloPF);
+                uint32_t d[N];
+                halo_V(i, d);
+                if (active) st_regs<N>(dst + (i & (kXbufGen - 1)) * Dp, d);
+                named_bar_sync(BAR_HALO + side, 64);
+            }
+            cp_async_wait<0>();
             return;
         }
         for (int i = 0; i + 1 < H; i++) {                    // record of row i: consumed by the edge warp in its row i + 1
@@ -952,6 +1099,12 @@ __global__ void __launch_bounds__(vert_max_threads(N), kVertCps) k_vert(const ui
     // exchange records: I publish side dirA of my strip, I consume side dirB of the neighbour
     const int nb = dirB == 0 ? b - 1 : b + 1;
     uint2* pub_base = xrec(xbuf, n, Dp, dirA, b, 0) + lane * N;
+    // HALO > 1: the records come from the columns HALO columns inside the strip's edges (inner warps: step A is their
+    // from-the-left step, step B their from-the-right step); the host guarantees TW > HALO
+    const bool pubA = HALO > 1 && exchange_on && g.agents && b < n - 1 && j == TW - HALO;
+    const bool pubB = HALO > 1 && exchange_on && g.agents && b > 0 && j == HALO - 1;
+    uint2* pubA_base = xrec(xbuf, n, Dp, 0, b, 0, XG) + lane * N;
+    uint2* pubB_base = xrec(xbuf, n, Dp, 1, b, 0, XG) + lane * N;
     const uint2* con_base = xrec(xbuf, n, Dp, dirB, edge ? nb : b, 0) + lane * N;
     const int gen_stride = Dp / 2;
 
@@ -1040,12 +1193,17 @@ __global__ void __launch_bounds__(vert_max_threads(N), kVertCps) k_vert(const ui
         // ---- step A (the direction this warp publishes)
         path_step<N>(Cc, LtA, LnA, lc);
         if (active) st_regs<N>(wrA[PAR], LtA);
-        if (EDGE) {
+        if (EDGE && HALO == 1) {
             if (active) {
                 uint2* rec = pub_base + Q * gen_stride;
 #pragma unroll
                 for (int q = 0; q < N; q++) st_volatile_v2(rec + q, LtA[q], uint32_t(r + 1));
             }
+        }
+        if (HALO > 1 && pubA && active) {
+            uint2* rec = pubA_base + (r & (XG - 1)) * gen_stride;
+#pragma unroll
+            for (int q = 0; q < N; q++) st_volatile_v2(rec + q, LtA[q], uint32_t(r + 1));
         }
         // ---- vertical path: registers only (SPLIT: after the row's arrival, nobody waits for it)
         if (!SPLIT) path_step<N>(Cc, LtV, LnV, lc);
@@ -1101,6 +1259,11 @@ __global__ void __launch_bounds__(vert_max_threads(N), kVertCps) k_vert(const ui
         if (!NO_B) {
             path_step<N>(Cc, LtB, LnB, lc);
             if (active) st_regs<N>(wrB[PAR], LtB);
+            if (HALO > 1 && pubB && active) {
+                uint2* rec = pubB_base + (r & (XG - 1)) * gen_stride;
+#pragma unroll
+                for (int q = 0; q < N; q++) st_volatile_v2(rec + q, LtB[q], uint32_t(r + 1));
+            }
         } else {
 #pragma unroll
             for (int q = 0; q < N; q++) LnB[q] = 0;
