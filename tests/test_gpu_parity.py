@@ -219,6 +219,24 @@ def test_wide_disparity_ranges_on_the_fused_path():
             assert np.array_equal(run_gpu(L, R, q), oracle.compute(L, R, q)), (W, H, D, minD, bs, mode)
 
 
+def test_halo_agents_on_narrow_strips():
+    """Strips of 5 to 10 columns up to 128 disparities run the vertical sweep with halo agents (the neighbour's record is used three
+    rows after it was written, strips drift apart): both modes, few and many rows, widths either side of the eligibility limits,
+    a one-lane and a several-lane engine (whose strips are wide: no halo) must agree with the oracle and with each other."""
+    for W, H, D, minD in [(900, 37, 64, 0), (1000, 150, 128, 3), (1290, 9, 64, -8), (1560, 64, 32, 0), (820, 5, 64, 0), (1700, 3, 128, 0)]:
+        p = SGBMParams(minDisparity=minD, numDisparities=D, P1=24, P2=96, uniquenessRatio=5)
+        L, R = synth.make_pair(W, H, D, minD, 900 + W)
+        for mode in (0, 1):
+            q = p.replace(mode=mode)
+            want = oracle.compute(L, R, q)
+            assert np.array_equal(run_gpu(L, R, q), want), (W, H, D, minD, mode)
+            eng = Engine(0, W, H, D, 3, q)
+            try:
+                assert np.array_equal(eng.compute(L, R), want), ("3 lanes", W, H, D, minD, mode)
+            finally:
+                eng.close()
+
+
 def test_cost_range_warning_and_lane_status():
     """int16 contract guard: a frame whose largest cost-volume cell + P2 exceeds 32767 is delivered with a warning
     (B200SGM_WARN_COST_RANGE) -- uncorrelated noise through a 21x21 window at the launch-default cap; the same images
