@@ -78,7 +78,8 @@ inline VertPlan plan_vert(const b200sgm_engine* h, const Eff& e)
     // diagonals through a halo of kHaloMax - 1 columns, which gives the records kHaloMax - 1 rows to arrive (k_vert's HALO).
     // Needs the agents, strips wider than the halo, and room for the halo rings.  Only for narrow strips (a single frame spread
     // over all SMs): wide strips are bound by their own work, and the halo's extra steps and C reads then cost more than the
-    // hand-over (1280x1024x128 MODE_HH on one lane: 1.115 -> 1.019 ms; four lanes of 16-column strips: 1053 -> 1011 frames/s).
+    // hand-over (1280x1024x128 MODE_HH on one lane: 1.115 -> 0.956 ms with a halo of 3, 1.019 with 4, 1.025 with 2; four lanes of
+    // 16-column strips: 1053 -> 1011 frames/s).
     static const bool halo_env = [] { const char* v = getenv("B200SGM_VERT_HALO"); return !v || atoi(v) != 0; }();
     static const bool plain_agents = getenv("B200SGM_NO_AGENTS") == nullptr && getenv("B200SGM_DEBUG_VERT") == nullptr;
     if (p.ok && N <= 2 && halo_env && plain_agents && kVertCps == 1 && !kVertTma && vert_ring(N) == VertCfg<N>::RING && n > 1 &&

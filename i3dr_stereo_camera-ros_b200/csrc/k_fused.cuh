@@ -541,7 +541,7 @@ constexpr int kHaloGen = 16;      // record generations of a HALO > 1 sweep: a s
                                   // their strip's edge warp has met its agent), so 2 * HALO + 1 generations are live at worst
 constexpr int kHaloRows = 8;      // rows of the agents' halo C rings
 constexpr int kHaloPF = 4;        // ... requested this many rows ahead
-constexpr int kHaloMax = 4;
+constexpr int kHaloMax = 3;
 // RING (template parameter of k_vert) = rows of C and of S_h in flight per column (cp.async rings in shared memory): DRAM latency x
 // row rate.  The two rings have the same depth -- cp.async groups retire in order, so a shallower S_h ring would make its wait
 // drain the younger C requests as well.  8 up to 256 disparities, 4 beyond (a row is then at least twice the bytes).
