@@ -78,12 +78,12 @@ inline VertPlan plan_vert(const b200sgm_engine* h, const Eff& e)
     // diagonals through a halo of kHaloMax - 1 columns, which gives the records kHaloMax - 1 rows to arrive (k_vert's HALO).
     // Needs the agents, strips wider than the halo, and room for the halo rings.  Only for narrow strips (a single frame spread
     // over all SMs): wide strips are bound by their own work, and the halo's extra steps and C reads then cost more than the
-    // hand-over (1280x1024x128 MODE_HH on one lane: 1.115 -> 0.956 ms with a halo of 3, 1.019 with 4, 1.025 with 2; four lanes of
-    // 16-column strips: 1053 -> 1011 frames/s).
+    // hand-over (1280x1024x128 MODE_HH on one lane: 1.115 -> 0.834 ms; four lanes of 16-column strips: 1050 -> 970 frames/s).
     static const bool halo_env = [] { const char* v = getenv("B200SGM_VERT_HALO"); return !v || atoi(v) != 0; }();
+    static const int halo_tw = [] { const char* v = getenv("B200SGM_VERT_HALO_TW"); return v ? atoi(v) : 10; }();   // widest strip that gets halo agents
     static const bool plain_agents = getenv("B200SGM_NO_AGENTS") == nullptr && getenv("B200SGM_DEBUG_VERT") == nullptr;
     if (p.ok && N <= 2 && halo_env && plain_agents && kVertCps == 1 && !kVertTma && vert_ring(N) == VertCfg<N>::RING && n > 1 &&
-        e.W1 / n > kHaloMax && tw <= 10 && vert_threads(tw, true) + 64 <= VertCfg<N>::MAXT && vert_smem_bytes(tw, e.Dp, vert_ring(N), kHaloMax) <= smem_cap) {
+        e.W1 / n > kHaloMax && tw <= halo_tw && vert_threads(tw, true) + 192 <= VertCfg<N>::MAXT && vert_smem_bytes(tw, e.Dp, vert_ring(N), kHaloMax) <= smem_cap) {
         p.halo = kHaloMax;
         p.smem = vert_smem_bytes(tw, e.Dp, vert_ring(N), kHaloMax);
     }
@@ -103,6 +103,7 @@ int launch_vert_r(b200sgm_engine* h, Lane& ln, const Eff& e, const VertPlan& vp,
     int nthreads = vert_threads(vp.twmax, DO_WTA);
     { static const bool no_agents = getenv("B200SGM_NO_AGENTS") != nullptr; g.agents = (!no_agents && nthreads + 64 <= VertCfg<N>::MAXT) ? 1 : 0; }
     if (g.agents) nthreads += 64;
+    if (HALO > 1) nthreads += 128;                 // the four halo producers
     auto kern = k_vert<N, RING, UP, DO_WTA, FULL, CLAMP_EACH, HALO>;
     if (HALO > 1 && !g.agents) return fail(h, B200SGM_ECUDA, "internal: halo sweep planned without agents");
     {

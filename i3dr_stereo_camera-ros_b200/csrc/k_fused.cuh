@@ -541,7 +541,7 @@ constexpr int kHaloGen = 16;      // record generations of a HALO > 1 sweep: a s
                                   // their strip's edge warp has met its agent), so 2 * HALO + 1 generations are live at worst
 constexpr int kHaloRows = 8;      // rows of the agents' halo C rings
 constexpr int kHaloPF = 4;        // ... requested this many rows ahead
-constexpr int kHaloMax = 3;
+constexpr int kHaloMax = 4;
 // RING (template parameter of k_vert) = rows of C and of S_h in flight per column (cp.async rings in shared memory): DRAM latency x
 // row rate.  The two rings have the same depth -- cp.async groups retire in order, so a shallower S_h ring would make its wait
 // drain the younger C requests as well.  8 up to 256 disparities, 4 beyond (a row is then at least twice the bytes).
@@ -592,7 +592,8 @@ __device__ __forceinline__ void named_bar_arrive(int id, int nthreads) { asm vol
 inline size_t vert_smem_bytes(int twmax, int Dp, int ring, int halo = 1)
 {
     return (size_t(4) * (twmax + 2) + size_t(2 * ring + kStage) * twmax + 2 * kXbufGen) * Dp * sizeof(uint16_t)   // 190 KB at c3
-           + (halo > 1 ? size_t(2) * kHaloRows * (halo - 1) * Dp * sizeof(uint16_t) : 0)                             // + the agents' halo C rings [side][row][column]
+           + (halo > 1 ? size_t(4) * kHaloRows * (halo - 1) * Dp * sizeof(uint16_t) : 0)                             // + the halo producers' C rings [side][producer][row][column]
+           + (halo > 1 ? size_t(2) * kXbufGen * Dp * sizeof(uint16_t) : 0)                                          // + their hand-over ring [side][row & 3]
            + (kVertTma ? size_t(ring) * sizeof(uint64_t) : 0)                                                        // + the ring's mbarriers
            + size_t(2) * kStage * ((twmax + kWC - 1) / kWC) * sizeof(uint64_t)                                       // + full/empty per WTA warp and slot
            + 2 * sizeof(uint64_t);                                                                                   // + the split-phase row barrier (padded to 16 bytes)
@@ -690,8 +691,19 @@ __global__ void __launch_bounds__(vert_max_threads(N), kVertCps) k_vert(const ui
     constexpr int BAR_ROWX = BAR_EMPTY;
     if (w >= agent_base) {
         // ================================ agent warps ================================
-        const int side = w - agent_base;                     // 0: left neighbour (feeds warp 0), 1: right neighbour (feeds warp TW-1)
+        // agent warps 0, 1: one per side (0: left neighbour, feeds warp 0; 1: right neighbour, feeds warp TW-1).  HALO > 1 launches
+        // four more, the halo PRODUCERS (two per side, alternating rows): they advance the incoming diagonal chains through the
+        // halo on their own clock and hand the result over through a 4-row ring and a 64-thread named barrier, so that the
+        // chain's serial latency is off the strip's row time; agents 0, 1 keep the edge column's own step (WTA sweeps).
+        const int aw = w - agent_base;
+        const bool producer_role = HALO > 1 && aw >= 2;
+        const int side = producer_role ? (aw - 2) >> 1 : aw;
+        const int prod = producer_role ? (aw - 2) & 1 : 0;
         if (!g.agents || !exchange_on || (side == 0 ? b == 0 : b == n - 1)) return;
+        if (HALO > 1 && !DO_WTA && !producer_role) return;      // sweeps without WTA: the edge path warp consumes the producers' ring itself
+        constexpr int BAR_HB = 8;                                // + 2 * side + producer (ids 8 .. 11; 10, 11 = BAR_HALO, unused by HALO > 1 sweeps)
+        uint16_t* vring = (DO_WTA ? haloring + size_t(4) * kHaloRows * (HALO - 1) * Dp + size_t(side) * kXbufGen * Dp
+                                  : xringbase + size_t(side) * kXbufGen * Dp) + lane * 2 * N;
         const uint2* rec0 = xrec(xbuf, n, Dp, side, side == 0 ? b - 1 : b + 1, 0, XG) + lane * N;
         uint16_t* dst = xringbase + size_t(side) * kXbufGen * Dp + lane * 2 * N;
         const int gen_stride = Dp / 2;
@@ -701,7 +713,7 @@ __global__ void __launch_bounds__(vert_max_threads(N), kVertCps) k_vert(const ui
         // in between; halo_V(i) = its state one column outside the edge column at row i = what the HALO = 1 record of row i holds.
         const int xe = side == 0 ? x0 : x1e - 1;                               // edge column (of the volume)
         const int hdir = side == 0 ? 1 : -1;                                   // the chain moves this way, one column per row
-        uint16_t* hring = haloring + size_t(side) * kHaloRows * (HALO - 1) * Dp + lane * 2 * N;
+        uint16_t* hring = haloring + size_t(2 * side + prod) * kHaloRows * (HALO - 1) * Dp + lane * 2 * N;
         const uint16_t* gHalo = Cvol + (size_t(UP ? H - 1 : 0) * W1 + (xe - hdir * (HALO - 1))) * Dp + lane * 2 * N;   // halo column k = 1, next row to request
         const ptrdiff_t hRowStride = (UP ? -1 : 1) * ptrdiff_t(W1) * Dp;
         auto halo_issue = [&](int row_) {
@@ -728,7 +740,7 @@ __global__ void __launch_bounds__(vert_max_threads(N), kVertCps) k_vert(const ui
                 for (int q = 0; q < N; q++) hpre[q] = ld_volatile_v2(rec + q);
             }
         };
-        auto halo_V = [&](int i, uint32_t (&St)[N]) {
+        auto halo_V = [&](int i, int inext, uint32_t (&St)[N]) {
 #pragma unroll
             for (int q = 0; q < N; q++) St[q] = 0;
             const int rho0 = i - (HALO - 1);
@@ -763,7 +775,7 @@ __global__ void __launch_bounds__(vert_max_threads(N), kVertCps) k_vert(const ui
             } else {
                 k0 = -rho0;                   // the chain starts at the first row of the sweep, from "outside the image"
             }
-            halo_prefetch(i + 1);
+            halo_prefetch(inext);
             cp_async_wait<kHaloPF>();         // the halo rows up to row i have landed (each lane reads only its own bytes)
 #pragma unroll
             for (int k = 1; k < HALO; k++) {
@@ -778,6 +790,18 @@ __global__ void __launch_bounds__(vert_max_threads(N), kVertCps) k_vert(const ui
                 }
             }
         };
+        if (producer_role) {
+            int next = 0;
+            for (int i = prod; i + 1 < H; i += 2) {              // state for the strip's row i + 1
+                while (next <= i + kHaloPF) halo_issue(next++);  // kHaloPF groups newer than halo row i in flight
+                uint32_t St[N];
+                halo_V(i, i + 2, St);
+                if (active) st_regs<N>(vring + (i & (kXbufGen - 1)) * Dp, St);
+                named_bar_sync(BAR_HB + 2 * side + prod, 64);    // meets the consumer at the top of row i + 1
+            }
+            cp_async_wait<0>();
+            return;
+        }
         if (DO_WTA) {
             // The agent OWNS the edge column's incoming-diagonal path (the one step of the row that depends on the
             // neighbour strip): record of row r-1 -> path update with C(r) from the column's cp.async ring -> new state for
@@ -795,12 +819,13 @@ __global__ void __launch_bounds__(vert_max_threads(N), kVertCps) k_vert(const ui
                 uint32_t Vp[N];                     // state one column outside the edge column at row r - 1 (zero: outside the image)
 #pragma unroll
                 for (int q = 0; q < N; q++) Vp[q] = 0;
-#pragma unroll
-                for (int i = 0; i < kHaloPF; i++) halo_issue(i);
                 uint64_t* fbh = fullbar + (je / kWC) * kStage;
                 uint64_t* ebh = emptybar + (je / kWC) * kStage;
                 for (int r = 0; r < H; r++) {
-                    halo_issue(r + kHaloPF);
+                    if (r > 0) {
+                        named_bar_sync(BAR_HB + 2 * side + ((r - 1) & 1), 64);        // the producer of row r - 1 has delivered
+                        if (active) ld_regs<N>(vring + ((r - 1) & (kXbufGen - 1)) * Dp, Vp);
+                    }
                     uint32_t Cc[N], Ln[N];
                     if (active) ld_regs<N>(cring + (r & (RING - 1)) * ringSlotStride, Cc);
                     else {
@@ -820,7 +845,6 @@ __global__ void __launch_bounds__(vert_max_threads(N), kVertCps) k_vert(const ui
                         if (active) st_regs<N>(sB + q4 * Dp, Ln);
                         named_bar_arrive(BAR_FULL + q4, nfe_a);
                     }
-                    if (r + 1 < H) halo_V(r, Vp);                      // for the next row: off the strip's critical path
                     if (FOLD && (r & 1)) named_bar_sync(BAR_ROWX + ((r >> 1) & 1), r >= 3 ? nfe_a : nrow_a);
                     else asm volatile("bar.sync 1, %0;" ::"r"(nrow_a) : "memory");             // BAR_ROW of row r
                 }
@@ -896,19 +920,6 @@ __global__ void __launch_bounds__(vert_max_threads(N), kVertCps) k_vert(const ui
                 if (FOLD && (r & 1)) named_bar_sync(BAR_ROWX + ((r >> 1) & 1), r >= 3 ? nfe_a : nrow_a);
                 else if (!SPLIT) asm volatile("bar.sync 1, %0;" ::"r"(nrow_a) : "memory");     // BAR_ROW of row r
             }
-            return;
-        }
-        if constexpr (HALO > 1) {
-#pragma unroll
-            for (int i = 0; i < kHaloPF; i++) halo_issue(i);
-            for (int i = 0; i + 1 < H; i++) {                // state for the edge warp's row i + 1
-                halo_issue(i + kHaloPF);
-                uint32_t d[N];
-                halo_V(i, d);
-                if (active) st_regs<N>(dst + (i & (kXbufGen - 1)) * Dp, d);
-                named_bar_sync(BAR_HALO + side, 64);
-            }
-            cp_async_wait<0>();
             return;
         }
         for (int i = 0; i + 1 < H; i++) {                    // record of row i: consumed by the edge warp in its row i + 1
@@ -1210,7 +1221,8 @@ __global__ void __launch_bounds__(vert_max_threads(N), kVertCps) k_vert(const ui
         // ---- step B
         if (EDGE && !NO_B) {
             if (consume && EMODE == 2) {
-                named_bar_sync(halo_bar, 64);          // my agent has dropped the record of row r-1 into shared memory
+                // my agent (HALO > 1: the halo producer of row r - 1) has dropped the state of row r - 1 into shared memory
+                named_bar_sync(HALO > 1 ? 8 + 2 * (j == 0 ? 0 : 1) + ((Q & 1) ^ 1) : halo_bar, 64);
                 if (active) ld_regs<N>(xin + ((Q + kXbufGen - 1) & (kXbufGen - 1)) * Dp, LtB);
                 else {
 #pragma unroll
