@@ -68,6 +68,10 @@ inline VertPlan plan_vert(const b200sgm_engine* h, const Eff& e)
     const int K = wide ? 1 : std::max(1, slots / std::max(1, nmin));
     int n = std::min(slots / K, e.W1 / 2);
     n = std::max(1, std::min(n, kMaxStrips));
+    // strips too narrow for the halo producers (below): somewhat fewer strips make every strip kHaloMax + 1 columns wide -- a
+    // narrow sweep is bound by the hand-over between strips, not by the SMs it leaves idle
+    static const bool halo_fit_env = [] { const char* v = getenv("B200SGM_VERT_HALO_FIT"); return !v || atoi(v) != 0; }();
+    if (N <= 2 && halo_fit_env && n > 1 && e.W1 / n <= kHaloMax && e.W1 / (kHaloMax + 1) * 4 >= n * 3) n = e.W1 / (kHaloMax + 1);
     int tw = (e.W1 + n - 1) / n;
     // wider than one co-resident wave of strips (or than a CTA has warps): use the hybrid path
     if (tw > kVertMaxWarps || vert_threads(tw, true) > VertCfg<N>::MAXT) return p;
