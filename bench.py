@@ -630,6 +630,22 @@ def side_config(torch, dev, cfg, alu_peak, hbm_peak, frames=8, lanes=4, reps=4):
         torch.cuda.synchronize()
         refs, kind = reference_outputs(cfg, pairs, os.cpu_count() or 1)
         got = dD.cpu().numpy()
+        # one frame on its own on a ONE-lane engine (what the plugin adapter creates): its sweeps take all SMs, narrow strips
+        # use the halo producers; checked against the same reference
+        eng1 = b200sgm.Engine(dev.index or 0, W, H, D, 1, p)
+        try:
+            d1 = torch.empty((H, W), dtype=torch.int16, device=dev)
+            eng1.compute_device(0, dL[0].data_ptr(), W, dR[0].data_ptr(), W, W, H, d1.data_ptr(), W * 2, stream=0)
+            torch.cuda.synchronize()
+            eng1.profile(True); eng1.stage_times(0)
+            for i in range(frames):
+                eng1.compute_device(0, dL[i].data_ptr(), W, dR[i].data_ptr(), W, W, H, d1.data_ptr(), W * 2, stream=0)
+            torch.cuda.synchronize()
+            st1, n1 = eng1.stage_times(0)
+            out["one_lane_engine_ms"] = sum(st1.values()) / max(n1, 1)
+            out["one_lane_engine_ok"] = bool(np.array_equal(d1.cpu().numpy(), refs[frames - 1]))
+        finally:
+            eng1.close()
         out.update({"frames_per_s": 1e3 / ms, "ms_per_frame_pipelined": ms, "stage_ms_per_frame": stages, "single_lane_ms": frame_ms,
                     "roofline": {"bound": "alu", "achieved": tops, "peak": alu_peak, "unit": "Tops/s (elementary int16 ops)",
                                  "frac": tops / alu_peak if alu_peak else None, "traffic": traffic,

@@ -1,4 +1,9 @@
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/rf_gputest.log 2>&1; echo RC=$? >> gpurun_out/rf_gputest.log
-tail -3 gpurun_out/rf_gputest.log
-(echo "halo-fit strips:"; timeout 500 python tools/fuzz_parity.py 400 701 2>&1 | tail -1; timeout 300 python tools/fuzz_sequence.py 120 2>&1 | tail -1) | tee gpurun_out/r2_fuzz7.txt
+python bench.py --no-cpu-baseline > gpurun_out/rl_bench.json 2> gpurun_out/rl_bench.err; echo rc=$?
+tail -c 300 gpurun_out/rl_bench.err
+python - <<'P'
+import json
+d=json.load(open('gpurun_out/rl_bench.json'))
+print(d['value'], d['parity_frames_ok'])
+for k,v in d['configs'].items(): print(k, v.get('frames_per_s'), v.get('single_lane_ms'), v.get('one_lane_engine_ms'), v.get('one_lane_engine_ok'), v.get('parity_frames_ok'))
+P
