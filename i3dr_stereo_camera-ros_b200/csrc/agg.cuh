@@ -82,7 +82,8 @@ inline VertPlan plan_vert(const b200sgm_engine* h, const Eff& e)
     // diagonals through a halo of kHaloMax - 1 columns, which gives the records kHaloMax - 1 rows to arrive (k_vert's HALO).
     // Needs the agents, strips wider than the halo, and room for the halo rings.  Only for narrow strips (a single frame spread
     // over all SMs): wide strips are bound by their own work, and the halo's extra steps and C reads then cost more than the
-    // hand-over (1280x1024x128 MODE_HH on one lane: 1.115 -> 0.834 ms; four lanes of 16-column strips: 1050 -> 970 frames/s).
+    // hand-over (1280x1024x128 MODE_HH on one lane: 1.115 -> 0.834 ms; four lanes of 16-column strips: 1050 -> 970 frames/s;
+    // 256 disparities on 7-column strips, 1280x720: 0.452 -> 0.640 ms -- those strips are bound by their own work).
     static const bool halo_env = [] { const char* v = getenv("B200SGM_VERT_HALO"); return !v || atoi(v) != 0; }();
     static const int halo_tw = [] { const char* v = getenv("B200SGM_VERT_HALO_TW"); return v ? atoi(v) : 10; }();   // widest strip that gets halo agents
     static const bool plain_agents = getenv("B200SGM_NO_AGENTS") == nullptr && getenv("B200SGM_DEBUG_VERT") == nullptr;

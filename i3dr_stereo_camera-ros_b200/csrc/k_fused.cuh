@@ -701,7 +701,7 @@ __global__ void __launch_bounds__(vert_max_threads(N), kVertCps) k_vert(const ui
         const int prod = producer_role ? (aw - 2) & 1 : 0;
         if (!g.agents || !exchange_on || (side == 0 ? b == 0 : b == n - 1)) return;
         if (HALO > 1 && !DO_WTA && !producer_role) return;      // sweeps without WTA: the edge path warp consumes the producers' ring itself
-        constexpr int BAR_HB = 8;                                // + 2 * side + producer (ids 8 .. 11; 10, 11 = BAR_HALO, unused by HALO > 1 sweeps)
+        constexpr int BAR_HB = 12;                               // + 2 * side + producer: ids 12 .. 15, free in every sweep kind
         uint16_t* vring = (DO_WTA ? haloring + size_t(4) * kHaloRows * (HALO - 1) * Dp + size_t(side) * kXbufGen * Dp
                                   : xringbase + size_t(side) * kXbufGen * Dp) + lane * 2 * N;
         const uint2* rec0 = xrec(xbuf, n, Dp, side, side == 0 ? b - 1 : b + 1, 0, XG) + lane * N;
@@ -1222,7 +1222,7 @@ __global__ void __launch_bounds__(vert_max_threads(N), kVertCps) k_vert(const ui
         if (EDGE && !NO_B) {
             if (consume && EMODE == 2) {
                 // my agent (HALO > 1: the halo producer of row r - 1) has dropped the state of row r - 1 into shared memory
-                named_bar_sync(HALO > 1 ? 8 + 2 * (j == 0 ? 0 : 1) + ((Q & 1) ^ 1) : halo_bar, 64);
+                named_bar_sync(HALO > 1 ? 12 + 2 * (j == 0 ? 0 : 1) + ((Q & 1) ^ 1) : halo_bar, 64);
                 if (active) ld_regs<N>(xin + ((Q + kXbufGen - 1) & (kXbufGen - 1)) * Dp, LtB);
                 else {
 #pragma unroll
