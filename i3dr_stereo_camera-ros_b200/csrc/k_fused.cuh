@@ -115,7 +115,8 @@ inline size_t horiz_ckpt_elems(int W1, int H, int Dp) { return size_t(H) * ((W1 
 inline size_t horiz_smem_per_warp(int Dp) { return size_t(kHRingB + kHRingF + 2 * kHT) * Dp * sizeof(uint16_t); }
 
 // dynamic smem per warp: ringB[kHRingB][Dp] | ringF[kHRingF][Dp] | tiles[2][kHT][Dp]  (uint16)
-// FULL : Dp == 64*N (every lane active, all shared-memory offsets are immediates; enables the unrolled fast loops)
+// FULL : Dp == 64*N (every lane active, all shared-memory offsets are immediates); padded counts run the same unrolled loops
+//        with run-time offsets and their idle lanes predicated off
 // CLAMP: saturate S_h (needed when 2*(Cmax+P2) could exceed 65535; padded cells are masked again before the WTA)
 template <int N, bool FULL, bool CLAMP>
 __global__ void __launch_bounds__(64) k_horiz(const uint16_t* __restrict__ Cvol, uint16_t* __restrict__ Sh,
@@ -181,21 +182,23 @@ __global__ void __launch_bounds__(64) k_horiz(const uint16_t* __restrict__ Cvol,
         int x = W1 - 1;
         for (int i = 0; i < PFB; i++) issueA(x - i);
         for (; (x & 7) != 7 && x >= kHT; x--) stepA(x);
-        if (FULL) {
-            // blocks of 8 columns x = xb+7 .. xb, all offsets immediate; needs the prefetched columns xb-7 .. xb-1 >= kHT
+        {
+            // blocks of 8 columns x = xb+7 .. xb (ring slots are immediates; with FULL every shared-memory offset is); needs the
+            // prefetched columns xb-7 .. xb-1 >= kHT.  Padded disparity counts run the same blocks with their idle lanes
+            // predicated off (they carry kMaxCost through the shuffles).
             const uint16_t* gp = Crow + size_t(x - 7 - PFB) * Dp;      // column (xb - 7): first prefetch target of the block
             uint16_t* ckp = ck + size_t((x - 7) / kHT - 1) * Dp;
             for (; x - 7 - PFB >= kHT; x -= 8, gp -= 8 * Dp, ckp -= Dp) {
 #pragma unroll
                 for (int i = 0; i < 8; i++) {
                     // processing column xb + 7 - i (slot 7 - i); request column xb - i (slot (8 - i) & 7)
-                    cp_async_lane<N>(ringB + ((8 - i) & 7) * Dp, gp + (7 - i) * Dp);
+                    if (active) cp_async_lane<N>(ringB + ((8 - i) & 7) * Dp, gp + (7 - i) * Dp);
                     cp_async_commit();
                     cp_async_wait<PFB>();
-                    ld_regs<N>(ringB + (7 - i) * Dp, Cc);
+                    ldC(ringB + (7 - i) * Dp, Cc);
                     path_step<N>(Cc, Lt, Ln, lc);
                 }
-                st_regs<N>(ckp, Lt);
+                if (active) st_regs<N>(ckp, Lt);
             }
         }
         for (; x >= kHT; x--) stepA(x);
@@ -250,7 +253,7 @@ __global__ void __launch_bounds__(64) k_horiz(const uint16_t* __restrict__ Cvol,
     for (int v = 0; v < PFB; v++) { issueB(v); cp_async_commit(); }
     int it = -8;
     for (; it < 0; it++) iterB(it);
-    if (FULL) {
+    {
         // fast blocks: -> on full tile t = it/8, <- on full tile t+1, prefetches reach into tile t+2 (must be full too)
         for (; it + 24 <= W1; it += 8) {
             const int t = it >> 3;
@@ -262,21 +265,24 @@ __global__ void __launch_bounds__(64) k_horiz(const uint16_t* __restrict__ Cvol,
 #pragma unroll
             for (int i = 0; i < 8; i++) {
                 // <- step v = it+8+i on column it+15-i; its prefetch v+7: i == 0 -> column it+8 (same tile), else it+24-i
-                cp_async_lane<N>(ringB + ((i + 7) & 7) * Dp, gF + (i == 0 ? 8 : 24 - i) * Dp);
-                cp_async_lane<N>(ringF + ((i + 3) & 3) * Dp, gF + (i + 3) * Dp);
+                if (active) {
+                    cp_async_lane<N>(ringB + ((i + 7) & 7) * Dp, gF + (i == 0 ? 8 : 24 - i) * Dp);
+                    cp_async_lane<N>(ringF + ((i + 3) & 3) * Dp, gF + (i + 3) * Dp);
+                }
                 cp_async_commit();
                 cp_async_wait<PFF>();
                 uint32_t Cb[N], Lnb[N], Lb[N];
-                ld_regs<N>(ringB + i * Dp, Cb);
-                ld_regs<N>(ringF + (i & 3) * Dp, Cc);
-                track(Cc);
-                ld_regs<N>(tcur + i * Dp, Lb);
+                ldC(ringB + i * Dp, Cb);
+                ldC(ringF + (i & 3) * Dp, Cc);
+                if (active) { track(Cc); ld_regs<N>(tcur + i * Dp, Lb); }
                 path_step<N>(Cb, Ltb, Lnb, lc);
                 path_step<N>(Cc, Lt, Ln, lc);
-                st_regs<N>(tnxt + (7 - i) * Dp, Lnb);
+                if (active) {
+                    st_regs<N>(tnxt + (7 - i) * Dp, Lnb);
 #pragma unroll
-                for (int j = 0; j < N; j++) Ln[j] = CLAMP ? __vminu2(Ln[j] + Lb[j], kMaxCostX2) : Ln[j] + Lb[j];
-                st_regs<N>(gS + i * Dp, Ln);
+                    for (int j = 0; j < N; j++) Ln[j] = CLAMP ? __vminu2(Ln[j] + Lb[j], kMaxCostX2) : Ln[j] + Lb[j];
+                    st_regs<N>(gS + i * Dp, Ln);
+                }
             }
         }
     }
