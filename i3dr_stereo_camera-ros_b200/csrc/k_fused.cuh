@@ -564,8 +564,10 @@ constexpr int kHaloMax = 4;
 #endif
 constexpr int kVertCps = B200SGM_VERT_CPS;
 // threads per CTA bound the registers per thread: beyond 256 disparities shared memory limits a strip to 13 / 6 / 3 columns, so
-// the bound follows and ptxas gets 88+ registers for the N >= 8 row loops (they spilled at 72)
-constexpr int vert_max_threads(int n) { return kVertCps == 2 ? 448 : (n <= 4 ? B200SGM_VERT_MAXT : (n == 8 ? 704 : (n == 16 ? 384 : 256))); }
+// the bound follows: 640 threads = 96 registers for N = 8 (the row loop spills 238 bytes at 80, 24 at 96).  A 13-column strip
+// (what 480 disparities leave of the shared memory) then has no room for the two agent warps and its edge warps poll the
+// records themselves: 4.97 -> 4.70 ms at 2448x2048x480 all the same; narrower strips keep their agents
+constexpr int vert_max_threads(int n) { return kVertCps == 2 ? 448 : (n <= 4 ? B200SGM_VERT_MAXT : (n == 8 ? 640 : (n == 16 ? 384 : 256))); }
 constexpr int kRowUnroll = 4; // the row loop is unrolled by this: record generation, stage slot, parity are immediates
 __device__ __forceinline__ uint2* xrec(uint2* xbuf, int nstrips, int Dp, int side, int strip, int row, int gens = kXbufGen)
 {
