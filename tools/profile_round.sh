@@ -1,3 +1,5 @@
+# One round's profile set on a B200 (run through gpurun): both bench arms, ncu launch lists of one frame per config, full captures of
+# the volume kernels at c3 and cL.  Post-process here with tools/summarize_launches.py, `ncu -i ... --page details` and tools/ncu_stalls.py.
 set -x
 mkdir -p gpurun_out
 # 1. bench lines (both arms), default flags
